@@ -1,0 +1,195 @@
+/*
+ * dspfront.h -- C ABI of libdspfront.so, the B200 (sm_100a) implementation of
+ * DSP-AudioRecLabs' data-parallel front end and KNN classify step.
+ *
+ * The reference has no FFI of its own: its boundary is the Python module
+ * surface of src/audio_processing.py, src/feature_extraction.py and the 'knn'
+ * branch of src/models.py.  Every entry point below
+ * names the reference interface (file:line under /root/reference) it stands
+ * in for; the ctypes binding a maintainer would add is shown in
+ * INTEGRATION.md and shipped as dsp_audioreclabs_b200/_capi.py.
+ *
+ * Conventions: plain pointers and sizes only; every function returns
+ * DSP_OK (0) or a negative dsp_status and leaves a message for
+ * dsp_last_error(); outputs are caller-allocated; "host" entry points take
+ * host pointers and return only when the outputs are filled; "device" entry
+ * points take device pointers, enqueue on the context's stream and return
+ * immediately (dsp_sync() waits).  There is no CPU implementation behind any
+ * of these calls: without a CUDA device dsp_create() fails.
+ */
+#ifndef DSPFRONT_H_
+#define DSPFRONT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSPFRONT_ABI_VERSION 1
+
+typedef enum {
+  DSP_OK = 0,
+  DSP_ERR_INVALID = -1,   /* bad argument (the Python shims raise ValueError) */
+  DSP_ERR_CUDA = -2,      /* CUDA runtime failure */
+  DSP_ERR_NO_DEVICE = -3, /* no usable sm_100 device */
+  DSP_ERR_UNSUPPORTED = -4,
+  DSP_ERR_NOMEM = -5
+} dsp_status;
+
+/* sample encodings accepted by the front end (what load_wav can produce,
+ * src/audio_processing.py:31-44, plus the float arrays the per-call API takes) */
+typedef enum {
+  DSP_S16 = 0, /* 16-bit PCM, value/32768.0      (:35-38) */
+  DSP_U8 = 1,  /* 8-bit PCM, (value-128)/128.0   (:31-34) */
+  DSP_F32 = 2, /* float samples, used as-is (widened to float64) */
+  DSP_F64 = 3  /* float64 samples, used as-is */
+} dsp_dtype;
+
+/* create_window, src/audio_processing.py:278-296 */
+typedef enum { DSP_WIN_RECTANGULAR = 0, DSP_WIN_HAMMING = 1, DSP_WIN_HANNING = 2 } dsp_window_type;
+
+/* per-utterance status written by the front end */
+#define DSP_UTT_OK 0
+#define DSP_UTT_EMPTY 1      /* no audio after endpoint detection: ValueError at :388-389 */
+#define DSP_UTT_NO_FRAMES 2  /* zero frames: ValueError at feature_extraction.py:27-28 */
+#define DSP_UTT_EXACT 0x100  /* flag bit: result came from the float64 replay kernel */
+
+/* Parameters of process_audio_file (src/audio_processing.py:336-343) with the
+ * config.py names (config.py:35-45). */
+typedef struct {
+  int32_t frame_length;        /* config.FRAME_LENGTH, samples */
+  int32_t frame_shift;         /* config.FRAME_SHIFT, samples */
+  int32_t window;              /* dsp_window_type */
+  int32_t do_endpoint_detection;
+  double energy_high_ratio;    /* config.ENERGY_HIGH_RATIO */
+  double energy_low_ratio;     /* config.ENERGY_LOW_RATIO */
+  double zcr_threshold_ratio;  /* config.ZCR_THRESHOLD_RATIO */
+  int32_t channels;            /* 1, or 2 = interleaved stereo averaged per frame (:43-44) */
+  int32_t force_exact;         /* 1: run every utterance through the float64 replay kernel */
+} dsp_frontend_params;
+
+/* Output pointers of one front-end batch.  Any pointer may be NULL to skip
+ * that output.  Ragged outputs are addressed through the offsets computed by
+ * dsp_frontend_plan(): utterance b owns [feat_offsets[b], feat_offsets[b+1])
+ * of energy/magnitude/zcr (n_frames[b] entries are valid) and
+ * [epd_offsets[b], epd_offsets[b+1]) of epd_energy/epd_zcr. */
+typedef struct {
+  int32_t* start;        /* [B] start_point                 (endpoint_detection :272) */
+  int32_t* end;          /* [B] end_point                   (:273) */
+  int32_t* n_epd_frames; /* [B] len(energy_list)            (:166) */
+  int32_t* n_frames;     /* [B] len(frames)                 (frame_signal :299-333) */
+  int32_t* status;       /* [B] DSP_UTT_* */
+  float* energy;         /* ragged, extract_frame_features 'energy'    (feature_extraction.py:34-37) */
+  float* magnitude;      /* ragged, 'magnitude' */
+  float* zcr;            /* ragged, 'zcr' (integer valued) */
+  float* stats;          /* [B,15] extract_statistical_features (:65-88) */
+  double* epd_energy;    /* ragged, energy_list of endpoint_detection (:183) */
+  float* epd_zcr;        /* ragged, zcr_list (:184) */
+} dsp_frontend_outputs;
+
+typedef struct dsp_context dsp_context;
+
+/* ---- context ----------------------------------------------------------- */
+int dsp_abi_version(void);
+const char* dsp_last_error(void);
+/* device: CUDA ordinal.  Fails with DSP_ERR_NO_DEVICE when there is no GPU. */
+int dsp_create(int device, dsp_context** out);
+int dsp_destroy(dsp_context* ctx);
+/* Use an existing CUDA stream (e.g. torch's) for all device entry points; 0 restores the context's own. */
+int dsp_set_stream(dsp_context* ctx, void* cuda_stream);
+int dsp_sync(dsp_context* ctx);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+int64_t dsp_launch_count(dsp_context* ctx);
+int dsp_device_sm_count(dsp_context* ctx);
+
+/* ---- front end --------------------------------------------------------- */
+/* Host arithmetic only.  offsets[B+1] are sample offsets of a packed ragged
+ * batch (in samples of one channel times `channels`, i.e. element offsets).
+ * Fills feat_offsets[B+1] / epd_offsets[B+1] (capacities: frame counts of the
+ * untrimmed utterances) and returns the longest utterance. */
+int dsp_frontend_plan(const int64_t* offsets, int64_t n_utts, const dsp_frontend_params* p,
+                      int64_t* feat_offsets, int64_t* epd_offsets, int64_t* max_len);
+
+/* create_window (src/audio_processing.py:278-296): float64 window of `length`. */
+int dsp_window(int window_type, int32_t length, double* out);
+
+/* process_audio_file minus the WAV decode + extract_features_from_frames
+ * ('statistical'), batched (src/audio_processing.py:364-394,
+ * src/feature_extraction.py:91-112).  All pointers are DEVICE pointers. */
+int dsp_frontend_batch_device(dsp_context* ctx, const void* samples, int dtype,
+                              const int64_t* offsets, const int64_t* feat_offsets,
+                              const int64_t* epd_offsets, int64_t n_utts, int64_t max_len,
+                              const dsp_frontend_params* p, const dsp_frontend_outputs* out);
+
+/* Same with HOST pointers: stages through pinned memory in chunks, overlapping
+ * upload, kernels and download.  This is the call the Python shims make. */
+int dsp_frontend_batch_host(dsp_context* ctx, const void* samples, int dtype,
+                            const int64_t* offsets, int64_t n_utts,
+                            const dsp_frontend_params* p, const dsp_frontend_outputs* out);
+
+/* preprocess = remove_dc + normalize_audio (src/audio_processing.py:49-90) for one
+ * float64 signal; mode 0 = remove_dc only, 1 = normalize only, 2 = both.  Host pointers. */
+int dsp_preprocess_host(dsp_context* ctx, const double* x, int64_t n, int mode, double* out);
+
+/* endpoint_detection on an already pre-processed float64 signal
+ * (src/audio_processing.py:135-275).  Host pointers; energy_list/zcr_list hold
+ * (n-fl)/fs+1 entries when n >= fl. */
+int dsp_endpoint_detection_host(dsp_context* ctx, const double* x, int64_t n,
+                                const dsp_frontend_params* p, int32_t* start, int32_t* end,
+                                int32_t* n_epd_frames, double* energy_list, double* zcr_list);
+
+/* frame_signal (src/audio_processing.py:299-333): frames_out is [n_frames, frame_length]
+ * float64 with n_frames from dsp_frame_count().  Host pointers. */
+int64_t dsp_frame_count(int64_t n, int32_t frame_length, int32_t frame_shift);
+int dsp_frame_signal_host(dsp_context* ctx, const double* x, int64_t n, int32_t frame_length,
+                          int32_t frame_shift, int window_type, double* frames_out);
+
+/* extract_frame_features + compute_statistics on an arbitrary float64 frame matrix
+ * (src/feature_extraction.py:12-88; with n_frames == 1 these are
+ * compute_short_time_energy/magnitude/zero_crossing_rate, audio_processing.py:93-132).
+ * energy/magnitude/zcr: [n_frames] float64, stats: [15] float64 (may be NULL). */
+int dsp_frame_features_host(dsp_context* ctx, const double* frames, int64_t n_frames,
+                            int32_t frame_length, double* energy, double* magnitude, double* zcr,
+                            double* stats);
+
+/* compute_statistics (src/feature_extraction.py:46-62) of one float64 sequence -> 5 values. */
+int dsp_sequence_stats_host(dsp_context* ctx, const double* seq, int64_t n, double* out5);
+
+/* normalize_features (src/feature_extraction.py:157-181).  fit != 0 computes mean/std
+ * (population) over axis 0 into mean/std first; std == 0 is replaced by 1 when applying
+ * (the returned std keeps the replacement, as the reference does). */
+int dsp_zscore_host(dsp_context* ctx, const double* x, int64_t n, int32_t d, int fit, double* mean,
+                    double* std, double* out);
+int dsp_zscore_device(dsp_context* ctx, const double* x, int64_t n, int32_t d, int fit, double* mean,
+                      double* std, double* out);
+
+/* ---- KNN classify (src/models.py:33-35,52-58 -> sklearn KNeighborsClassifier) ---- */
+typedef struct dsp_knn dsp_knn;
+/* fit: keeps a device copy of train[n,d] (float64, row major) and labels[n].
+ * index_base is added to local row numbers in every reported neighbour index
+ * (row-sharded multi-GPU: the shard's first global row). */
+int dsp_knn_fit_host(dsp_context* ctx, const double* train, const int32_t* labels, int64_t n,
+                     int32_t d, int32_t k, int64_t index_base, dsp_knn** out);
+int dsp_knn_fit_device(dsp_context* ctx, const double* train, const int32_t* labels, int64_t n,
+                       int32_t d, int32_t k, int64_t index_base, dsp_knn** out);
+int dsp_knn_free(dsp_knn* knn);
+/* k nearest train rows of each query by exact float64 squared Euclidean distance, ties to
+ * the lower index: nbr_idx[m,k] (global), nbr_sqdist[m,k], nbr_label[m,k]; any may be NULL. */
+int dsp_knn_topk_host(dsp_knn* knn, const double* queries, int64_t m, int64_t* nbr_idx,
+                      double* nbr_sqdist, int32_t* nbr_label);
+int dsp_knn_topk_device(dsp_knn* knn, const double* queries, int64_t m, int64_t* nbr_idx,
+                        double* nbr_sqdist, int32_t* nbr_label);
+/* predict = topk + majority vote, vote ties to the smallest label. */
+int dsp_knn_predict_host(dsp_knn* knn, const double* queries, int64_t m, int32_t* labels_out);
+int dsp_knn_predict_device(dsp_knn* knn, const double* queries, int64_t m, int32_t* labels_out);
+/* Merge R candidate lists (as gathered from R row shards, layout [R,m,k]) into the global
+ * top-k and vote.  Device pointers. */
+int dsp_knn_merge_vote_device(dsp_context* ctx, const double* cand_sqdist, const int64_t* cand_idx,
+                              const int32_t* cand_label, int32_t n_lists, int64_t m, int32_t k,
+                              int32_t* labels_out, int64_t* nbr_idx_out, double* nbr_sqdist_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSPFRONT_H_ */
