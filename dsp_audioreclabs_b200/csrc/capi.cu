@@ -1,0 +1,807 @@
+// C ABI of libdspfront.so (include/dspfront.h): context, planning, host staging pipeline and
+// the launch logic that routes a batch to the int16 fast kernel (frontend_pcm.cu) with the
+// float64 replay kernel (frontend_exact.cu) behind it.  No CPU implementation lives here:
+// host code only plans, copies and launches.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "knn.cuh"
+#include "misc.cuh"
+
+using namespace dsp;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(expr)                                                                         \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+      return fail(DSP_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                  __FILE__, __LINE__);                                                   \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMallocHost(&p, bytes + 256);
+    if (e == cudaSuccess) cap = bytes + 256;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+constexpr size_t kMaxSmemPerCta = 227 * 1024;
+constexpr int64_t kFastMaxLen = 1 << 20;          // exact-integer bounds of the fast kernel
+constexpr size_t kHostChunkBytes = 96u << 20;     // samples per staged chunk of the host pipeline
+
+size_t dtype_size(int dtype) {
+  switch (dtype) {
+    case DSP_S16: return 2;
+    case DSP_U8: return 1;
+    case DSP_F32: return 4;
+    case DSP_F64: return 8;
+    default: return 0;
+  }
+}
+
+struct Slot {
+  DevBuf samples, off, foff, eoff, ints, stats, feat, epd_e, epd_z;
+  PinBuf h_off;
+  cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;
+  bool busy = false;
+};
+
+}  // namespace
+
+struct dsp_context {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t own = nullptr, stream = nullptr, s_in = nullptr, s_out = nullptr;
+  int64_t launches = 0;
+  int win_type = -1, win_len = -1;
+  DevBuf win64, win32;
+  DevBuf counters;   // [0] work counter (u32)  [1] flag count (i32)
+  DevBuf flag_list, zbuf, seqbuf;
+  size_t occ_smem = 0;
+  int occ = 0;
+  Slot slot[2];
+  DevBuf tmp[10];
+};
+
+struct dsp_knn {
+  dsp_context* ctx = nullptr;
+  int64_t n = 0, index_base = 0;
+  int d = 0, dp = 0, k = 0;
+  float tnorm_max = 0.f;
+  DevBuf train64, train32, labels, tnorm, cand_idx, cand_worst, qnorm, redo_list, redo_count, nbr_label, q, o_idx, o_dist, o_lab;
+};
+
+namespace {
+
+int host_window(int type, int n, std::vector<double>& w) {
+  if (n < 0) return fail(DSP_ERR_INVALID, "window length must be >= 0");
+  w.assign((size_t)n, 1.0);
+  if (type == DSP_WIN_RECTANGULAR) return DSP_OK;
+  if (type != DSP_WIN_HAMMING && type != DSP_WIN_HANNING)
+    return fail(DSP_ERR_INVALID, "unsupported window type: %d", type);   // audio_processing.py:296
+  if (n <= 1) return DSP_OK;  // np.hamming(1) == np.hanning(1) == [1.]
+  const double a = type == DSP_WIN_HAMMING ? 0.54 : 0.5, b = type == DSP_WIN_HAMMING ? 0.46 : 0.5;
+  for (int i = 0; i < n; ++i) {
+    const double m = (double)(1 - n + 2 * i);   // np: n = arange(1-M, M, 2)
+    w[(size_t)i] = a + b * std::cos(M_PI * m / (double)(n - 1));
+  }
+  return DSP_OK;
+}
+
+int ensure_window(dsp_context* c, int type, int fl) {
+  if (c->win_type == type && c->win_len == fl) return DSP_OK;
+  std::vector<double> w;
+  int rc = host_window(type, fl, w);
+  if (rc) return rc;
+  std::vector<float> wf(w.begin(), w.end());
+  CU(c->win64.ensure(sizeof(double) * (size_t)fl + 16));
+  CU(c->win32.ensure(sizeof(float) * (size_t)fl + 16));
+  // the previous window may still be in use by kernels on the stream
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpy(c->win64.p, w.data(), sizeof(double) * (size_t)fl, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->win32.p, wf.data(), sizeof(float) * (size_t)fl, cudaMemcpyHostToDevice));
+  c->win_type = type; c->win_len = fl;
+  return DSP_OK;
+}
+
+int check_params(const dsp_frontend_params* p) {
+  if (!p) return fail(DSP_ERR_INVALID, "params is NULL");
+  if (p->frame_length < 1 || p->frame_shift < 1) return fail(DSP_ERR_INVALID, "frame_length and frame_shift must be >= 1");
+  if (p->window < 0 || p->window > 2) return fail(DSP_ERR_INVALID, "unsupported window type: %d", p->window);
+  if (p->channels != 1 && p->channels != 2) return fail(DSP_ERR_INVALID, "channels must be 1 or 2");
+  return DSP_OK;
+}
+
+struct ExactExtras {
+  int pre_mode = 3, do_features = 1;
+  double* pre_out = nullptr;
+  double* frames_out = nullptr;
+  double* epd_zcr_f64 = nullptr;
+  double* feat_f64[3] = {nullptr, nullptr, nullptr};
+  double* stats_f64 = nullptr;
+};
+
+int launch_exact(dsp_context* c, const void* samples, int dtype, const int64_t* offsets,
+                 const int64_t* feat_offsets, const int64_t* epd_offsets, const int32_t* list,
+                 const int32_t* list_count, int64_t n_items, int64_t max_len, const dsp_frontend_params* p,
+                 const dsp_frontend_outputs* out, const ExactExtras& ex, int grid) {
+  if (grid < 1) grid = 1;
+  const int64_t cap_frames = std::max<int64_t>(frame_count_host_device(max_len, p->frame_length, p->frame_shift), 1);
+  CU(c->zbuf.ensure(sizeof(double) * (size_t)grid * (size_t)std::max<int64_t>(max_len, 1)));
+  CU(c->seqbuf.ensure(sizeof(double) * (size_t)grid * 5 * (size_t)cap_frames));
+  ExactArgs a{};
+  a.samples = samples; a.dtype = dtype; a.channels = p->channels;
+  a.offsets = offsets; a.feat_offsets = feat_offsets; a.epd_offsets = epd_offsets;
+  a.list = list; a.list_count = list_count; a.n_items = n_items;
+  a.fl = p->frame_length; a.fs = p->frame_shift;
+  a.do_epd = p->do_endpoint_detection; a.pre_mode = ex.pre_mode; a.do_features = ex.do_features;
+  a.hr = p->energy_high_ratio; a.lr = p->energy_low_ratio; a.zr = p->zcr_threshold_ratio;
+  a.win = c->win64.as<double>();
+  a.zbuf = c->zbuf.as<double>(); a.zbuf_stride = std::max<int64_t>(max_len, 1);
+  a.seqbuf = c->seqbuf.as<double>(); a.seq_cap = cap_frames;
+  if (out) a.out = *out;
+  a.pre_out = ex.pre_out; a.frames_out = ex.frames_out; a.epd_zcr_f64 = ex.epd_zcr_f64;
+  a.feat_f64[0] = ex.feat_f64[0]; a.feat_f64[1] = ex.feat_f64[1]; a.feat_f64[2] = ex.feat_f64[2];
+  a.stats_f64 = ex.stats_f64;
+  frontend_exact_kernel<<<grid, kExactThreads, 0, c->stream>>>(a);
+  c->launches++;
+  CU(cudaGetLastError());
+  return DSP_OK;
+}
+
+int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_t* offsets,
+                    const int64_t* feat_offsets, const int64_t* epd_offsets, int64_t B, int64_t max_len,
+                    const dsp_frontend_params* p, const dsp_frontend_outputs* out) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  if (!dtype_size(dtype)) return fail(DSP_ERR_INVALID, "unsupported sample dtype %d", dtype);
+  if (!out) return fail(DSP_ERR_INVALID, "outputs is NULL");
+  if (B < 0 || max_len < 0) return fail(DSP_ERR_INVALID, "negative batch size or length");
+  if (B == 0) return DSP_OK;
+  if (B > INT32_MAX / 2) return fail(DSP_ERR_UNSUPPORTED, "more than 2^30 utterances in one call");
+  if (p->channels == 2 && (dtype == DSP_F32 || dtype == DSP_F64))
+    return fail(DSP_ERR_INVALID, "stereo input is only defined for PCM (load_wav)");
+  if ((out->energy || out->magnitude || out->zcr) && !feat_offsets) return fail(DSP_ERR_INVALID, "feat_offsets is NULL");
+  if ((out->epd_energy || out->epd_zcr) && !epd_offsets) return fail(DSP_ERR_INVALID, "epd_offsets is NULL");
+  rc = ensure_window(c, p->window, p->frame_length);
+  if (rc) return rc;
+  const int fl = p->frame_length, fs = p->frame_shift;
+  const int64_t cap_frames64 = std::max<int64_t>(frame_count_host_device(max_len, fl, fs), 1);
+
+  bool fast = dtype == DSP_S16 && p->channels == 1 && !p->force_exact && max_len <= kFastMaxLen &&
+              feat_offsets;
+  size_t smem = 0;
+  int cap_samples = 0;
+  if (fast) {
+    cap_samples = (int)((std::max<int64_t>(max_len, 1) + 63) / 64 * 64);
+    smem = pcm_kernel_smem_bytes(cap_samples, (int)cap_frames64, fl);
+    if (smem > kMaxSmemPerCta) fast = false;
+  }
+  if (!fast) {
+    const int grid = (int)std::min<int64_t>(B, (int64_t)c->sm_count * 4);
+    ExactExtras ex;
+    return launch_exact(c, samples, dtype, offsets, feat_offsets, epd_offsets, nullptr, nullptr, B, max_len,
+                        p, out, ex, grid);
+  }
+  if (c->occ_smem != smem) {
+    c->occ = pcm_kernel_max_ctas_per_sm(smem);
+    c->occ_smem = smem;
+    if (c->occ < 1) return fail(DSP_ERR_CUDA, "fast kernel does not fit: %zu bytes of shared memory", smem);
+  }
+  CU(c->counters.ensure(64));
+  CU(c->flag_list.ensure(sizeof(int32_t) * (size_t)B));
+  CU(cudaMemsetAsync(c->counters.p, 0, 64, c->stream));
+  PcmArgs a{};
+  a.samples = reinterpret_cast<const int16_t*>(samples);
+  a.offsets = offsets; a.feat_offsets = feat_offsets; a.epd_offsets = epd_offsets;
+  a.n_utts = B; a.fl = fl; a.fs = fs; a.window = p->window; a.do_epd = p->do_endpoint_detection;
+  a.hr = p->energy_high_ratio; a.lr = p->energy_low_ratio; a.zr = p->zcr_threshold_ratio;
+  a.win_f32 = c->win32.as<float>();
+  a.cap_samples = cap_samples; a.cap_frames = (int)cap_frames64;
+  a.work_counter = c->counters.as<unsigned int>();
+  a.flag_count = c->counters.as<int32_t>() + 1;
+  a.flag_list = c->flag_list.as<int32_t>();
+  a.out = *out;
+  const int grid = (int)std::min<int64_t>(B, (int64_t)c->sm_count * c->occ);
+  CU(launch_frontend_pcm(a, grid, smem, c->stream));
+  c->launches++;
+  // float64 replay of the utterances whose threshold margins could not be certified
+  ExactExtras ex;
+  const int xgrid = (int)std::min<int64_t>(B, (int64_t)c->sm_count);
+  return launch_exact(c, samples, dtype, offsets, feat_offsets, epd_offsets, a.flag_list, a.flag_count, 0,
+                      max_len, p, out, ex, xgrid);
+}
+
+// small helper for the single-signal host entry points
+struct OneShot {
+  dsp_context* c;
+  int n_tmp = 0;
+  explicit OneShot(dsp_context* ctx) : c(ctx) {}
+  template <class T> T* dev(size_t count) {
+    DevBuf& b = c->tmp[n_tmp++];
+    if (b.ensure(sizeof(T) * std::max<size_t>(count, 1)) != cudaSuccess) return nullptr;
+    return b.as<T>();
+  }
+};
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int dsp_abi_version(void) { return DSPFRONT_ABI_VERSION; }
+const char* dsp_last_error(void) { return g_err.c_str(); }
+
+int dsp_create(int device, dsp_context** out) {
+  if (!out) return fail(DSP_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return fail(DSP_ERR_NO_DEVICE, "no CUDA device: libdspfront has no CPU path");
+  }
+  if (device < 0 || device >= count) return fail(DSP_ERR_INVALID, "device %d out of range (%d visible)", device, count);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(DSP_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  dsp_context* c = new dsp_context();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&c->own, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+  c->stream = c->own;
+  for (auto& s : c->slot) {
+    CU(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
+  }
+  *out = c;
+  return DSP_OK;
+}
+
+int dsp_destroy(dsp_context* c) {
+  if (!c) return DSP_OK;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (auto& s : c->slot) {
+    s.samples.release(); s.off.release(); s.foff.release(); s.eoff.release(); s.ints.release();
+    s.stats.release(); s.feat.release(); s.epd_e.release(); s.epd_z.release(); s.h_off.release();
+    if (s.ev_in) cudaEventDestroy(s.ev_in);
+    if (s.ev_k) cudaEventDestroy(s.ev_k);
+    if (s.ev_out) cudaEventDestroy(s.ev_out);
+  }
+  for (auto& b : c->tmp) b.release();
+  c->win64.release(); c->win32.release(); c->counters.release(); c->flag_list.release();
+  c->zbuf.release(); c->seqbuf.release();
+  if (c->own) cudaStreamDestroy(c->own);
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
+  delete c;
+  return DSP_OK;
+}
+
+int dsp_set_stream(dsp_context* c, void* cuda_stream) {
+  if (!c) return fail(DSP_ERR_INVALID, "context is NULL");
+  c->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  return DSP_OK;
+}
+
+int dsp_use_own_stream(dsp_context* c) {
+  if (!c) return fail(DSP_ERR_INVALID, "context is NULL");
+  c->stream = c->own;
+  return DSP_OK;
+}
+
+int dsp_sync(dsp_context* c) {
+  if (!c) return fail(DSP_ERR_INVALID, "context is NULL");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  return DSP_OK;
+}
+
+int64_t dsp_launch_count(dsp_context* c) { return c ? c->launches : 0; }
+int dsp_device_sm_count(dsp_context* c) { return c ? c->sm_count : 0; }
+
+int64_t dsp_frame_count(int64_t n, int32_t fl, int32_t fs) {
+  if (fl < 1 || fs < 1) return 0;
+  return frame_count_host_device(n, fl, fs);
+}
+
+int dsp_frontend_plan(const int64_t* offsets, int64_t B, const dsp_frontend_params* p, int64_t* feat_offsets,
+                      int64_t* epd_offsets, int64_t* max_len) {
+  int rc = check_params(p);
+  if (rc) return rc;
+  if (!offsets || B < 0) return fail(DSP_ERR_INVALID, "bad offsets");
+  int64_t fo = 0, eo = 0, mx = 0;
+  for (int64_t b = 0; b < B; ++b) {
+    const int64_t len = offsets[b + 1] - offsets[b];
+    if (len < 0 || len % p->channels) return fail(DSP_ERR_INVALID, "offsets must be non-decreasing and a multiple of channels (utterance %lld)", (long long)b);
+    const int64_t n = len / p->channels;
+    if (n > INT32_MAX / 4) return fail(DSP_ERR_UNSUPPORTED, "utterance %lld is too long", (long long)b);
+    if (feat_offsets) feat_offsets[b] = fo;
+    if (epd_offsets) epd_offsets[b] = eo;
+    fo += frame_count_host_device(n, p->frame_length, p->frame_shift);
+    eo += (p->do_endpoint_detection && n >= p->frame_length) ? (n - p->frame_length) / p->frame_shift + 1 : 0;
+    mx = std::max(mx, n);
+  }
+  if (feat_offsets) feat_offsets[B] = fo;
+  if (epd_offsets) epd_offsets[B] = eo;
+  if (max_len) *max_len = mx;
+  return DSP_OK;
+}
+
+int dsp_window(int window_type, int32_t length, double* out) {
+  std::vector<double> w;
+  int rc = host_window(window_type, length, w);
+  if (rc) return rc;
+  if (length > 0 && !out) return fail(DSP_ERR_INVALID, "out is NULL");
+  std::memcpy(out, w.data(), sizeof(double) * w.size());
+  return DSP_OK;
+}
+
+int dsp_frontend_batch_device(dsp_context* c, const void* samples, int dtype, const int64_t* offsets,
+                              const int64_t* feat_offsets, const int64_t* epd_offsets, int64_t n_utts,
+                              int64_t max_len, const dsp_frontend_params* p, const dsp_frontend_outputs* out) {
+  if (!c) return fail(DSP_ERR_INVALID, "context is NULL");
+  CU(cudaSetDevice(c->device));
+  return frontend_device(c, samples, dtype, offsets, feat_offsets, epd_offsets, n_utts, max_len, p, out);
+}
+
+int dsp_frontend_batch_host(dsp_context* c, const void* samples, int dtype, const int64_t* offsets,
+                            int64_t B, const dsp_frontend_params* p, const dsp_frontend_outputs* out) {
+  if (!c) return fail(DSP_ERR_INVALID, "context is NULL");
+  int rc = check_params(p);
+  if (rc) return rc;
+  const size_t esz = dtype_size(dtype);
+  if (!esz) return fail(DSP_ERR_INVALID, "unsupported sample dtype %d", dtype);
+  if (!out || !offsets) return fail(DSP_ERR_INVALID, "NULL argument");
+  if (B == 0) return DSP_OK;
+  CU(cudaSetDevice(c->device));
+  std::vector<int64_t> foff((size_t)B + 1), eoff((size_t)B + 1);
+  int64_t max_len_all = 0;
+  rc = dsp_frontend_plan(offsets, B, p, foff.data(), eoff.data(), &max_len_all);
+  if (rc) return rc;
+  rc = ensure_window(c, p->window, p->frame_length);
+  if (rc) return rc;
+
+  const unsigned char* src = reinterpret_cast<const unsigned char*>(samples);
+  int64_t b0 = 0;
+  int chunk = 0;
+  while (b0 < B) {
+    // chunk = as many utterances as fit the staging budget (at least one)
+    int64_t b1 = b0 + 1;
+    while (b1 < B && (size_t)(offsets[b1 + 1] - offsets[b0]) * esz <= kHostChunkBytes) ++b1;
+    const int64_t bc = b1 - b0;
+    Slot& s = c->slot[chunk & 1];
+    if (s.busy) { CU(cudaEventSynchronize(s.ev_out)); s.busy = false; }
+    const int64_t e0 = offsets[b0], e1 = offsets[b1];
+    const int64_t f0 = foff[(size_t)b0], f1 = foff[(size_t)b1], g0 = eoff[(size_t)b0], g1 = eoff[(size_t)b1];
+    CU(s.h_off.ensure(sizeof(int64_t) * 3 * (size_t)(bc + 1)));
+    int64_t* h = s.h_off.as<int64_t>();
+    int64_t chunk_max = 0;
+    for (int64_t i = 0; i <= bc; ++i) {
+      h[i] = offsets[b0 + i] - e0;
+      h[(bc + 1) + i] = foff[(size_t)(b0 + i)] - f0;
+      h[2 * (bc + 1) + i] = eoff[(size_t)(b0 + i)] - g0;
+      if (i < bc) chunk_max = std::max(chunk_max, (offsets[b0 + i + 1] - offsets[b0 + i]) / p->channels);
+    }
+    CU(s.samples.ensure((size_t)(e1 - e0) * esz + 64));
+    CU(s.off.ensure(sizeof(int64_t) * 3 * (size_t)(bc + 1)));
+    CU(s.ints.ensure(sizeof(int32_t) * 5 * (size_t)bc));
+    CU(s.stats.ensure(sizeof(float) * kStats * (size_t)bc));
+    CU(s.feat.ensure(sizeof(float) * 3 * (size_t)std::max<int64_t>(f1 - f0, 1)));
+    CU(s.epd_e.ensure(sizeof(double) * (size_t)std::max<int64_t>(g1 - g0, 1)));
+    CU(s.epd_z.ensure(sizeof(float) * (size_t)std::max<int64_t>(g1 - g0, 1)));
+    // upload
+    CU(cudaMemcpyAsync(s.samples.p, src + (size_t)e0 * esz, (size_t)(e1 - e0) * esz, cudaMemcpyHostToDevice, c->s_in));
+    CU(cudaMemcpyAsync(s.off.p, h, sizeof(int64_t) * 3 * (size_t)(bc + 1), cudaMemcpyHostToDevice, c->s_in));
+    CU(cudaEventRecord(s.ev_in, c->s_in));
+    CU(cudaStreamWaitEvent(c->stream, s.ev_in, 0));
+    // kernels
+    int32_t* di = s.ints.as<int32_t>();
+    float* df = s.feat.as<float>();
+    const int64_t fn = std::max<int64_t>(f1 - f0, 1);
+    dsp_frontend_outputs o{};
+    o.start = di; o.end = di + bc; o.n_epd_frames = di + 2 * bc; o.n_frames = di + 3 * bc; o.status = di + 4 * bc;
+    o.energy = df; o.magnitude = df + fn; o.zcr = df + 2 * fn;
+    o.stats = s.stats.as<float>();
+    o.epd_energy = out->epd_energy ? s.epd_e.as<double>() : nullptr;
+    o.epd_zcr = out->epd_zcr ? s.epd_z.as<float>() : nullptr;
+    const int64_t* doff = s.off.as<int64_t>();
+    rc = frontend_device(c, s.samples.p, dtype, doff, doff + (bc + 1), doff + 2 * (bc + 1), bc, chunk_max, p, &o);
+    if (rc) return rc;
+    CU(cudaEventRecord(s.ev_k, c->stream));
+    CU(cudaStreamWaitEvent(c->s_out, s.ev_k, 0));
+    // download straight into the caller's arrays
+    auto d2h = [&](void* dst, const void* srcp, size_t bytes) -> cudaError_t {
+      if (!dst || bytes == 0) return cudaSuccess;
+      return cudaMemcpyAsync(dst, srcp, bytes, cudaMemcpyDeviceToHost, c->s_out);
+    };
+    CU(d2h(out->start ? out->start + b0 : nullptr, o.start, sizeof(int32_t) * (size_t)bc));
+    CU(d2h(out->end ? out->end + b0 : nullptr, o.end, sizeof(int32_t) * (size_t)bc));
+    CU(d2h(out->n_epd_frames ? out->n_epd_frames + b0 : nullptr, o.n_epd_frames, sizeof(int32_t) * (size_t)bc));
+    CU(d2h(out->n_frames ? out->n_frames + b0 : nullptr, o.n_frames, sizeof(int32_t) * (size_t)bc));
+    CU(d2h(out->status ? out->status + b0 : nullptr, o.status, sizeof(int32_t) * (size_t)bc));
+    CU(d2h(out->stats ? out->stats + b0 * kStats : nullptr, o.stats, sizeof(float) * kStats * (size_t)bc));
+    CU(d2h(out->energy ? out->energy + f0 : nullptr, o.energy, sizeof(float) * (size_t)(f1 - f0)));
+    CU(d2h(out->magnitude ? out->magnitude + f0 : nullptr, o.magnitude, sizeof(float) * (size_t)(f1 - f0)));
+    CU(d2h(out->zcr ? out->zcr + f0 : nullptr, o.zcr, sizeof(float) * (size_t)(f1 - f0)));
+    CU(d2h(out->epd_energy ? out->epd_energy + g0 : nullptr, o.epd_energy, sizeof(double) * (size_t)(g1 - g0)));
+    CU(d2h(out->epd_zcr ? out->epd_zcr + g0 : nullptr, o.epd_zcr, sizeof(float) * (size_t)(g1 - g0)));
+    CU(cudaEventRecord(s.ev_out, c->s_out));
+    s.busy = true;
+    b0 = b1;
+    ++chunk;
+  }
+  for (auto& s : c->slot)
+    if (s.busy) { CU(cudaEventSynchronize(s.ev_out)); s.busy = false; }
+  return DSP_OK;
+}
+
+// ---- single-signal entry points (the per-call Python surface) -------------------------------
+static int one_signal(dsp_context* c, const double* x, int64_t n, const dsp_frontend_params* p,
+                      const ExactExtras& ex_in, dsp_frontend_outputs* dout, OneShot& os) {
+  int rc = ensure_window(c, p->window, p->frame_length);
+  if (rc) return rc;
+  double* dx = os.dev<double>((size_t)n);
+  int64_t* doff = os.dev<int64_t>(2);
+  if (!dx || !doff) return fail(DSP_ERR_NOMEM, "device allocation failed");
+  const int64_t hoff[2] = {0, n};
+  CU(cudaMemcpyAsync(dx, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(doff, hoff, sizeof hoff, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // hoff is a stack array
+  return launch_exact(c, dx, DSP_F64, doff, nullptr, nullptr, nullptr, nullptr, 1, n, p, dout, ex_in, 1);
+}
+
+int dsp_preprocess_host(dsp_context* c, const double* x, int64_t n, int mode, double* out) {
+  if (!c || (!x && n) || (!out && n) || n < 0 || mode < 0 || mode > 2) return fail(DSP_ERR_INVALID, "bad argument");
+  if (n == 0) return fail(DSP_ERR_INVALID, "zero-size array to reduction operation maximum which has no identity");
+  CU(cudaSetDevice(c->device));
+  dsp_frontend_params p{};
+  p.frame_length = 1; p.frame_shift = 1; p.window = 0; p.channels = 1;
+  OneShot os(c);
+  double* dout = os.dev<double>((size_t)n);
+  if (!dout) return fail(DSP_ERR_NOMEM, "device allocation failed");
+  ExactExtras ex;
+  ex.pre_mode = mode == 0 ? 1 : (mode == 1 ? 2 : 3);
+  ex.do_features = 0;
+  ex.pre_out = dout;
+  dsp_frontend_outputs o{};
+  int rc = one_signal(c, x, n, &p, ex, &o, os);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(out, dout, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return DSP_OK;
+}
+
+int dsp_endpoint_detection_host(dsp_context* c, const double* x, int64_t n, const dsp_frontend_params* p,
+                                int32_t* start, int32_t* end, int32_t* n_epd_frames, double* energy_list,
+                                double* zcr_list) {
+  if (!c || (!x && n) || n < 0) return fail(DSP_ERR_INVALID, "bad argument");
+  int rc = check_params(p);
+  if (rc) return rc;
+  CU(cudaSetDevice(c->device));
+  dsp_frontend_params q = *p;
+  q.do_endpoint_detection = 1; q.channels = 1; q.window = DSP_WIN_RECTANGULAR;
+  const int64_t f1 = n >= q.frame_length ? (n - q.frame_length) / q.frame_shift + 1 : 0;
+  OneShot os(c);
+  int32_t* di = os.dev<int32_t>(8);
+  double* de = os.dev<double>((size_t)f1);
+  double* dz = os.dev<double>((size_t)f1);
+  if (!di || !de || !dz) return fail(DSP_ERR_NOMEM, "device allocation failed");
+  ExactExtras ex;
+  ex.pre_mode = 0; ex.do_features = 0; ex.epd_zcr_f64 = dz;
+  dsp_frontend_outputs o{};
+  o.start = di; o.end = di + 1; o.n_epd_frames = di + 2; o.epd_energy = de;
+  // one_signal passes epd_offsets == NULL -> offset 0
+  rc = one_signal(c, x, n, &q, ex, &o, os);
+  if (rc) return rc;
+  int32_t hi[3];
+  CU(cudaMemcpyAsync(hi, di, sizeof hi, cudaMemcpyDeviceToHost, c->stream));
+  if (energy_list && f1) CU(cudaMemcpyAsync(energy_list, de, sizeof(double) * (size_t)f1, cudaMemcpyDeviceToHost, c->stream));
+  if (zcr_list && f1) CU(cudaMemcpyAsync(zcr_list, dz, sizeof(double) * (size_t)f1, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  if (start) *start = hi[0];
+  if (end) *end = hi[1];
+  if (n_epd_frames) *n_epd_frames = hi[2];
+  return DSP_OK;
+}
+
+int dsp_frame_signal_host(dsp_context* c, const double* x, int64_t n, int32_t fl, int32_t fs, int window_type,
+                          double* frames_out) {
+  if (!c || (!x && n) || n < 0) return fail(DSP_ERR_INVALID, "bad argument");
+  dsp_frontend_params p{};
+  p.frame_length = fl; p.frame_shift = fs; p.window = window_type; p.channels = 1;
+  int rc = check_params(&p);
+  if (rc) return rc;
+  const int64_t nf = frame_count_host_device(n, fl, fs);
+  if (nf == 0) return DSP_OK;
+  if (!frames_out) return fail(DSP_ERR_INVALID, "frames_out is NULL");
+  CU(cudaSetDevice(c->device));
+  OneShot os(c);
+  double* dfr = os.dev<double>((size_t)nf * (size_t)fl);
+  if (!dfr) return fail(DSP_ERR_NOMEM, "device allocation failed");
+  ExactExtras ex;
+  ex.pre_mode = 0; ex.do_features = 1; ex.frames_out = dfr;
+  dsp_frontend_outputs o{};
+  rc = one_signal(c, x, n, &p, ex, &o, os);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(frames_out, dfr, sizeof(double) * (size_t)nf * (size_t)fl, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return DSP_OK;
+}
+
+int dsp_frame_features_host(dsp_context* c, const double* frames, int64_t n_frames, int32_t fl, double* energy,
+                            double* magnitude, double* zcr, double* stats) {
+  if (!c || n_frames < 0 || fl < 0) return fail(DSP_ERR_INVALID, "bad argument");
+  if (n_frames == 0) return fail(DSP_ERR_INVALID, "No frames provided for feature extraction.");  // feature_extraction.py:27-28
+  if (n_frames > INT32_MAX) return fail(DSP_ERR_UNSUPPORTED, "too many frames");
+  CU(cudaSetDevice(c->device));
+  OneShot os(c);
+  double* dfr = os.dev<double>((size_t)n_frames * (size_t)fl);
+  double* de = os.dev<double>((size_t)n_frames * 3);
+  double* dst = os.dev<double>(kStats);
+  if (!dfr || !de || !dst) return fail(DSP_ERR_NOMEM, "device allocation failed");
+  double* dm = de + n_frames; double* dz = dm + n_frames;
+  if (fl > 0) CU(cudaMemcpyAsync(dfr, frames, sizeof(double) * (size_t)n_frames * (size_t)fl, cudaMemcpyHostToDevice, c->stream));
+  frame_features_kernel<<<(unsigned)((n_frames + 127) / 128), 128, 0, c->stream>>>(dfr, n_frames, fl, de, dm, dz);
+  c->launches++;
+  CU(cudaGetLastError());
+  if (stats) {
+    sequence_stats_kernel<<<1, kExactThreads, 0, c->stream>>>(de, dm, dz, (int)n_frames, dst);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(stats, dst, sizeof(double) * kStats, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (energy) CU(cudaMemcpyAsync(energy, de, sizeof(double) * (size_t)n_frames, cudaMemcpyDeviceToHost, c->stream));
+  if (magnitude) CU(cudaMemcpyAsync(magnitude, dm, sizeof(double) * (size_t)n_frames, cudaMemcpyDeviceToHost, c->stream));
+  if (zcr) CU(cudaMemcpyAsync(zcr, dz, sizeof(double) * (size_t)n_frames, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return DSP_OK;
+}
+
+int dsp_sequence_stats_host(dsp_context* c, const double* seq, int64_t n, double* out5) {
+  if (!c || !out5 || n < 0) return fail(DSP_ERR_INVALID, "bad argument");
+  if (n == 0) return fail(DSP_ERR_INVALID, "zero-size array to reduction operation maximum which has no identity");
+  if (n > INT32_MAX) return fail(DSP_ERR_UNSUPPORTED, "sequence too long");
+  CU(cudaSetDevice(c->device));
+  OneShot os(c);
+  double* ds = os.dev<double>((size_t)n);
+  double* dst = os.dev<double>(kStats);
+  if (!ds || !dst) return fail(DSP_ERR_NOMEM, "device allocation failed");
+  CU(cudaMemcpyAsync(ds, seq, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  sequence_stats_kernel<<<1, kExactThreads, 0, c->stream>>>(ds, nullptr, nullptr, (int)n, dst);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out5, dst, sizeof(double) * 5, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return DSP_OK;
+}
+
+int dsp_zscore_device(dsp_context* c, const double* x, int64_t n, int32_t d, int fit, double* mean, double* std,
+                      double* out) {
+  if (!c || n < 0 || d < 1 || !mean || !std) return fail(DSP_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(c->device));
+  if (fit) {
+    if (n == 0) return fail(DSP_ERR_INVALID, "cannot fit on zero rows");
+    CU(zscore_fit(x, n, d, (fit == 2) ? 1 : 0, mean, std, c->stream));
+    c->launches++;
+  }
+  if (out) { CU(zscore_apply(x, n, d, mean, std, out, c->stream)); c->launches += 2; }
+  return DSP_OK;
+}
+
+int dsp_zscore_host(dsp_context* c, const double* x, int64_t n, int32_t d, int fit, double* mean, double* std,
+                    double* out) {
+  if (!c || n < 0 || d < 1 || !mean || !std || (!x && n)) return fail(DSP_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(c->device));
+  OneShot os(c);
+  double* dx = os.dev<double>((size_t)n * d);
+  double* dm = os.dev<double>((size_t)d);
+  double* ds = os.dev<double>((size_t)d);
+  double* dy = os.dev<double>((size_t)n * d);
+  if (!dx || !dm || !ds || !dy) return fail(DSP_ERR_NOMEM, "device allocation failed");
+  CU(cudaMemcpyAsync(dx, x, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice, c->stream));
+  if (!fit) {
+    CU(cudaMemcpyAsync(dm, mean, sizeof(double) * d, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(ds, std, sizeof(double) * d, cudaMemcpyHostToDevice, c->stream));
+  }
+  int rc = dsp_zscore_device(c, dx, n, d, fit, dm, ds, out ? dy : nullptr);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(mean, dm, sizeof(double) * d, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaMemcpyAsync(std, ds, sizeof(double) * d, cudaMemcpyDeviceToHost, c->stream));
+  if (out) CU(cudaMemcpyAsync(out, dy, sizeof(double) * (size_t)n * d, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return DSP_OK;
+}
+
+// ---- KNN ----------------------------------------------------------------------------------------
+static void knn_release(dsp_knn* k) {
+  DevBuf* all[] = {&k->train64, &k->train32, &k->labels, &k->tnorm, &k->cand_idx, &k->cand_worst, &k->qnorm,
+                   &k->redo_list, &k->redo_count, &k->nbr_label, &k->q, &k->o_idx, &k->o_dist, &k->o_lab};
+  for (DevBuf* b : all) b->release();
+}
+
+int dsp_knn_fit_device(dsp_context* c, const double* train, const int32_t* labels, int64_t n, int32_t d, int32_t k,
+                       int64_t index_base, dsp_knn** out) {
+  if (!c || !out || n < 1 || d < 1 || k < 1 || !train || !labels) return fail(DSP_ERR_INVALID, "bad argument");
+  if (k > kKnnMaxK) return fail(DSP_ERR_UNSUPPORTED, "n_neighbors > %d is not supported", kKnnMaxK);
+  if (n > INT32_MAX) return fail(DSP_ERR_UNSUPPORTED, "more than 2^31 train rows per shard");
+  CU(cudaSetDevice(c->device));
+  dsp_knn* h = new dsp_knn();
+  h->ctx = c; h->n = n; h->d = d; h->k = k; h->index_base = index_base; h->dp = knn_padded_dim(d);
+  auto bail = [&](int code) { knn_release(h); delete h; return code; };
+  if (h->train64.ensure(sizeof(double) * (size_t)n * d) != cudaSuccess || h->labels.ensure(sizeof(int32_t) * (size_t)n) != cudaSuccess ||
+      h->tnorm.ensure(64) != cudaSuccess || h->redo_count.ensure(64) != cudaSuccess)
+    return bail(fail(DSP_ERR_NOMEM, "device allocation failed"));
+  cudaMemcpyAsync(h->train64.p, train, sizeof(double) * (size_t)n * d, cudaMemcpyDeviceToDevice, c->stream);
+  cudaMemcpyAsync(h->labels.p, labels, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream);
+  if (h->dp) {
+    if (h->train32.ensure(sizeof(float) * (size_t)n * h->dp) != cudaSuccess) return bail(fail(DSP_ERR_NOMEM, "device allocation failed"));
+    cudaError_t e = knn_pack(h->train64.as<double>(), n, d, h->dp, h->train32.as<float>(), h->tnorm.as<float>(), c->stream);
+    c->launches++;
+    if (e != cudaSuccess) return bail(fail(DSP_ERR_CUDA, "knn_pack: %s", cudaGetErrorString(e)));
+    cudaMemcpyAsync(&h->tnorm_max, h->tnorm.p, sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+  }
+  cudaError_t e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) return bail(fail(DSP_ERR_CUDA, "knn fit: %s", cudaGetErrorString(e)));
+  *out = h;
+  return DSP_OK;
+}
+
+int dsp_knn_fit_host(dsp_context* c, const double* train, const int32_t* labels, int64_t n, int32_t d, int32_t k,
+                     int64_t index_base, dsp_knn** out) {
+  if (!c || !out || n < 1 || d < 1 || !train || !labels) return fail(DSP_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(c->device));
+  OneShot os(c);
+  double* dt = os.dev<double>((size_t)n * d);
+  int32_t* dl = os.dev<int32_t>((size_t)n);
+  if (!dt || !dl) return fail(DSP_ERR_NOMEM, "device allocation failed");
+  CU(cudaMemcpyAsync(dt, train, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaMemcpyAsync(dl, labels, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  return dsp_knn_fit_device(c, dt, dl, n, d, k, index_base, out);
+}
+
+int dsp_knn_free(dsp_knn* k) {
+  if (!k) return DSP_OK;
+  cudaSetDevice(k->ctx->device);
+  cudaStreamSynchronize(k->ctx->stream);
+  knn_release(k);
+  delete k;
+  return DSP_OK;
+}
+
+int dsp_knn_topk_device(dsp_knn* h, const double* q, int64_t m, int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label) {
+  if (!h || m < 0 || (!q && m)) return fail(DSP_ERR_INVALID, "bad argument");
+  if (m == 0) return DSP_OK;
+  if (m > INT32_MAX) return fail(DSP_ERR_UNSUPPORTED, "more than 2^31 queries per call");
+  dsp_context* c = h->ctx;
+  CU(cudaSetDevice(c->device));
+  CU(h->redo_list.ensure(sizeof(int32_t) * (size_t)m));
+  if (h->dp) {
+    CU(h->cand_idx.ensure(sizeof(int) * (size_t)m * kKnnCand));
+    CU(h->cand_worst.ensure(sizeof(float) * (size_t)m));
+    CU(h->qnorm.ensure(sizeof(float) * (size_t)m));
+    CU(knn_scan(h->dp, h->train32.as<float>(), h->n, q, m, h->d, h->cand_idx.as<int>(), h->cand_worst.as<float>(),
+                h->qnorm.as<float>(), c->stream));
+    CU(knn_rerank(h->train64.as<double>(), h->train32.as<float>(), h->dp, h->n, q, m, h->d, h->k, h->index_base,
+                  h->labels.as<int32_t>(), h->cand_idx.as<int>(), h->cand_worst.as<float>(), h->qnorm.as<float>(),
+                  h->tnorm_max, nbr_idx, nbr_sqdist, nbr_label, h->redo_list.as<int32_t>(),
+                  h->redo_count.as<int32_t>(), c->stream));
+    c->launches += 2;
+  } else {
+    // feature dimension beyond the tiled scan: exhaustive float64 scan of every query
+    CU(knn_redo_all(h->redo_list.as<int32_t>(), h->redo_count.as<int32_t>(), m, c->stream));
+    c->launches++;
+  }
+  CU(knn_rescan(h->train64.as<double>(), h->n, q, h->d, h->k, h->index_base, h->labels.as<int32_t>(),
+                h->redo_list.as<int32_t>(), h->redo_count.as<int32_t>(), nbr_idx, nbr_sqdist, nbr_label,
+                c->sm_count, c->stream));
+  c->launches++;
+  return DSP_OK;
+}
+
+int dsp_knn_predict_device(dsp_knn* h, const double* q, int64_t m, int32_t* labels_out) {
+  if (!h || !labels_out) return fail(DSP_ERR_INVALID, "bad argument");
+  if (m == 0) return DSP_OK;
+  dsp_context* c = h->ctx;
+  CU(cudaSetDevice(c->device));
+  CU(h->nbr_label.ensure(sizeof(int32_t) * (size_t)m * h->k));
+  int rc = dsp_knn_topk_device(h, q, m, nullptr, nullptr, h->nbr_label.as<int32_t>());
+  if (rc) return rc;
+  CU(knn_vote(h->nbr_label.as<int32_t>(), m, h->k, labels_out, c->stream));
+  c->launches++;
+  return DSP_OK;
+}
+
+int dsp_knn_topk_host(dsp_knn* h, const double* q, int64_t m, int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label) {
+  if (!h || m < 0 || (!q && m)) return fail(DSP_ERR_INVALID, "bad argument");
+  if (m == 0) return DSP_OK;
+  dsp_context* c = h->ctx;
+  CU(cudaSetDevice(c->device));
+  CU(h->q.ensure(sizeof(double) * (size_t)m * h->d));
+  CU(h->o_idx.ensure(sizeof(int64_t) * (size_t)m * h->k));
+  CU(h->o_dist.ensure(sizeof(double) * (size_t)m * h->k));
+  CU(h->o_lab.ensure(sizeof(int32_t) * (size_t)m * h->k));
+  CU(cudaMemcpyAsync(h->q.p, q, sizeof(double) * (size_t)m * h->d, cudaMemcpyHostToDevice, c->stream));
+  int rc = dsp_knn_topk_device(h, h->q.as<double>(), m, h->o_idx.as<int64_t>(), h->o_dist.as<double>(), h->o_lab.as<int32_t>());
+  if (rc) return rc;
+  if (nbr_idx) CU(cudaMemcpyAsync(nbr_idx, h->o_idx.p, sizeof(int64_t) * (size_t)m * h->k, cudaMemcpyDeviceToHost, c->stream));
+  if (nbr_sqdist) CU(cudaMemcpyAsync(nbr_sqdist, h->o_dist.p, sizeof(double) * (size_t)m * h->k, cudaMemcpyDeviceToHost, c->stream));
+  if (nbr_label) CU(cudaMemcpyAsync(nbr_label, h->o_lab.p, sizeof(int32_t) * (size_t)m * h->k, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return DSP_OK;
+}
+
+int dsp_knn_predict_host(dsp_knn* h, const double* q, int64_t m, int32_t* labels_out) {
+  if (!h || !labels_out || m < 0 || (!q && m)) return fail(DSP_ERR_INVALID, "bad argument");
+  if (m == 0) return DSP_OK;
+  dsp_context* c = h->ctx;
+  CU(cudaSetDevice(c->device));
+  CU(h->q.ensure(sizeof(double) * (size_t)m * h->d));
+  CU(h->o_lab.ensure(sizeof(int32_t) * (size_t)m));
+  CU(cudaMemcpyAsync(h->q.p, q, sizeof(double) * (size_t)m * h->d, cudaMemcpyHostToDevice, c->stream));
+  int rc = dsp_knn_predict_device(h, h->q.as<double>(), m, h->o_lab.as<int32_t>());
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(labels_out, h->o_lab.p, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return DSP_OK;
+}
+
+int dsp_knn_merge_vote_device(dsp_context* c, const double* cand_sqdist, const int64_t* cand_idx, const int32_t* cand_label,
+                              int32_t n_lists, int64_t m, int32_t k, int32_t* labels_out, int64_t* nbr_idx_out,
+                              double* nbr_sqdist_out) {
+  if (!c || !cand_sqdist || !cand_idx || !cand_label || n_lists < 1 || m < 0 || k < 1 || k > kKnnMaxK)
+    return fail(DSP_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(c->device));
+  CU(knn_merge_vote(cand_sqdist, cand_idx, cand_label, n_lists, m, k, labels_out, nbr_idx_out, nbr_sqdist_out, c->stream));
+  c->launches++;
+  return DSP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,590 @@
+// Fused front-end kernel for 16-bit mono PCM (the throughput path).
+//
+// One CTA owns one utterance at a time (persistent grid, dynamic work counter).  The
+// utterance is brought into shared memory ONCE with 1-D bulk async copies (TMA,
+// cp.async.bulk + mbarrier) and every later stage reads shared memory only, so frame
+// overlap and the reference's two framing passes cost no extra HBM traffic:
+//
+//   P1  sum / min / max of the PCM codes            -> DC (exact rational S/N), peak
+//   P2  per 64-sample group: sum d, sum d^2 (exact integers, d = k - round(S/N)) and one
+//       sign bit per sample                          -> every EPD frame from group sums
+//   P3  endpoint decision: 90th percentile by radix select, thresholds, six ballot-style
+//       searches; a certified-margin test flags utterances for the float64 replay kernel
+//   P4  windowed energy / magnitude over the trimmed frames (fp32 FMA, 8 lanes per frame),
+//       zero-crossing counts by popcount over the sign bits
+//   P5  mean / std / max / min / median of the three sequences, one warp per sequence
+//
+// Exactness (DESIGN.md "numerics"): with PCM input the reference's float64 values are
+// x_i = k_i/32768, so sign(x_i - mean) == sign(N*k_i - S) and sum((x_i-mean)/peak)^2 over a
+// frame equals (sum d^2 - 2*phi*sum d + fl*phi^2) * (N/M)^2 with integers N, S, M and
+// phi = S/N - round(S/N): zero-crossing counts are exact and EPD energies are within a few
+// ulp of the real-number value.  Threshold comparisons closer than a rigorous bound on the
+// reference's own rounding are not decided here but replayed in float64 NumPy order.
+//
+// Reference: src/audio_processing.py:49-90,135-275,299-333; src/feature_extraction.py:12-88.
+#include "kernels.cuh"
+
+namespace dsp {
+
+namespace {
+
+constexpr int kGroup = 64;          // samples per group-sum record
+constexpr int kLanesPerFrame = 8;   // P4: lanes cooperating on one frame
+constexpr int kTmaChunk = 16384;    // bytes per bulk copy
+
+struct SmemLayout {
+  int samples, bits, g2, g1, e, z, win, hist, sh, misc, total;
+};
+
+__host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
+
+__host__ __device__ inline SmemLayout make_layout(int cap_samples, int cap_frames, int fl) {
+  SmemLayout L;
+  const int ng = cap_samples / kGroup;
+  int o = 0;
+  L.samples = o; o += align16(2 * cap_samples + 32);
+  L.bits = o;    o += align16(4 * (cap_samples / 32 + 4));
+  // group sums; the same region later holds the three float feature sequences
+  const int gbytes = 12 * ng, fbytes = 12 * cap_frames;
+  L.g2 = o;
+  L.g1 = o + 8 * ng;
+  o += align16(gbytes > fbytes ? gbytes : fbytes);
+  L.e = o;       o += align16(8 * cap_frames);
+  L.z = o;       o += align16(4 * cap_frames);
+  L.win = o;     o += align16(4 * fl);
+  L.hist = o;    o += 3 * 256 * 4;
+  L.sh = o;      o += 64 * 8;
+  L.misc = o;    o += 256;
+  L.total = o;
+  return L;
+}
+
+// ---- mbarrier / bulk-copy PTX ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- sign-bit string helpers ----------------------------------------------------------
+__device__ __forceinline__ int bit_at(const uint32_t* bits, int i) { return (bits[i >> 5] >> (i & 31)) & 1; }
+
+// number of i in [p, q-1) with bit[i] != bit[i+1]  (sign changes among samples p..q-1)
+__device__ __forceinline__ int count_changes(const uint32_t* bits, int p, int q) {
+  if (q - p < 2) return 0;
+  const int last = q - 2;  // last pair start
+  int c = 0;
+  const int w0 = p >> 5, w1 = last >> 5;
+  for (int w = w0; w <= w1; ++w) {
+    const uint32_t cur = bits[w], nxt = bits[w + 1];
+    uint32_t x = cur ^ ((cur >> 1) | (nxt << 31));
+    if (w == w0) x &= 0xffffffffu << (p & 31);
+    if (w == w1) x &= 0xffffffffu >> (31 - (last & 31));
+    c += __popc(x);
+  }
+  return c;
+}
+
+// zero crossings of one windowed frame (compute_zero_crossing_rate on frame*window,
+// audio_processing.py:119-132): zero-padded samples and Hanning's exact-zero end points count
+// as negative.
+__device__ __forceinline__ int frame_zcr(const uint32_t* bits, int p, int valid, int fl, bool hann) {
+  if (hann && fl <= 2) return 0;
+  int zc = count_changes(bits, p, p + valid);
+  if (valid < fl) zc += bit_at(bits, p + valid - 1);
+  if (hann) {
+    const int s0 = bit_at(bits, p), s1 = valid > 1 ? bit_at(bits, p + 1) : 0;
+    zc += s1 - (s0 ^ s1);
+    if (fl - 1 < valid) {
+      const int sl = bit_at(bits, p + fl - 1), sp = bit_at(bits, p + fl - 2);
+      zc += sp - (sp ^ sl);
+    }
+  }
+  return zc;
+}
+
+__device__ __forceinline__ int sext16(uint32_t w) { return (int)(short)(w & 0xffffu); }
+
+struct UttConst {
+  int mu_int;      // round(S/N)
+  int c;           // sample is positive iff (k - mu_int) > c
+  float phi;       // S/N - mu_int
+  double phi_d;
+  double inv_m;    // N/M (1 when the signal is constant)
+  double mu;       // S/N
+};
+
+}  // namespace
+
+size_t pcm_kernel_smem_bytes(int cap_samples, int cap_frames, int fl) {
+  return (size_t)make_layout(cap_samples, cap_frames, fl).total;
+}
+
+__global__ void __launch_bounds__(kPcmThreads, 2)
+frontend_pcm_kernel(const PcmArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const SmemLayout L = make_layout(a.cap_samples, a.cap_frames, a.fl);
+  int16_t* s_x = reinterpret_cast<int16_t*>(smem + L.samples);
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + L.bits);
+  unsigned long long* s_g2 = reinterpret_cast<unsigned long long*>(smem + L.g2);
+  int* s_g1 = reinterpret_cast<int*>(smem + L.g1);
+  float* s_fe = reinterpret_cast<float*>(smem + L.g2);            // aliases the group sums
+  float* s_fm = s_fe + a.cap_frames;
+  float* s_fz = s_fm + a.cap_frames;
+  double* s_e = reinterpret_cast<double*>(smem + L.e);
+  int* s_z = reinterpret_cast<int*>(smem + L.z);
+  float* s_win = reinterpret_cast<float*>(smem + L.win);
+  int* s_hist = reinterpret_cast<int*>(smem + L.hist);
+  unsigned long long* s_sh = reinterpret_cast<unsigned long long*>(smem + L.sh);
+  // misc block: [0] mbarrier, then scalars
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L.misc);
+  int* s_int = reinterpret_cast<int*>(smem + L.misc + 16);         // 24 ints
+  double* s_dbl = reinterpret_cast<double*>(smem + L.misc + 128);  // 16 doubles
+
+  const int tid = threadIdx.x;
+  const int fl = a.fl, fs = a.fs;
+  const bool hann = (a.window == DSP_WIN_HANNING);
+
+  for (int j = tid; j < fl; j += kPcmThreads) s_win[j] = a.win_f32[j];
+  if (tid == 0) {
+    mbar_init(s_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    s_int[0] = (int)atomicAdd(a.work_counter, 1u);
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+  int u = s_int[0];
+
+  // issue the load of utterance `uu` (thread-block uniform); returns true when TMA was used
+  auto issue_load = [&](int uu) {
+    const int64_t off = a.offsets[uu];
+    const int n = (int)(a.offsets[uu + 1] - off);
+    const int16_t* src = a.samples + off;
+    const bool tma = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    if (tma) {
+      const uint32_t bytes = ((uint32_t)n * 2u) & ~15u;
+      if (tid < 32) {
+        if (bytes > 0) {
+          if (tid == 0) { fence_proxy_async(); mbar_expect_tx(s_bar, bytes); }
+          __syncwarp();
+          for (uint32_t o = (uint32_t)tid * kTmaChunk; o < bytes; o += 32u * kTmaChunk) {
+            const uint32_t sz = min((uint32_t)kTmaChunk, bytes - o);
+            bulk_g2s(reinterpret_cast<unsigned char*>(s_x) + o, reinterpret_cast<const unsigned char*>(src) + o, sz, s_bar);
+          }
+        }
+      }
+      // tail (< 8 samples) by plain loads
+      const int done = (int)(bytes >> 1);
+      if (tid >= 32 && tid < 32 + (n - done)) s_x[done + tid - 32] = src[done + tid - 32];
+    } else if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+      const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+      uint32_t* d32 = reinterpret_cast<uint32_t*>(s_x);
+      for (int i = tid; i < (n >> 1); i += kPcmThreads) d32[i] = __ldg(s32 + i);
+      if ((n & 1) && tid == 0) s_x[n - 1] = src[n - 1];
+    } else {
+      for (int i = tid; i < n; i += kPcmThreads) s_x[i] = src[i];
+    }
+  };
+  auto wait_load = [&](int uu) {
+    const int64_t off = a.offsets[uu];
+    const int n = (int)(a.offsets[uu + 1] - off);
+    const bool tma = ((reinterpret_cast<uintptr_t>(a.samples + off) & 15) == 0);
+    if (tma && (((uint32_t)n * 2u) & ~15u) > 0) { mbar_wait(s_bar, parity); parity ^= 1; }
+    __syncthreads();
+  };
+
+  if (u < a.n_utts) issue_load(u);
+
+  while (u < a.n_utts) {
+    const int64_t off = a.offsets[u];
+    const int n = (int)(a.offsets[u + 1] - off);
+    wait_load(u);
+
+    // =========================== P1: sum, min, max ===================================
+    {
+      int sum = 0;
+      uint32_t mn2 = 0x7fff7fffu, mx2 = 0x80008000u;
+      const int nvec = n >> 3;
+      const int4* xv = reinterpret_cast<const int4*>(s_x);
+      for (int v = tid; v < nvec; v += kPcmThreads) {
+        const int4 q = xv[v];
+        sum = __dp2a_lo(q.x, 0x0101, sum); sum = __dp2a_lo(q.y, 0x0101, sum);
+        sum = __dp2a_lo(q.z, 0x0101, sum); sum = __dp2a_lo(q.w, 0x0101, sum);
+        mn2 = __vmins2(mn2, q.x); mx2 = __vmaxs2(mx2, q.x);
+        mn2 = __vmins2(mn2, q.y); mx2 = __vmaxs2(mx2, q.y);
+        mn2 = __vmins2(mn2, q.z); mx2 = __vmaxs2(mx2, q.z);
+        mn2 = __vmins2(mn2, q.w); mx2 = __vmaxs2(mx2, q.w);
+      }
+      int mn = min(sext16(mn2), (int)mn2 >> 16), mx = max(sext16(mx2), (int)mx2 >> 16);
+      if (tid < (n & 7)) { const int k = s_x[(nvec << 3) + tid]; sum += k; mn = min(mn, k); mx = max(mx, k); }
+      long long S = block_reduce<long long>((long long)sum, OpAddLL(), 0ll, reinterpret_cast<long long*>(s_sh));
+      mn = block_reduce<int>(mn, OpMinI(), 32767, reinterpret_cast<int*>(s_sh));
+      mx = block_reduce<int>(mx, OpMaxI(), -32768, reinterpret_cast<int*>(s_sh));
+      if (tid == 0) {
+        const long long N = n > 0 ? n : 1;
+        // mu_int = round-half-up(S/N) by floor division
+        long long num = 2 * S + N, den = 2 * N;
+        long long q = num / den; if ((num % den) != 0 && ((num < 0) != (den < 0))) --q;
+        const long long R = S - N * q;            // |R| <= N/2
+        const long long M = max(N * (long long)mx - S, S - N * (long long)mn);
+        s_int[1] = (int)q;
+        s_int[2] = (R < 0) ? -1 : 0;
+        s_dbl[0] = (double)R / (double)N;
+        s_dbl[1] = (M > 0) ? (double)N / (double)M : 1.0;
+        s_dbl[2] = (double)S / (double)N;
+        s_int[3] = 0;   // flag
+        s_int[4] = n;   // n3 (min)      -- initial values for the searches
+        s_int[5] = -1;  // n4 (max)
+      }
+      __syncthreads();
+    }
+    UttConst uc;
+    uc.mu_int = s_int[1]; uc.c = s_int[2]; uc.phi_d = s_dbl[0]; uc.phi = (float)uc.phi_d;
+    uc.inv_m = s_dbl[1]; uc.mu = s_dbl[2];
+
+    // =========================== P2: group sums + sign bits ==========================
+    const int ng = (n + kGroup - 1) / kGroup;
+    for (int g = tid; g < ng; g += kPcmThreads) {
+      int s1 = 0;
+      unsigned long long s2 = 0;
+      uint32_t b0 = 0, b1 = 0;
+      const int base = g * kGroup;
+      if (base + kGroup <= n) {
+        const int4* gv = reinterpret_cast<const int4*>(s_x + base);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int vi = (j + g) & 7;             // rotated: conflict-free 16-byte accesses
+          const int4 q = gv[vi];
+          const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+          uint32_t byte = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int lo = sext16(w[k]) - uc.mu_int, hi = ((int)w[k] >> 16) - uc.mu_int;
+            s1 += lo + hi;
+            s2 += (unsigned long long)((long long)lo * lo) + (unsigned long long)((long long)hi * hi);
+            byte |= ((uint32_t)(uc.c - lo) >> 31) << (2 * k);
+            byte |= ((uint32_t)(uc.c - hi) >> 31) << (2 * k + 1);
+          }
+          if (vi < 4) b0 |= byte << (8 * vi); else b1 |= byte << (8 * (vi - 4));
+        }
+      } else {
+        for (int i = 0; i < kGroup && base + i < n; ++i) {
+          const int d = (int)s_x[base + i] - uc.mu_int;
+          s1 += d; s2 += (unsigned long long)((long long)d * d);
+          const uint32_t bit = (uint32_t)(uc.c - d) >> 31;
+          if (i < 32) b0 |= bit << i; else b1 |= bit << (i - 32);
+        }
+      }
+      s_g1[g] = s1; s_g2[g] = s2;
+      s_bits[2 * g] = b0; s_bits[2 * g + 1] = b1;
+    }
+    if (tid < 4) s_bits[2 * ng + tid] = 0;
+    __syncthreads();
+
+    // =========================== P2b: EPD frame energies / crossings =================
+    int f1 = 0;
+    if (a.do_epd && n >= fl) f1 = (n - fl) / fs + 1;
+    for (int f = tid; f < f1; f += kPcmThreads) {
+      const int p = f * fs, q = p + fl;
+      long long s1 = 0; unsigned long long s2 = 0;
+      const int ga = (p + kGroup - 1) / kGroup, gb = q / kGroup;
+      auto direct = [&](int i0, int i1) {
+        for (int i = i0; i < i1; ++i) { const int d = (int)s_x[i] - uc.mu_int; s1 += d; s2 += (unsigned long long)((long long)d * d); }
+      };
+      if (ga > gb) direct(p, q);
+      else {
+        for (int g = ga; g < gb; ++g) { s1 += s_g1[g]; s2 += s_g2[g]; }
+        direct(p, ga * kGroup);
+        direct(gb * kGroup, q);
+      }
+      // sum (d - phi)^2: s2, s1 exact integers; |terms| <= 9x the result (DESIGN.md "numerics")
+      const double ep = ((double)s2 - 2.0 * uc.phi_d * (double)s1) + (double)fl * uc.phi_d * uc.phi_d;
+      s_e[f] = ep * uc.inv_m * uc.inv_m;
+      s_z[f] = count_changes(s_bits, p, q);
+    }
+    __syncthreads();
+
+    // =========================== P3: endpoint decision ===============================
+    int start = 0, end = n;
+    if (f1 > 0) {
+      // E_max for the tolerance model
+      double emx = 0.0;
+      for (int f = tid; f < f1; f += kPcmThreads) emx = fmax(emx, s_e[f]);
+      emx = block_reduce<double>(emx, OpMaxD(), 0.0, reinterpret_cast<double*>(s_sh));
+      const int nf = min(5, f1 / 10);
+      uint64_t ka, kb;
+      const double v = (double)(f1 - 1) * (90.0 / 100.0);
+      auto get = [&](int i) { return f64_key(s_e[i]); };
+      if (v >= (double)(f1 - 1)) { block_select_pair(get, f1, f1 - 1, s_hist, s_sh, &ka, &kb); kb = ka; }
+      else block_select_pair(get, f1, (int)floor(v), s_hist, s_sh, &ka, &kb);
+      if (tid == 0) {
+        const double speech = np_lerp(key_f64(ka), key_f64(kb), v - floor(v));
+        double noise_e, noise_z;
+        if (nf > 0) {
+          auto te = [&](int64_t i) { return i < nf ? s_e[i] : s_e[f1 - 2 * nf + i]; };
+          auto tz = [&](int64_t i) { return (double)(i < nf ? s_z[i] : s_z[f1 - 2 * nf + i]); };
+          noise_e = np_pairwise_leaf(te, 0, 2 * nf) / (double)(2 * nf);
+          noise_z = np_pairwise_leaf(tz, 0, 2 * nf) / (double)(2 * nf);
+        } else {
+          noise_e = s_e[0]; noise_z = (double)s_z[0];
+          for (int i = 1; i < f1; ++i) { noise_e = fmin(noise_e, s_e[i]); noise_z = fmin(noise_z, (double)s_z[i]); }
+        }
+        const double t1 = speech * a.hr;
+        const double t2 = noise_e + (speech - noise_e) * a.lr;
+        const double t3 = noise_z * a.zr;
+        s_dbl[3] = t1; s_dbl[4] = t2; s_dbl[5] = t3;
+        // slack on the thresholds: relative part plus the reference's mean-rounding term at E_max
+        const double eps = 1.0 / 1099511627776.0;  // 2^-40
+        const double smax = ldexp(fabs(uc.mu) * sqrt((double)fl * emx) * uc.inv_m, -50);
+        s_dbl[6] = eps * fabs(t1) + fabs(a.hr) * smax;
+        s_dbl[7] = eps * (fabs(noise_e) + fabs(a.lr) * (fabs(speech) + fabs(noise_e))) +
+                   (fabs(1.0 - a.lr) + fabs(a.lr)) * smax;
+      }
+      __syncthreads();
+      const double t1 = s_dbl[3], t2 = s_dbl[4], t3 = s_dbl[5];
+      const double tol1 = s_dbl[6], tol2 = s_dbl[7];
+      const double eps = 1.0 / 1099511627776.0;
+      {
+        int n3 = f1, n4 = -1, flag = 0;
+        for (int f = tid; f < f1; f += kPcmThreads) {
+          const double e = s_e[f];
+          if (e > t1) { n3 = min(n3, f); n4 = max(n4, f); }
+          // |mu| * sqrt(fl * E') / m^2 with E' = E * m^2  ->  |mu| * sqrt(fl*E) / m
+          const double sf = ldexp(fabs(uc.mu) * sqrt((double)fl * e) * uc.inv_m, -50) + eps * e;
+          if (!(e == 0.0 && t1 == 0.0) && fabs(e - t1) <= sf + tol1) flag = 1;
+          if (!(e == 0.0 && t2 == 0.0) && fabs(e - t2) <= sf + tol2) flag = 1;
+        }
+        n3 = warp_reduce(n3, OpMinI()); n4 = warp_reduce(n4, OpMaxI());
+        flag = warp_reduce(flag, OpMaxI());
+        if (lane_id() == 0) {
+          if (n3 < f1) atomicMin(&s_int[4], n3);
+          if (n4 >= 0) atomicMax(&s_int[5], n4);
+          if (flag) atomicOr(&s_int[3], 1);
+        }
+        if (tid == 0) { s_int[6] = 0; s_int[7] = f1 - 1; s_int[8] = 0; s_int[9] = f1 - 1; }
+      }
+      __syncthreads();
+      const int n3 = s_int[4], n4 = s_int[5];
+      if (n4 >= 0) {
+        {
+          int n2 = 0, n5 = f1 - 1;
+          for (int f = tid; f < f1; f += kPcmThreads)
+            if (s_e[f] <= t2) { if (f < n3) n2 = max(n2, f + 1); if (f > n4) n5 = min(n5, f - 1); }
+          n2 = warp_reduce(n2, OpMaxI()); n5 = warp_reduce(n5, OpMinI());
+          if (lane_id() == 0) { if (n2 > 0) atomicMax(&s_int[6], n2); if (n5 < f1 - 1) atomicMin(&s_int[7], n5); }
+        }
+        __syncthreads();
+        const int n2 = s_int[6], n5 = s_int[7];
+        {
+          int n1 = 0, n6 = f1 - 1;
+          for (int f = tid; f < f1; f += kPcmThreads)
+            if ((double)s_z[f] <= t3) { if (f < n2) n1 = max(n1, f + 1); if (f > n5) n6 = min(n6, f - 1); }
+          n1 = warp_reduce(n1, OpMaxI()); n6 = warp_reduce(n6, OpMinI());
+          if (lane_id() == 0) { if (n1 > 0) atomicMax(&s_int[8], n1); if (n6 < f1 - 1) atomicMin(&s_int[9], n6); }
+        }
+        __syncthreads();
+        start = s_int[8] * fs;
+        end = min(s_int[9] * fs + fl, n);
+      }
+      // EPD lists out (the group-sum region is dead from here on; E/Z stay valid)
+      if (a.out.epd_energy || a.out.epd_zcr) {
+        const int64_t eo = a.epd_offsets[u];
+        for (int f = tid; f < f1; f += kPcmThreads) {
+          if (a.out.epd_energy) a.out.epd_energy[eo + f] = s_e[f];
+          if (a.out.epd_zcr) a.out.epd_zcr[eo + f] = (float)s_z[f];
+        }
+      }
+    }
+    const int flagged = s_int[3];
+    __syncthreads();
+
+    // =========================== P4: windowed frame features =========================
+    const int seg = end - start;
+    const int f2 = (int)frame_count_host_device(seg, fl, fs);
+    {
+      const int sub = tid & (kLanesPerFrame - 1);
+      const int slot = tid / kLanesPerFrame;
+      constexpr int kSlots = kPcmThreads / kLanesPerFrame;
+      const bool vec_ok = ((start & 7) == 0) && ((fs & 7) == 0);
+      const float phi = uc.phi;
+      for (int t0 = 0; t0 < f2; t0 += kSlots) {
+        const int t = t0 + slot;
+        float e = 0.f, m = 0.f;
+        int p = 0, valid = 0;
+        if (t < f2) {
+          p = start + t * fs;
+          valid = min(fl, end - p);
+          int jdone = 0;
+          if (vec_ok) {
+            const int nv = valid >> 3;
+            const int4* xv = reinterpret_cast<const int4*>(s_x + p);
+            const float4* wv = reinterpret_cast<const float4*>(s_win);
+            for (int v = sub; v < nv; v += kLanesPerFrame) {
+              const int4 q = xv[v];
+              const float4 wa = wv[2 * v], wb = wv[2 * v + 1];
+              const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+              const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float dlo = (float)(sext16(w[k]) - uc.mu_int) - phi;
+                const float dhi = (float)(((int)w[k] >> 16) - uc.mu_int) - phi;
+                const float alo = ww[2 * k] * dlo, ahi = ww[2 * k + 1] * dhi;
+                e = fmaf(alo, alo, e); m += fabsf(alo);
+                e = fmaf(ahi, ahi, e); m += fabsf(ahi);
+              }
+            }
+            jdone = nv << 3;
+          }
+          for (int j = jdone + sub; j < valid; j += kLanesPerFrame) {
+            const float d = (float)((int)s_x[p + j] - uc.mu_int) - phi;
+            const float av = s_win[j] * d;
+            e = fmaf(av, av, e); m += fabsf(av);
+          }
+        }
+#pragma unroll
+        for (int o = kLanesPerFrame / 2; o > 0; o >>= 1) {
+          e += __shfl_xor_sync(0xffffffffu, e, o);
+          m += __shfl_xor_sync(0xffffffffu, m, o);
+        }
+        if (t < f2) {
+          if (sub == 0) {
+            s_fe[t] = (float)((double)e * uc.inv_m * uc.inv_m);
+            s_fm[t] = (float)((double)m * uc.inv_m);
+          } else if (sub == 1) {
+            s_fz[t] = (float)frame_zcr(s_bits, p, valid, fl, hann);
+          }
+        }
+      }
+    }
+    __syncthreads();   // samples / sign bits are dead: the next utterance may be loaded
+
+    if (tid == 0) s_int[0] = (int)atomicAdd(a.work_counter, 1u);
+    __syncthreads();
+    const int u_next = s_int[0];
+    if (u_next < a.n_utts) issue_load(u_next);
+
+    // =========================== P5: statistics, one warp per sequence ===============
+    if (f2 > 0 && a.out.stats && warp_id() < 3) {
+      const int wq = warp_id(), lane = lane_id();
+      const float* seq = wq == 0 ? s_fe : (wq == 1 ? s_fm : s_fz);
+      double sum = 0.0; float mx = -INFINITY, mn = INFINITY;
+      for (int i = lane; i < f2; i += 32) { const float x = seq[i]; sum += (double)x; mx = fmaxf(mx, x); mn = fminf(mn, x); }
+      sum = warp_reduce(sum, OpAddD());
+      mx = warp_reduce(mx, [](float x, float y) { return fmaxf(x, y); });
+      mn = warp_reduce(mn, [](float x, float y) { return fminf(x, y); });
+      const double mean = sum / (double)f2;
+      double ss = 0.0;
+      for (int i = lane; i < f2; i += 32) { const double d = (double)seq[i] - mean; ss += d * d; }
+      ss = warp_reduce(ss, OpAddD());
+      // median: warp-level MSD radix select on the (non-negative) float bit patterns
+      int* hist = s_hist + 256 * wq;
+      uint32_t prefix = 0, mask = 0;
+      int rank = (f2 - 1) / 2;
+      for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = lane; i < 256; i += 32) hist[i] = 0;
+        __syncwarp();
+        for (int i = lane; i < f2; i += 32) {
+          const uint32_t k = __float_as_uint(seq[i]);
+          if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 0xff], 1);
+        }
+        __syncwarp();
+        int c[8], tot = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { c[j] = hist[lane * 8 + j]; tot += c[j]; }
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int tt = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += tt; }
+        int run = incl - tot, digit = -1, newrank = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { if (digit < 0 && rank >= run && rank < run + c[j]) { digit = lane * 8 + j; newrank = rank - run; } run += c[j]; }
+        const unsigned who = __ballot_sync(0xffffffffu, digit >= 0);
+        const int src = __ffs(who) - 1;
+        digit = __shfl_sync(0xffffffffu, digit, src);
+        rank = __shfl_sync(0xffffffffu, newrank, src);
+        prefix |= (uint32_t)digit << shift; mask |= 0xffu << shift;
+        __syncwarp();
+      }
+      const float med_lo = __uint_as_float(prefix);
+      int le = 0; float nxt = INFINITY;
+      for (int i = lane; i < f2; i += 32) { const float x = seq[i]; if (x <= med_lo) ++le; else nxt = fminf(nxt, x); }
+      le = warp_reduce(le, OpAddI());
+      nxt = warp_reduce(nxt, [](float x, float y) { return fminf(x, y); });
+      const int r = (f2 - 1) / 2;
+      const float med_hi = (le >= r + 2 || nxt == INFINITY) ? med_lo : nxt;
+      if (lane == 0) {
+        float* o = a.out.stats + (int64_t)u * kStats + 5 * wq;
+        o[0] = (float)mean;
+        o[1] = (float)sqrt(ss / (double)f2);
+        o[2] = mx; o[3] = mn;
+        o[4] = (f2 & 1) ? med_lo : (float)(((double)med_lo + (double)med_hi) * 0.5);
+      }
+    }
+
+    // =========================== P6: outputs =========================================
+    {
+      const int64_t fo = a.feat_offsets[u];
+      for (int t = tid; t < f2; t += kPcmThreads) {
+        if (a.out.energy) a.out.energy[fo + t] = s_fe[t];
+        if (a.out.magnitude) a.out.magnitude[fo + t] = s_fm[t];
+        if (a.out.zcr) a.out.zcr[fo + t] = s_fz[t];
+      }
+      if (tid == 0) {
+        int status = DSP_UTT_OK;
+        if (seg <= 0) status = DSP_UTT_EMPTY; else if (f2 == 0) status = DSP_UTT_NO_FRAMES;
+        if (a.out.start) a.out.start[u] = start;
+        if (a.out.end) a.out.end[u] = end;
+        if (a.out.n_epd_frames) a.out.n_epd_frames[u] = f1;
+        if (a.out.n_frames) a.out.n_frames[u] = f2;
+        if (a.out.status) a.out.status[u] = status;
+        if (flagged) { const int slot = atomicAdd(a.flag_count, 1); a.flag_list[slot] = u; }
+      }
+    }
+    __syncthreads();
+    u = u_next;
+  }
+}
+
+cudaError_t launch_frontend_pcm(const PcmArgs& a, int grid, size_t smem, cudaStream_t st) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(frontend_pcm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  frontend_pcm_kernel<<<grid, kPcmThreads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+int pcm_kernel_max_ctas_per_sm(size_t smem) {
+  int n = 0;
+  cudaFuncSetAttribute(frontend_pcm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frontend_pcm_kernel, kPcmThreads, smem) != cudaSuccess) return 0;
+  return n;
+}
+
+}  // namespace dsp

@@ -1,0 +1,374 @@
+// KNN classify (src/models.py:33-35,52-58 -> sklearn KNeighborsClassifier(n_neighbors=k),
+// Euclidean, uniform vote).
+//
+// The reference's result is the k train rows with the smallest float64 distance and a
+// majority vote with ties to the smallest label.  The feature dimension of this path is
+// 15 (pad 16): far too thin for a tensor-core contraction to be "genuinely dense", so the
+// scan is a shared-memory tiled fp32 kernel:
+//
+//   scan    each thread keeps QPT queries in registers (pre-scaled by -2) and streams train
+//           tiles staged in shared memory ([t_0..t_{D-1}, |t|^2] per row, broadcast loads);
+//           per pair it is D FMAs starting from |t|^2, then one compare against the worst of
+//           a sorted register list of KC candidates.  The train matrix is never re-read from
+//           HBM per query and the m x n distance matrix is never materialised.
+//   rerank  float64 direct-form distances sum_j (q_j - t_j)^2 (the kd-tree's accumulation
+//           order) for the KC candidates, sorted by (distance, index); the top k are CERTIFIED
+//           exact when the k-th exact distance is below the worst kept fp32 score minus a
+//           bound on the fp32 error -- otherwise the query is rescanned exhaustively in
+//           float64 (rescan kernel), so labels never depend on fp32 rounding.
+#include "kernels.cuh"
+#include "knn.cuh"
+
+namespace dsp {
+
+namespace {
+
+constexpr int kScanThreads = 128;
+constexpr int kTileRows = 128;
+
+template <int KC>
+__device__ __forceinline__ void cand_insert(float (&cd)[KC], int (&ci)[KC], float d, int idx) {
+  // sorted ascending; cd[KC-1] is the worst kept score
+  if (d < cd[KC - 1]) {
+    cd[KC - 1] = d; ci[KC - 1] = idx;
+#pragma unroll
+    for (int s = KC - 1; s > 0; --s) {
+      if (cd[s] < cd[s - 1]) {
+        const float td = cd[s]; cd[s] = cd[s - 1]; cd[s - 1] = td;
+        const int ti = ci[s]; ci[s] = ci[s - 1]; ci[s - 1] = ti;
+      }
+    }
+  }
+}
+
+// fp32 candidate scan.  train32: [n, DP] rows of (t_0..t_{D-1}, 0.., |t|^2 at DP-1) -- |t|^2 rounded
+// to float.  queries: float64 [m, d].  Outputs KC candidate indices per query and the worst
+// kept score.
+template <int DP, int QPT>
+__global__ void __launch_bounds__(kScanThreads)
+knn_scan_kernel(const float* __restrict__ train32, int64_t n, const double* __restrict__ queries,
+                int64_t m, int d, int* __restrict__ cand_idx, float* __restrict__ cand_worst,
+                float* __restrict__ qnorm_out) {
+  __shared__ __align__(16) float tile[kTileRows * DP];
+  const int64_t q0 = ((int64_t)blockIdx.x * kScanThreads + threadIdx.x) * QPT;
+  float q[QPT][DP - 1];
+  float cd[QPT][kKnnCand];
+  int ci[QPT][kKnnCand];
+#pragma unroll
+  for (int r = 0; r < QPT; ++r) {
+    float nn = 0.f;
+#pragma unroll
+    for (int j = 0; j < DP - 1; ++j) {
+      const float v = (q0 + r < m && j < d) ? (float)queries[(q0 + r) * d + j] : 0.f;
+      nn = fmaf(v, v, nn);
+      q[r][j] = -2.f * v;
+    }
+    if (q0 + r < m) qnorm_out[q0 + r] = nn;
+#pragma unroll
+    for (int c = 0; c < kKnnCand; ++c) { cd[r][c] = INFINITY; ci[r][c] = -1; }
+  }
+  for (int64_t base = 0; base < n; base += kTileRows) {
+    const int rows = (int)min((int64_t)kTileRows, n - base);
+    __syncthreads();
+    {
+      const float4* src = reinterpret_cast<const float4*>(train32 + base * DP);
+      float4* dst = reinterpret_cast<float4*>(tile);
+      for (int i = threadIdx.x; i < rows * (DP / 4); i += kScanThreads) dst[i] = src[i];
+    }
+    __syncthreads();
+    for (int j = 0; j < rows; ++j) {
+      const float4* row = reinterpret_cast<const float4*>(tile + j * DP);
+      float acc[QPT];
+      const float tn = tile[j * DP + DP - 1];
+#pragma unroll
+      for (int r = 0; r < QPT; ++r) acc[r] = tn;
+#pragma unroll
+      for (int v = 0; v < DP / 4; ++v) {
+        const float4 x = row[v];
+#pragma unroll
+        for (int r = 0; r < QPT; ++r) {
+          acc[r] = fmaf(q[r][4 * v], x.x, acc[r]);
+          acc[r] = fmaf(q[r][4 * v + 1], x.y, acc[r]);
+          acc[r] = fmaf(q[r][4 * v + 2], x.z, acc[r]);
+          if (4 * v + 3 < DP - 1) acc[r] = fmaf(q[r][4 * v + 3], x.w, acc[r]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < QPT; ++r) cand_insert<kKnnCand>(cd[r], ci[r], acc[r], (int)(base + j));
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < QPT; ++r) {
+    if (q0 + r < m) {
+#pragma unroll
+      for (int c = 0; c < kKnnCand; ++c) cand_idx[(q0 + r) * kKnnCand + c] = ci[r][c];
+      cand_worst[q0 + r] = cd[r][kKnnCand - 1];
+    }
+  }
+}
+
+__device__ __forceinline__ double sqdist64(const double* q, const double* t, int d) {
+  double s = 0.0;
+  for (int j = 0; j < d; ++j) { const double x = q[j] - t[j]; s += x * x; }
+  return s;
+}
+
+__device__ __forceinline__ bool less_di(double da, int64_t ia, double db, int64_t ib) {
+  return da < db || (da == db && ia < ib);
+}
+
+// float64 rerank + certification.  One thread per query.
+__global__ void knn_rerank_kernel(const double* __restrict__ train, const float* __restrict__ train32,
+                                  int dp, int64_t n, const double* __restrict__ queries, int64_t m,
+                                  int d, int k, int64_t index_base, const int32_t* __restrict__ labels,
+                                  const int* __restrict__ cand_idx, const float* __restrict__ cand_worst,
+                                  const float* __restrict__ qnorm, float tnorm_max,
+                                  int64_t* __restrict__ nbr_idx, double* __restrict__ nbr_sqdist,
+                                  int32_t* __restrict__ nbr_label, int32_t* __restrict__ redo_list,
+                                  int32_t* __restrict__ redo_count) {
+  const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= m) return;
+  const double* q = queries + qi * d;
+  double cd[kKnnCand];
+  int cidx[kKnnCand];
+  int nc = 0;
+  for (int c = 0; c < kKnnCand; ++c) {
+    const int i = cand_idx[qi * kKnnCand + c];
+    if (i < 0) continue;
+    const double dd = sqdist64(q, train + (int64_t)i * d, d);
+    int s = nc++;
+    while (s > 0 && less_di(dd, i, cd[s - 1], cidx[s - 1])) { cd[s] = cd[s - 1]; cidx[s] = cidx[s - 1]; --s; }
+    cd[s] = dd; cidx[s] = i;
+  }
+  const int kk = (int)min((int64_t)k, n);
+  bool ok = (nc >= kk);
+  if (ok && n > kKnnCand) {
+    // every row that is NOT a candidate has fp32 score >= worst kept score; its exact squared
+    // distance is at least (score + |q|^2) - err.  err bounds the fp32 evaluation of
+    // |t|^2 - 2 q.t + |q|^2: (d+2) roundings on terms bounded by (|q| + |t|)^2.
+    const float qn = qnorm[qi];
+    const double bound = (double)(sqrtf(qn) + sqrtf(tnorm_max));
+    const double err = (double)(d + 4) * 1.1920929e-7 * bound * bound;
+    const double lower = (double)cand_worst[qi] + (double)qn - err;
+    ok = cd[kk - 1] < lower;
+  }
+  if (!ok) {
+    const int slot = atomicAdd(redo_count, 1);
+    redo_list[slot] = (int)qi;
+    return;
+  }
+  for (int c = 0; c < kk; ++c) {
+    if (nbr_idx) nbr_idx[qi * k + c] = index_base + cidx[c];
+    if (nbr_sqdist) nbr_sqdist[qi * k + c] = cd[c];
+    if (nbr_label) nbr_label[qi * k + c] = labels[cidx[c]];
+  }
+  for (int c = kk; c < k; ++c) {
+    if (nbr_idx) nbr_idx[qi * k + c] = -1;
+    if (nbr_sqdist) nbr_sqdist[qi * k + c] = INFINITY;
+    if (nbr_label) nbr_label[qi * k + c] = -1;
+  }
+}
+
+// Exhaustive float64 scan for the queries the certificate rejected: one warp per query.
+__global__ void knn_rescan_kernel(const double* __restrict__ train, int64_t n,
+                                  const double* __restrict__ queries, int d, int k, int64_t index_base,
+                                  const int32_t* __restrict__ labels, const int32_t* __restrict__ redo_list,
+                                  const int32_t* __restrict__ redo_count, int64_t* __restrict__ nbr_idx,
+                                  double* __restrict__ nbr_sqdist, int32_t* __restrict__ nbr_label) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int total = *redo_count;
+  for (int item = blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < total;
+       item += gridDim.x * warps_per_block) {
+    const int64_t qi = redo_list[item];
+    const double* q = queries + qi * d;
+    double bd[kKnnMaxK];
+    int64_t bi[kKnnMaxK];
+    for (int c = 0; c < k; ++c) { bd[c] = INFINITY; bi[c] = INT64_MAX; }
+    for (int64_t i = lane; i < n; i += 32) {
+      const double dd = sqdist64(q, train + i * d, d);
+      if (less_di(dd, i, bd[k - 1], bi[k - 1])) {
+        int s = k - 1;
+        while (s > 0 && less_di(dd, i, bd[s - 1], bi[s - 1])) { bd[s] = bd[s - 1]; bi[s] = bi[s - 1]; --s; }
+        bd[s] = dd; bi[s] = i;
+      }
+    }
+    // merge the 32 sorted lists: k rounds of "global minimum, pop from its owner"
+    int head = 0;
+    for (int c = 0; c < k; ++c) {
+      double md = head < k ? bd[head] : INFINITY;
+      int64_t mi = head < k ? bi[head] : INT64_MAX;
+      int owner = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, md, o);
+        const int64_t oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        const int oo = __shfl_xor_sync(0xffffffffu, owner, o);
+        if (less_di(od, oi, md, mi)) { md = od; mi = oi; owner = oo; }
+      }
+      if (owner == lane && mi != INT64_MAX) ++head;
+      if (lane == 0) {
+        const bool valid = (mi != INT64_MAX);
+        if (nbr_idx) nbr_idx[qi * k + c] = valid ? index_base + mi : -1;
+        if (nbr_sqdist) nbr_sqdist[qi * k + c] = md;
+        if (nbr_label) nbr_label[qi * k + c] = valid ? labels[mi] : -1;
+      }
+    }
+  }
+}
+
+// train float64 [n,d] -> padded fp32 rows with |t|^2 in the last column; also max |t|^2.
+__global__ void knn_pack_kernel(const double* __restrict__ train, int64_t n, int d, int dp,
+                                float* __restrict__ train32, float* __restrict__ tnorm_max) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float nn = 0.f;
+  if (i < n) {
+    for (int j = 0; j < dp - 1; ++j) {
+      const float v = j < d ? (float)train[i * d + j] : 0.f;
+      train32[i * dp + j] = v;
+      nn = fmaf(v, v, nn);
+    }
+    train32[i * dp + dp - 1] = nn;
+  }
+  nn = warp_reduce(nn, [](float a, float b) { return fmaxf(a, b); });
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(tnorm_max), __float_as_int(nn));
+}
+
+// majority vote over k neighbour labels, ties to the smallest label
+// (sklearn/neighbors/_classification.py:262-309); one thread per query.
+__global__ void knn_vote_kernel(const int32_t* __restrict__ nbr_label, int64_t m, int k,
+                                int32_t* __restrict__ out) {
+  const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= m) return;
+  const int32_t* l = nbr_label + qi * k;
+  int best = -1, best_cnt = 0;
+  for (int a = 0; a < k; ++a) {
+    if (l[a] < 0) continue;
+    int cnt = 0;
+    for (int b = 0; b < k; ++b) cnt += (l[b] == l[a]);
+    if (cnt > best_cnt || (cnt == best_cnt && l[a] < best)) { best = l[a]; best_cnt = cnt; }
+  }
+  out[qi] = best;
+}
+
+// merge R candidate lists [R, m, k] -> global top-k by (distance, index), then vote.
+__global__ void knn_merge_vote_kernel(const double* __restrict__ cd, const int64_t* __restrict__ ci,
+                                      const int32_t* __restrict__ cl, int r, int64_t m, int k,
+                                      int32_t* __restrict__ labels_out, int64_t* __restrict__ idx_out,
+                                      double* __restrict__ dist_out) {
+  const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= m) return;
+  double bd[kKnnMaxK];
+  int64_t bi[kKnnMaxK];
+  int32_t bl[kKnnMaxK];
+  for (int c = 0; c < k; ++c) { bd[c] = INFINITY; bi[c] = INT64_MAX; bl[c] = -1; }
+  for (int s = 0; s < r; ++s) {
+    for (int c = 0; c < k; ++c) {
+      const int64_t o = ((int64_t)s * m + qi) * k + c;
+      const int64_t idx = ci[o];
+      if (idx < 0) continue;
+      const double dd = cd[o];
+      if (less_di(dd, idx, bd[k - 1], bi[k - 1])) {
+        int p = k - 1;
+        while (p > 0 && less_di(dd, idx, bd[p - 1], bi[p - 1])) { bd[p] = bd[p - 1]; bi[p] = bi[p - 1]; bl[p] = bl[p - 1]; --p; }
+        bd[p] = dd; bi[p] = idx; bl[p] = cl[o];
+      }
+    }
+  }
+  int best = -1, best_cnt = 0;
+  for (int a = 0; a < k; ++a) {
+    if (bl[a] < 0) continue;
+    int cnt = 0;
+    for (int b = 0; b < k; ++b) cnt += (bl[b] == bl[a]);
+    if (cnt > best_cnt || (cnt == best_cnt && bl[a] < best)) { best = bl[a]; best_cnt = cnt; }
+  }
+  if (labels_out) labels_out[qi] = best;
+  for (int c = 0; c < k; ++c) {
+    if (idx_out) idx_out[qi * k + c] = bi[c] == INT64_MAX ? -1 : bi[c];
+    if (dist_out) dist_out[qi * k + c] = bd[c];
+  }
+}
+
+__global__ void knn_iota_kernel(int32_t* list, int32_t* count, int64_t m) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) list[i] = (int32_t)i;
+  if (i == 0) *count = (int32_t)m;
+}
+
+}  // namespace
+
+int knn_padded_dim(int d) {
+  if (d + 1 <= 16) return 16;
+  if (d + 1 <= 32) return 32;
+  if (d + 1 <= 64) return 64;
+  return 0;
+}
+
+cudaError_t knn_pack(const double* train, int64_t n, int d, int dp, float* train32, float* tnorm_max,
+                     cudaStream_t st) {
+  cudaMemsetAsync(tnorm_max, 0, sizeof(float), st);
+  if (n > 0) knn_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(train, n, d, dp, train32, tnorm_max);
+  return cudaGetLastError();
+}
+
+cudaError_t knn_scan(int dp, const float* train32, int64_t n, const double* q, int64_t m, int d,
+                     int* cand_idx, float* cand_worst, float* qnorm, cudaStream_t st) {
+  if (m == 0) return cudaSuccess;
+  if (dp == 16) {
+    constexpr int QPT = 2;
+    const unsigned grid = (unsigned)((m + (int64_t)kScanThreads * QPT - 1) / ((int64_t)kScanThreads * QPT));
+    knn_scan_kernel<16, QPT><<<grid, kScanThreads, 0, st>>>(train32, n, q, m, d, cand_idx, cand_worst, qnorm);
+  } else if (dp == 32) {
+    const unsigned grid = (unsigned)((m + kScanThreads - 1) / kScanThreads);
+    knn_scan_kernel<32, 1><<<grid, kScanThreads, 0, st>>>(train32, n, q, m, d, cand_idx, cand_worst, qnorm);
+  } else {
+    const unsigned grid = (unsigned)((m + kScanThreads - 1) / kScanThreads);
+    knn_scan_kernel<64, 1><<<grid, kScanThreads, 0, st>>>(train32, n, q, m, d, cand_idx, cand_worst, qnorm);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t knn_rerank(const double* train, const float* train32, int dp, int64_t n, const double* q,
+                       int64_t m, int d, int k, int64_t index_base, const int32_t* labels,
+                       const int* cand_idx, const float* cand_worst, const float* qnorm,
+                       float tnorm_max_host, int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label,
+                       int32_t* redo_list, int32_t* redo_count, cudaStream_t st) {
+  if (m == 0) return cudaSuccess;
+  cudaMemsetAsync(redo_count, 0, sizeof(int32_t), st);
+  knn_rerank_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(
+      train, train32, dp, n, q, m, d, k, index_base, labels, cand_idx, cand_worst, qnorm, tnorm_max_host,
+      nbr_idx, nbr_sqdist, nbr_label, redo_list, redo_count);
+  return cudaGetLastError();
+}
+
+cudaError_t knn_redo_all(int32_t* redo_list, int32_t* redo_count, int64_t m, cudaStream_t st) {
+  if (m == 0) return cudaSuccess;
+  knn_iota_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(redo_list, redo_count, m);
+  return cudaGetLastError();
+}
+
+cudaError_t knn_rescan(const double* train, int64_t n, const double* q, int d, int k, int64_t index_base,
+                       const int32_t* labels, const int32_t* redo_list, const int32_t* redo_count,
+                       int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label, int sm_count,
+                       cudaStream_t st) {
+  knn_rescan_kernel<<<sm_count * 2, 256, 0, st>>>(train, n, q, d, k, index_base, labels, redo_list,
+                                                 redo_count, nbr_idx, nbr_sqdist, nbr_label);
+  return cudaGetLastError();
+}
+
+cudaError_t knn_vote(const int32_t* nbr_label, int64_t m, int k, int32_t* out, cudaStream_t st) {
+  if (m == 0) return cudaSuccess;
+  knn_vote_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(nbr_label, m, k, out);
+  return cudaGetLastError();
+}
+
+cudaError_t knn_merge_vote(const double* cd, const int64_t* ci, const int32_t* cl, int r, int64_t m,
+                           int k, int32_t* labels_out, int64_t* idx_out, double* dist_out,
+                           cudaStream_t st) {
+  if (m == 0) return cudaSuccess;
+  knn_merge_vote_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(cd, ci, cl, r, m, k, labels_out,
+                                                                    idx_out, dist_out);
+  return cudaGetLastError();
+}
+
+}  // namespace dsp

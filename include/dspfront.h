@@ -41,7 +41,7 @@ typedef enum {
  * src/audio_processing.py:31-44, plus the float arrays the per-call API takes) */
 typedef enum {
   DSP_S16 = 0, /* 16-bit PCM, value/32768.0      (:35-38) */
-  DSP_U8 = 1,  /* 8-bit PCM, (value-128)/128.0   (:31-34) */
+  DSP_U8 = 1,  /* 8-bit PCM, uint8(value-128)/128.0: the reference's uint8 subtraction wraps (:31-34) */
   DSP_F32 = 2, /* float samples, used as-is (widened to float64) */
   DSP_F64 = 3  /* float64 samples, used as-is */
 } dsp_dtype;
@@ -96,8 +96,10 @@ const char* dsp_last_error(void);
 /* device: CUDA ordinal.  Fails with DSP_ERR_NO_DEVICE when there is no GPU. */
 int dsp_create(int device, dsp_context** out);
 int dsp_destroy(dsp_context* ctx);
-/* Use an existing CUDA stream (e.g. torch's) for all device entry points; 0 restores the context's own. */
+/* Enqueue all device entry points on an existing CUDA stream (e.g. torch's current stream; a NULL
+ * handle is CUDA's legacy default stream).  dsp_use_own_stream() returns to the context's own. */
 int dsp_set_stream(dsp_context* ctx, void* cuda_stream);
+int dsp_use_own_stream(dsp_context* ctx);
 int dsp_sync(dsp_context* ctx);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t dsp_launch_count(dsp_context* ctx);

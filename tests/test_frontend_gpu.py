@@ -1,0 +1,226 @@
+"""GPU parity of the front end (through the C ABI) against the reference's golden
+fixtures and the NumPy oracle.
+
+Bars (BASELINE.json north_star): bit-exact zero-crossing counts, endpoint indices and frame
+counts; energy / magnitude within 1e-5 relative (fp32 feature pass); float64 EPD energies of
+the fast kernel within 1e-12 relative; everything the float64 replay kernel produces in
+float64 is bit-identical to NumPy.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_names, golden_pcm
+
+pytestmark = pytest.mark.gpu
+
+RTOL_F32 = 1e-5          # north-star tolerance for energy / magnitude
+RTOL_EPD = 1e-12         # fast-kernel float64 EPD energies (exact-integer formulation)
+
+
+def pack(utts):
+    lens = np.array([len(u) for u in utts], dtype=np.int64)
+    off = np.zeros(len(utts) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    return np.concatenate(utts) if len(utts) else np.zeros(0, np.int16), off
+
+
+def assert_stats_close(got, ref, seqs):
+    """mean / max / median: 1e-5 relative; std / min: 1e-5 of the sequence's scale (a std that is
+    tiny next to the mean cannot be held to a relative bound by any fp32 per-frame pass)."""
+    for s, key in enumerate(("energy", "magnitude", "zcr")):
+        scale = max(float(np.max(np.abs(seqs[key]))), 1e-300)
+        g, r = got[5 * s:5 * s + 5].astype(np.float64), ref[5 * s:5 * s + 5]
+        assert np.allclose(g, r, rtol=2 * RTOL_F32, atol=2 * RTOL_F32 * scale), (key, g, r)
+
+
+def check_against_golden(g, res, names, ci, win, rtol_feat):
+    for b, name in enumerate(names):
+        base = f"fe/{ci}/{name}/{win}"
+        err = int(g[base + "/error"])
+        st = int(res.status[b]) & 0xff
+        if err:
+            assert st != 0, (base, st)
+            continue
+        assert st == 0, (base, st)
+        assert int(res.start[b]) == int(g[f"epd/{ci}/{name}/start"]), base
+        assert int(res.end[b]) == int(g[f"epd/{ci}/{name}/end"]), base
+        el, zl = res.epd_lists(b)
+        rel, rzl = g[f"epd/{ci}/{name}/energy_list"], g[f"epd/{ci}/{name}/zcr_list"]
+        assert len(el) == len(rel)
+        assert np.array_equal(zl.astype(np.float64), rzl), base
+        assert np.allclose(el, rel, rtol=RTOL_EPD, atol=0), (base, np.max(np.abs(el - rel) / np.maximum(rel, 1e-300)))
+        assert int(res.n_frames[b]) == int(g[base + "/n_frames"]), base
+        e, m, z = res.frames(b)
+        assert np.array_equal(z.astype(np.float64), g[base + "/zcr"]), base
+        assert np.allclose(e, g[base + "/energy"], rtol=rtol_feat, atol=0), base
+        assert np.allclose(m, g[base + "/magnitude"], rtol=rtol_feat, atol=0), base
+        assert_stats_close(res.stats[b], g[base + "/stats"],
+                           {"energy": g[base + "/energy"], "magnitude": g[base + "/magnitude"], "zcr": g[base + "/zcr"]})
+
+
+@pytest.mark.parametrize("ci", range(7))
+@pytest.mark.parametrize("win", ["rectangular", "hamming", "hanning"])
+def test_fast_kernel_matches_reference_fixtures(ctx, golden_fe, ci, win):
+    from dsp_audioreclabs_b200 import batch
+    g = golden_fe
+    fl, fs = (int(v) for v in g["configs"][ci])
+    names = golden_names(g)
+    samples, off = pack([golden_pcm(g, n) for n in names])
+    res = batch.frontend_batch(samples, off, fl, fs, win, emit_epd_lists=True, ctx=ctx)
+    check_against_golden(g, res, names, ci, win, RTOL_F32)
+
+
+@pytest.mark.parametrize("ci", [0, 1, 3])
+@pytest.mark.parametrize("win", ["rectangular", "hamming", "hanning"])
+def test_float64_replay_kernel_matches_reference_fixtures(ctx, golden_fe, ci, win):
+    from dsp_audioreclabs_b200 import batch
+    g = golden_fe
+    fl, fs = (int(v) for v in g["configs"][ci])
+    names = golden_names(g)
+    samples, off = pack([golden_pcm(g, n) for n in names])
+    res = batch.frontend_batch(samples, off, fl, fs, win, emit_epd_lists=True, force_exact=True, ctx=ctx)
+    assert np.all((res.status & 0x100) != 0)
+    check_against_golden(g, res, names, ci, win, 2e-7)       # float32 storage of float64-exact values
+    for b, name in enumerate(names):                          # float64 outputs are bit-identical
+        el, _ = res.epd_lists(b)
+        assert np.array_equal(el, g[f"epd/{ci}/{name}/energy_list"]), name
+
+
+def test_no_endpoint_detection_zero_padded_last_frame(ctx, golden_fe):
+    from dsp_audioreclabs_b200 import batch
+    g = golden_fe
+    for ci in range(4):
+        fl, fs = (int(v) for v in g["configs"][ci])
+        names = ["syn0", "syn3", "short100", "len256"]
+        samples, off = pack([g[f"pcm/{n}"] for n in names])
+        for win in g["windows"]:
+            for exact in (False, True):
+                res = batch.frontend_batch(samples, off, fl, fs, str(win), do_endpoint_detection=False,
+                                           force_exact=exact, ctx=ctx)
+                for b, name in enumerate(names):
+                    base = f"noepd/{ci}/{name}/{win}"
+                    assert int(res.start[b]) == 0 and int(res.end[b]) == len(g[f"pcm/{name}"])
+                    assert int(res.n_frames[b]) == int(g[base + "/n_frames"])
+                    e, m, z = res.frames(b)
+                    assert np.array_equal(z.astype(np.float64), g[base + "/zcr"]), (base, exact)
+                    assert np.allclose(e, g[base + "/energy"], rtol=RTOL_F32, atol=0)
+                    assert np.allclose(m, g[base + "/magnitude"], rtol=RTOL_F32, atol=0)
+
+
+@pytest.mark.parametrize("fl,fs", [(256, 128), (1102, 441)])
+def test_batch_against_numpy_oracle(ctx, fl, fs):
+    """Seeded synthetic utterances (SURVEY.md 8(d) generator), ragged lengths, three windows."""
+    from dsp_audioreclabs_b200 import batch
+    from oracle import frontend_oracle as fo, synth
+    nb = 96
+    lens = synth.ragged_lengths(nb, 0.5, 1.2, seed=5)
+    samples, off = synth.batch_pcm(nb, seed0=4321, lengths=lens)
+    trimmed = 0
+    for win in ("rectangular", "hamming", "hanning"):
+        res = batch.frontend_batch(samples, off, fl, fs, win, emit_epd_lists=True, ctx=ctx)
+        ref = fo.frontend_batch(samples, off, fl, fs, win)
+        for b in range(nb):
+            r = ref[b]
+            assert res.ok(b) and r is not None
+            assert (int(res.start[b]), int(res.end[b])) == (r["start"], r["end"]), b
+            trimmed += r["start"] > 0 and r["end"] < lens[b]
+            el, zl = res.epd_lists(b)
+            assert np.array_equal(zl.astype(np.float64), r["zcr_list"])
+            assert np.allclose(el, r["energy_list"], rtol=RTOL_EPD, atol=0)
+            e, m, z = res.frames(b)
+            assert len(e) == r["n_frames"]
+            assert np.array_equal(z.astype(np.float64), r["zcr"])
+            assert np.allclose(e, r["energy"], rtol=RTOL_F32, atol=0)
+            assert np.allclose(m, r["magnitude"], rtol=RTOL_F32, atol=0)
+            assert_stats_close(res.stats[b], r["stats"], r)
+    assert trimmed > nb            # the generator yields real endpoints, not whole clips
+
+
+def test_misaligned_and_odd_offsets(ctx):
+    """Utterances that start at odd sample offsets take the non-TMA load path; results must not
+    depend on where an utterance sits in the buffer."""
+    from dsp_audioreclabs_b200 import batch
+    from oracle import synth
+    utts = [synth.utterance_pcm(50 + i, n, seed0=9) for i, n in enumerate([9001, 12345, 7777, 15001, 8192])]
+    a_s, a_o = pack(utts)
+    ra = batch.frontend_batch(a_s, a_o, 256, 128, "hamming", emit_epd_lists=True, ctx=ctx)
+    # same utterances behind a 3-sample pad and in reverse order
+    rev = utts[::-1]
+    b_s, b_o = pack(rev)
+    b_s = np.concatenate([np.zeros(3, np.int16), b_s])
+    b_o = b_o + 3
+    rb = batch.frontend_batch(b_s, b_o, 256, 128, "hamming", emit_epd_lists=True, ctx=ctx)
+    for i in range(len(utts)):
+        j = len(utts) - 1 - i
+        assert (ra.start[i], ra.end[i], ra.n_frames[i]) == (rb.start[j], rb.end[j], rb.n_frames[j])
+        for x, y in zip(ra.frames(i), rb.frames(j)):
+            assert np.array_equal(x, y)
+        for x, y in zip(ra.epd_lists(i), rb.epd_lists(j)):
+            assert np.array_equal(x, y)
+        assert np.array_equal(ra.stats[i], rb.stats[j])
+
+
+def test_empty_and_degenerate_inputs(ctx):
+    from dsp_audioreclabs_b200 import batch
+    z = np.zeros(0, np.int16)
+    res = batch.frontend_batch(z, np.array([0]), 256, 128, ctx=ctx)      # empty batch
+    assert len(res) == 0
+    # a zero-length utterance between two real ones: the reference raises ValueError for it
+    from oracle import synth
+    u = synth.utterance_pcm(1, 5000)
+    samples = np.concatenate([u, u])
+    off = np.array([0, 5000, 5000, 10000])
+    for exact in (False, True):
+        res = batch.frontend_batch(samples, off, 256, 128, force_exact=exact, ctx=ctx)
+        assert res.ok(0) and res.ok(2) and not res.ok(1)
+        assert int(res.n_frames[1]) == 0
+        assert np.array_equal(res.stats[0], res.stats[2])
+    with pytest.raises(ValueError):
+        batch.frontend_batch(u, np.array([0, 5000]), 256, 128, "blackman", ctx=ctx)
+    with pytest.raises(ValueError):
+        batch.frontend_batch(u, np.array([0, 5000]), 0, 128, ctx=ctx)
+
+
+def test_per_call_surface_float64(ctx, golden_fe):
+    """remove_dc / normalize / preprocess / endpoint_detection / frame_signal /
+    extract_frame_features on a non-PCM float64 signal: bit-identical to NumPy except the
+    window's cos() (last-ulp) in frame_signal."""
+    from dsp_audioreclabs_b200 import batch
+    from oracle import frontend_oracle as fo
+    g = golden_fe
+    x = g["float/x"]
+    assert np.array_equal(batch.preprocess(x, 0, ctx=ctx), x - np.mean(x))
+    assert np.array_equal(batch.preprocess(x, 1, ctx=ctx), fo.normalize_audio(x))
+    z = batch.preprocess(x, 2, ctx=ctx)
+    assert np.array_equal(z, g["float/preprocessed"])
+    s, e, el, zl = batch.endpoint_detection(z, 256, 128, ctx=ctx)
+    assert (s, e) == (int(g["float/start"]), int(g["float/end"]))
+    assert np.array_equal(el, g["float/energy_list"]) and np.array_equal(zl, g["float/zcr_list"])
+    fr = batch.frame_signal(z[s:e], 256, 128, "hamming", ctx=ctx)
+    assert fr.shape == g["float/frames"].shape
+    assert np.allclose(fr, g["float/frames"], rtol=1e-14, atol=1e-17)
+    en, mg, zc, st = batch.frame_features(g["float/frames"], ctx=ctx)
+    assert np.array_equal(en, g["float/energy"]) and np.array_equal(mg, g["float/magnitude"])
+    assert np.array_equal(zc, g["float/zcr"])
+    assert np.array_equal(st, g["float/stats"])
+    assert np.array_equal(batch.sequence_stats(g["float/energy"], ctx=ctx), g["float/stats"][:5])
+    for win in g["windows"]:
+        for n in (1, 2, 3, 64, 255, 256, 1102):
+            assert np.allclose(batch.window(str(win), n), g[f"window/{win}/{n}"], rtol=1e-14, atol=1e-16)
+    # a constant float signal: the result hinges on NumPy's exact summation order
+    c = np.full(5000, 0.1)
+    assert np.array_equal(batch.preprocess(c, 2, ctx=ctx), fo.preprocess(c))
+    with pytest.raises(ValueError):
+        batch.frame_features(np.zeros((0, 256)), ctx=ctx)
+
+
+def test_wav_encodings_through_the_batch_api(ctx, golden_fe):
+    """8-bit and stereo PCM (load_wav's other branches) go through the float64 replay kernel."""
+    from dsp_audioreclabs_b200 import batch
+    g = golden_fe
+    for key in ("m16", "s16", "m8", "s8"):
+        raw = g[f"wav/{key}/raw"]
+        width, ch = (int(v) for v in g[f"wav/{key}/width_channels"])
+        res = batch.frontend_batch(raw, np.array([0, raw.size]), 1102, 441, "hamming", channels=ch, ctx=ctx)
+        assert [int(res.start[0]), int(res.end[0])] == list(g[f"wav/{key}/start_end"]), key
+        assert np.allclose(res.stats[0], g[f"wav/{key}/stats"], rtol=2e-5, atol=0), key
