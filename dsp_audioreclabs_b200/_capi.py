@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdspfront.so")
+LIB_PATH = os.environ.get("DSP_LIB_PATH") or os.path.join(_HERE, "libdspfront.so")   # override: tuning builds only
 
 DSP_S16, DSP_U8, DSP_F32, DSP_F64 = 0, 1, 2, 3
 WINDOW_IDS = {"rectangular": 0, "hamming": 1, "hanning": 2}

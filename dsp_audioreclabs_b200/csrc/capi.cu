@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -101,6 +102,7 @@ struct dsp_context {
   DevBuf counters;   // [0] work counter (u32)  [1] flag count (i32)
   DevBuf flag_list, zbuf, seqbuf;
   size_t occ_smem = 0;
+  int tma_chunk = 4096;         // bytes per bulk copy; DSP_TMA_CHUNK overrides (tuning knob)
   int occ = 0;
   Slot slot[2];
   DevBuf tmp[10];
@@ -241,6 +243,7 @@ int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_
   a.hr = p->energy_high_ratio; a.lr = p->energy_low_ratio; a.zr = p->zcr_threshold_ratio;
   a.win_f32 = c->win32.as<float>();
   a.cap_samples = cap_samples; a.cap_frames = (int)cap_frames64;
+  a.tma_chunk = c->tma_chunk;
   a.work_counter = c->counters.as<unsigned int>();
   a.flag_count = c->counters.as<int32_t>() + 1;
   a.flag_list = c->flag_list.as<int32_t>();
@@ -295,6 +298,7 @@ int dsp_create(int device, dsp_context** out) {
   CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
   c->stream = c->own;
+  if (const char* e = std::getenv("DSP_TMA_CHUNK")) { int v = std::atoi(e); if (v >= 16 && v % 16 == 0) c->tma_chunk = v; }
   for (auto& s : c->slot) {
     CU(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming));

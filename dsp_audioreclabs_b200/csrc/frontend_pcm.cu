@@ -6,18 +6,20 @@
 // overlap and the reference's two framing passes cost no extra HBM traffic:
 //
 //   P1  sum / min / max of the PCM codes            -> DC (exact rational S/N), peak
-//   P2  per 64-sample group: sum d, sum d^2 (exact integers, d = k - round(S/N)) and one
-//       sign bit per sample                          -> every EPD frame from group sums
-//   P3  endpoint decision: 90th percentile by radix select, thresholds, six ballot-style
-//       searches; a certified-margin test flags utterances for the float64 replay kernel
-//   P4  windowed energy / magnitude over the trimmed frames (fp32 FMA, 8 lanes per frame),
-//       zero-crossing counts by popcount over the sign bits
+//   P2  per 64-sample group: sum d, sum d^2 (exact integers, d = k - thr with
+//       thr = floor(S/N)+1, so "sample above the mean" is just d >= 0) and one sign bit per
+//       sample                                       -> every EPD frame from group sums
+//   P3  endpoint decision: 90th percentile by a warp-level radix select, thresholds, six
+//       ballot-style searches; a certified-margin test flags utterances for the float64 replay
+//   P4  windowed energy / magnitude over the trimmed frames (fp32 FMA); for hop 128 / length
+//       256 a sample-stationary chain (each sample converted once, window in registers),
+//       otherwise 8 lanes per frame; zero-crossing counts by popcount over the sign bits
 //   P5  mean / std / max / min / median of the three sequences, one warp per sequence
 //
 // Exactness (DESIGN.md "numerics"): with PCM input the reference's float64 values are
 // x_i = k_i/32768, so sign(x_i - mean) == sign(N*k_i - S) and sum((x_i-mean)/peak)^2 over a
 // frame equals (sum d^2 - 2*phi*sum d + fl*phi^2) * (N/M)^2 with integers N, S, M and
-// phi = S/N - round(S/N): zero-crossing counts are exact and EPD energies are within a few
+// phi = S/N - thr in [-1, 0): zero-crossing counts are exact and EPD energies are within a few
 // ulp of the real-number value.  Threshold comparisons closer than a rigorous bound on the
 // reference's own rounding are not decided here but replayed in float64 NumPy order.
 //
@@ -29,11 +31,11 @@ namespace dsp {
 namespace {
 
 constexpr int kGroup = 64;          // samples per group-sum record
-constexpr int kLanesPerFrame = 8;   // P4: lanes cooperating on one frame
-constexpr int kTmaChunk = 16384;    // bytes per bulk copy
+constexpr int kLanesPerFrame = 8;   // generic P4: lanes cooperating on one frame
+constexpr int kWarps = kPcmThreads / 32;
 
 struct SmemLayout {
-  int samples, bits, g2, g1, e, z, win, hist, sh, misc, total;
+  int samples, bits, g2, g1, e, z, win, hist, cand, sh, misc, total;
 };
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
@@ -53,6 +55,7 @@ __host__ __device__ inline SmemLayout make_layout(int cap_samples, int cap_frame
   L.z = o;       o += align16(4 * cap_frames);
   L.win = o;     o += align16(4 * fl);
   L.hist = o;    o += 3 * 256 * 4;
+  L.cand = o;    o += 3 * 32 * 8;
   L.sh = o;      o += 64 * 8;
   L.misc = o;    o += 256;
   L.total = o;
@@ -97,12 +100,23 @@ __device__ __forceinline__ int bit_at(const uint32_t* bits, int i) { return (bit
 // number of i in [p, q-1) with bit[i] != bit[i+1]  (sign changes among samples p..q-1)
 __device__ __forceinline__ int count_changes(const uint32_t* bits, int p, int q) {
   if (q - p < 2) return 0;
-  const int last = q - 2;  // last pair start
   int c = 0;
+  if (((p | q) & 31) == 0) {               // word-aligned frame: no edge masks except the last pair
+    const int w0 = p >> 5, w1 = (q >> 5) - 1;
+    uint32_t cur = bits[w0];
+    for (int w = w0; w < w1; ++w) {
+      const uint32_t nxt = bits[w + 1];
+      c += __popc(cur ^ __funnelshift_r(cur, nxt, 1));
+      cur = nxt;
+    }
+    c += __popc((cur ^ (cur >> 1)) & 0x7fffffffu);
+    return c;
+  }
+  const int last = q - 2;  // last pair start
   const int w0 = p >> 5, w1 = last >> 5;
   for (int w = w0; w <= w1; ++w) {
     const uint32_t cur = bits[w], nxt = bits[w + 1];
-    uint32_t x = cur ^ ((cur >> 1) | (nxt << 31));
+    uint32_t x = cur ^ __funnelshift_r(cur, nxt, 1);
     if (w == w0) x &= 0xffffffffu << (p & 31);
     if (w == w1) x &= 0xffffffffu >> (31 - (last & 31));
     c += __popc(x);
@@ -131,13 +145,89 @@ __device__ __forceinline__ int frame_zcr(const uint32_t* bits, int p, int valid,
 __device__ __forceinline__ int sext16(uint32_t w) { return (int)(short)(w & 0xffffu); }
 
 struct UttConst {
-  int mu_int;      // round(S/N)
-  int c;           // sample is positive iff (k - mu_int) > c
-  float phi;       // S/N - mu_int
+  int thr;         // floor(S/N) + 1: sample is above the mean iff k >= thr
+  float phi;       // S/N - thr, in [-1, 0)
   double phi_d;
   double inv_m;    // N/M (1 when the signal is constant)
   double mu;       // S/N
 };
+
+// ---------------------------------------------------------------------------------------
+// Warp-level order statistics: the keys of rank r and r+1 (ascending, 0-based) among n
+// 64-bit monotone keys.  MSD radix select, 8 bits per pass, that stops as soon as at most 32
+// candidates share the prefix and finishes by ranking those in registers.  One warp; `hist`
+// holds 256 ints and `cand` 32 keys of that warp's shared memory.
+// ---------------------------------------------------------------------------------------
+template <class Get>
+__device__ void warp_select_pair(Get get, int n, int r, int* hist, unsigned long long* cand,
+                                 uint64_t* k_lo, uint64_t* k_hi) {
+  const int lane = threadIdx.x & 31;
+  uint64_t prefix = 0, mask = 0;
+  int rank = r, cnt = n;
+  for (int shift = 56; shift >= 0 && cnt > 32; shift -= 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hist[lane * 8 + j] = 0;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      const uint64_t k = get(i);
+      if ((k & mask) == prefix) atomicAdd(&hist[(int)((k >> shift) & 0xff)], 1);
+    }
+    __syncwarp();
+    int c[8], tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { c[j] = hist[lane * 8 + j]; tot += c[j]; }
+    int incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    int run = incl - tot, digit = -1, newrank = 0, newcnt = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (digit < 0 && rank >= run && rank < run + c[j]) { digit = lane * 8 + j; newrank = rank - run; newcnt = c[j]; }
+      run += c[j];
+    }
+    const int src = __ffs(__ballot_sync(0xffffffffu, digit >= 0)) - 1;
+    digit = __shfl_sync(0xffffffffu, digit, src);
+    rank = __shfl_sync(0xffffffffu, newrank, src);
+    cnt = __shfl_sync(0xffffffffu, newcnt, src);
+    prefix |= (uint64_t)digit << shift;
+    mask |= 0xffull << shift;
+    __syncwarp();
+  }
+  uint64_t sel, sel2;
+  bool have2 = false;
+  if (cnt > 32) {            // all 64 bits consumed: every remaining candidate equals the prefix
+    sel = prefix; sel2 = prefix; have2 = (rank + 1 < cnt);
+  } else {
+    // gather the (<= 32) candidates, one per lane, then rank them in registers
+    if (lane == 0) hist[0] = 0;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+      const uint64_t k = get(i);
+      if ((k & mask) == prefix) cand[atomicAdd(&hist[0], 1)] = k;
+    }
+    __syncwarp();
+    const uint64_t mine = lane < cnt ? cand[lane] : ~0ull;
+    int below = 0;
+    for (int j = 0; j < cnt; ++j) {
+      const uint64_t o = __shfl_sync(0xffffffffu, mine, j);
+      below += (o < mine) || (o == mine && j < lane);
+    }
+    const unsigned m1 = __ballot_sync(0xffffffffu, lane < cnt && below == rank);
+    const unsigned m2 = __ballot_sync(0xffffffffu, lane < cnt && below == rank + 1);
+    sel = __shfl_sync(0xffffffffu, mine, __ffs(m1) - 1);
+    have2 = (m2 != 0);
+    sel2 = have2 ? __shfl_sync(0xffffffffu, mine, __ffs(m2) - 1) : sel;
+    __syncwarp();
+  }
+  if (!have2) {              // rank r+1 lies outside the candidate set: smallest key above sel
+    unsigned long long nxt = ~0ull;
+    for (int i = lane; i < n; i += 32) { const uint64_t k = get(i); if (k > sel && k < nxt) nxt = k; }
+    nxt = warp_reduce(nxt, OpMinU64());
+    sel2 = (nxt == ~0ull) ? sel : (uint64_t)nxt;
+  }
+  *k_lo = sel;
+  *k_hi = sel2;
+}
 
 }  // namespace
 
@@ -160,6 +250,7 @@ frontend_pcm_kernel(const PcmArgs a) {
   int* s_z = reinterpret_cast<int*>(smem + L.z);
   float* s_win = reinterpret_cast<float*>(smem + L.win);
   int* s_hist = reinterpret_cast<int*>(smem + L.hist);
+  unsigned long long* s_cand = reinterpret_cast<unsigned long long*>(smem + L.cand);
   unsigned long long* s_sh = reinterpret_cast<unsigned long long*>(smem + L.sh);
   // misc block: [0] mbarrier, then scalars
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L.misc);
@@ -167,6 +258,7 @@ frontend_pcm_kernel(const PcmArgs a) {
   double* s_dbl = reinterpret_cast<double*>(smem + L.misc + 128);  // 16 doubles
 
   const int tid = threadIdx.x;
+  const int lane = tid & 31, wid = tid >> 5;
   const int fl = a.fl, fs = a.fs;
   const bool hann = (a.window == DSP_WIN_HANNING);
 
@@ -180,7 +272,21 @@ frontend_pcm_kernel(const PcmArgs a) {
   uint32_t parity = 0;
   int u = s_int[0];
 
-  // issue the load of utterance `uu` (thread-block uniform); returns true when TMA was used
+  // window coefficients of the hop-128 / length-256 chain (P4 fast path): lane owns samples
+  // 8*(lane&15) .. +8 of every hop block; c = 0 is the first half of a frame, c = 1 the second
+  const bool chain_cfg = (fs == 128 && fl == 256);
+  float cw[2][8], cw2[2][8];
+  if (chain_cfg) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int s = 0; s < 8; ++s) {
+        const float w = s_win[c * 128 + 8 * (lane & 15) + s];
+        cw[c][s] = w; cw2[c][s] = w * w;
+      }
+  }
+
+  // issue the load of utterance `uu` (thread-block uniform)
   auto issue_load = [&](int uu) {
     const int64_t off = a.offsets[uu];
     const int n = (int)(a.offsets[uu + 1] - off);
@@ -192,8 +298,9 @@ frontend_pcm_kernel(const PcmArgs a) {
         if (bytes > 0) {
           if (tid == 0) { fence_proxy_async(); mbar_expect_tx(s_bar, bytes); }
           __syncwarp();
-          for (uint32_t o = (uint32_t)tid * kTmaChunk; o < bytes; o += 32u * kTmaChunk) {
-            const uint32_t sz = min((uint32_t)kTmaChunk, bytes - o);
+          const uint32_t chunk = (uint32_t)a.tma_chunk;
+          for (uint32_t o = (uint32_t)tid * chunk; o < bytes; o += 32u * chunk) {
+            const uint32_t sz = min(chunk, bytes - o);
             bulk_g2s(reinterpret_cast<unsigned char*>(s_x) + o, reinterpret_cast<const unsigned char*>(src) + o, sz, s_bar);
           }
         }
@@ -242,18 +349,22 @@ frontend_pcm_kernel(const PcmArgs a) {
       }
       int mn = min(sext16(mn2), (int)mn2 >> 16), mx = max(sext16(mx2), (int)mx2 >> 16);
       if (tid < (n & 7)) { const int k = s_x[(nvec << 3) + tid]; sum += k; mn = min(mn, k); mx = max(mx, k); }
-      long long S = block_reduce<long long>((long long)sum, OpAddLL(), 0ll, reinterpret_cast<long long*>(s_sh));
-      mn = block_reduce<int>(mn, OpMinI(), 32767, reinterpret_cast<int*>(s_sh));
-      mx = block_reduce<int>(mx, OpMaxI(), -32768, reinterpret_cast<int*>(s_sh));
+      // one barrier: per-warp partials, then every thread of warp 0 combines them
+      sum = warp_reduce(sum, OpAddI());     // |sum| <= 32 lanes * 173 samples * 2^15 < 2^31
+      mn = warp_reduce(mn, OpMinI());
+      mx = warp_reduce(mx, OpMaxI());
+      int* part = reinterpret_cast<int*>(s_sh);
+      if (lane == 0) { part[wid] = sum; part[kWarps + wid] = mn; part[2 * kWarps + wid] = mx; }
+      __syncthreads();
       if (tid == 0) {
+        long long S = 0; int gmn = 32767, gmx = -32768;
+        for (int w = 0; w < kWarps; ++w) { S += part[w]; gmn = min(gmn, part[kWarps + w]); gmx = max(gmx, part[2 * kWarps + w]); }
         const long long N = n > 0 ? n : 1;
-        // mu_int = round-half-up(S/N) by floor division
-        long long num = 2 * S + N, den = 2 * N;
-        long long q = num / den; if ((num % den) != 0 && ((num < 0) != (den < 0))) --q;
-        const long long R = S - N * q;            // |R| <= N/2
-        const long long M = max(N * (long long)mx - S, S - N * (long long)mn);
-        s_int[1] = (int)q;
-        s_int[2] = (R < 0) ? -1 : 0;
+        long long q = S / N; if ((S % N) != 0 && (S < 0)) --q;      // floor(S/N)
+        const long long thr = q + 1;
+        const long long R = S - N * thr;                             // in [-N, 0)
+        const long long M = max(N * (long long)gmx - S, S - N * (long long)gmn);
+        s_int[1] = (int)thr;
         s_dbl[0] = (double)R / (double)N;
         s_dbl[1] = (M > 0) ? (double)N / (double)M : 1.0;
         s_dbl[2] = (double)S / (double)N;
@@ -264,44 +375,52 @@ frontend_pcm_kernel(const PcmArgs a) {
       __syncthreads();
     }
     UttConst uc;
-    uc.mu_int = s_int[1]; uc.c = s_int[2]; uc.phi_d = s_dbl[0]; uc.phi = (float)uc.phi_d;
+    uc.thr = s_int[1]; uc.phi_d = s_dbl[0]; uc.phi = (float)uc.phi_d;
     uc.inv_m = s_dbl[1]; uc.mu = s_dbl[2];
 
     // =========================== P2: group sums + sign bits ==========================
     const int ng = (n + kGroup - 1) / kGroup;
-    for (int g = tid; g < ng; g += kPcmThreads) {
-      int s1 = 0;
-      unsigned long long s2 = 0;
-      uint32_t b0 = 0, b1 = 0;
-      const int base = g * kGroup;
-      if (base + kGroup <= n) {
-        const int4* gv = reinterpret_cast<const int4*>(s_x + base);
+    {
+      const int rot = tid & 7;               // == g & 7 for every group this thread owns
+      for (int g = tid; g < ng; g += kPcmThreads) {
+        int s1 = 0;
+        unsigned long long s2 = 0;
+        uint32_t b0, b1;
+        const int base = g * kGroup;
+        if (base + kGroup <= n) {
+          const unsigned char* gp = reinterpret_cast<const unsigned char*>(s_x + base);
+          uint32_t nlo = 0, nhi = 0;         // "below the mean" bits, MSB-first, in processing order
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int vi = (j + g) & 7;             // rotated: conflict-free 16-byte accesses
-          const int4 q = gv[vi];
-          const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
-          uint32_t byte = 0;
+          for (int j = 0; j < 8; ++j) {
+            const int vi = (j + rot) & 7;    // rotated start: conflict-free 16-byte accesses
+            const int4 q = *reinterpret_cast<const int4*>(gp + 16 * vi);
+            const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int lo = sext16(w[k]) - uc.mu_int, hi = ((int)w[k] >> 16) - uc.mu_int;
-            s1 += lo + hi;
-            s2 += (unsigned long long)((long long)lo * lo) + (unsigned long long)((long long)hi * hi);
-            byte |= ((uint32_t)(uc.c - lo) >> 31) << (2 * k);
-            byte |= ((uint32_t)(uc.c - hi) >> 31) << (2 * k + 1);
+            for (int k = 0; k < 4; ++k) {
+              const int lo = sext16(w[k]) - uc.thr, hi = ((int)w[k] >> 16) - uc.thr;
+              s1 += lo + hi;
+              s2 += (unsigned long long)((long long)lo * lo) + (unsigned long long)((long long)hi * hi);
+              if (j < 4) { nhi = __funnelshift_l((uint32_t)lo, nhi, 1); nhi = __funnelshift_l((uint32_t)hi, nhi, 1); }
+              else       { nlo = __funnelshift_l((uint32_t)lo, nlo, 1); nlo = __funnelshift_l((uint32_t)hi, nlo, 1); }
+            }
           }
-          if (vi < 4) b0 |= byte << (8 * vi); else b1 |= byte << (8 * (vi - 4));
+          // stream (nhi:nlo) holds vector rot first (at the top); reverse to LSB-first, undo the rotation
+          const unsigned long long y = ((unsigned long long)__brev(nlo) << 32) | (unsigned long long)__brev(nhi);
+          const int sh = 8 * rot;
+          const unsigned long long z = sh ? ((y << sh) | (y >> (64 - sh))) : y;
+          b0 = ~(uint32_t)z; b1 = ~(uint32_t)(z >> 32);
+        } else {
+          b0 = 0; b1 = 0;
+          for (int i = 0; i < kGroup && base + i < n; ++i) {
+            const int d = (int)s_x[base + i] - uc.thr;
+            s1 += d; s2 += (unsigned long long)((long long)d * d);
+            const uint32_t bit = (d >= 0);
+            if (i < 32) b0 |= bit << i; else b1 |= bit << (i - 32);
+          }
         }
-      } else {
-        for (int i = 0; i < kGroup && base + i < n; ++i) {
-          const int d = (int)s_x[base + i] - uc.mu_int;
-          s1 += d; s2 += (unsigned long long)((long long)d * d);
-          const uint32_t bit = (uint32_t)(uc.c - d) >> 31;
-          if (i < 32) b0 |= bit << i; else b1 |= bit << (i - 32);
-        }
+        s_g1[g] = s1; s_g2[g] = s2;
+        s_bits[2 * g] = b0; s_bits[2 * g + 1] = b1;
       }
-      s_g1[g] = s1; s_g2[g] = s2;
-      s_bits[2 * g] = b0; s_bits[2 * g + 1] = b1;
     }
     if (tid < 4) s_bits[2 * ng + tid] = 0;
     __syncthreads();
@@ -309,84 +428,98 @@ frontend_pcm_kernel(const PcmArgs a) {
     // =========================== P2b: EPD frame energies / crossings =================
     int f1 = 0;
     if (a.do_epd && n >= fl) f1 = (n - fl) / fs + 1;
-    for (int f = tid; f < f1; f += kPcmThreads) {
-      const int p = f * fs, q = p + fl;
-      long long s1 = 0; unsigned long long s2 = 0;
-      const int ga = (p + kGroup - 1) / kGroup, gb = q / kGroup;
-      auto direct = [&](int i0, int i1) {
-        for (int i = i0; i < i1; ++i) { const int d = (int)s_x[i] - uc.mu_int; s1 += d; s2 += (unsigned long long)((long long)d * d); }
-      };
-      if (ga > gb) direct(p, q);
-      else {
-        for (int g = ga; g < gb; ++g) { s1 += s_g1[g]; s2 += s_g2[g]; }
-        direct(p, ga * kGroup);
-        direct(gb * kGroup, q);
+    {
+      double emx = 0.0, amx = 0.0;
+      for (int f = tid; f < f1; f += kPcmThreads) {
+        const int p = f * fs, q = p + fl;
+        long long s1 = 0; unsigned long long s2 = 0;
+        const int ga = (p + kGroup - 1) / kGroup, gb = q / kGroup;
+        auto direct = [&](int i0, int i1) {
+          for (int i = i0; i < i1; ++i) { const int d = (int)s_x[i] - uc.thr; s1 += d; s2 += (unsigned long long)((long long)d * d); }
+        };
+        if (ga > gb) direct(p, q);
+        else {
+          for (int g = ga; g < gb; ++g) { s1 += s_g1[g]; s2 += s_g2[g]; }
+          direct(p, ga * kGroup);
+          direct(gb * kGroup, q);
+        }
+        // sum (d - phi)^2 from exact integer sums; `mag` bounds the rounding of the three terms
+        const double t1 = 2.0 * uc.phi_d * (double)s1, t2 = (double)fl * uc.phi_d * uc.phi_d;
+        const double ep = ((double)s2 - t1) + t2;
+        const double e = ep * uc.inv_m * uc.inv_m;
+        s_e[f] = e;
+        s_z[f] = count_changes(s_bits, p, q);
+        emx = fmax(emx, e);
+        amx = fmax(amx, ((double)s2 + fabs(t1)) + t2);
       }
-      // sum (d - phi)^2: s2, s1 exact integers; |terms| <= 9x the result (DESIGN.md "numerics")
-      const double ep = ((double)s2 - 2.0 * uc.phi_d * (double)s1) + (double)fl * uc.phi_d * uc.phi_d;
-      s_e[f] = ep * uc.inv_m * uc.inv_m;
-      s_z[f] = count_changes(s_bits, p, q);
+      emx = warp_reduce(emx, OpMaxD());
+      amx = warp_reduce(amx, OpMaxD());
+      double* part = reinterpret_cast<double*>(s_sh);
+      if (lane == 0) { part[wid] = emx; part[kWarps + wid] = amx; }
     }
     __syncthreads();
 
     // =========================== P3: endpoint decision ===============================
     int start = 0, end = n;
     if (f1 > 0) {
-      // E_max for the tolerance model
-      double emx = 0.0;
-      for (int f = tid; f < f1; f += kPcmThreads) emx = fmax(emx, s_e[f]);
-      emx = block_reduce<double>(emx, OpMaxD(), 0.0, reinterpret_cast<double*>(s_sh));
-      const int nf = min(5, f1 / 10);
-      uint64_t ka, kb;
-      const double v = (double)(f1 - 1) * (90.0 / 100.0);
-      auto get = [&](int i) { return f64_key(s_e[i]); };
-      if (v >= (double)(f1 - 1)) { block_select_pair(get, f1, f1 - 1, s_hist, s_sh, &ka, &kb); kb = ka; }
-      else block_select_pair(get, f1, (int)floor(v), s_hist, s_sh, &ka, &kb);
-      if (tid == 0) {
-        const double speech = np_lerp(key_f64(ka), key_f64(kb), v - floor(v));
-        double noise_e, noise_z;
-        if (nf > 0) {
-          auto te = [&](int64_t i) { return i < nf ? s_e[i] : s_e[f1 - 2 * nf + i]; };
-          auto tz = [&](int64_t i) { return (double)(i < nf ? s_z[i] : s_z[f1 - 2 * nf + i]); };
-          noise_e = np_pairwise_leaf(te, 0, 2 * nf) / (double)(2 * nf);
-          noise_z = np_pairwise_leaf(tz, 0, 2 * nf) / (double)(2 * nf);
-        } else {
-          noise_e = s_e[0]; noise_z = (double)s_z[0];
-          for (int i = 1; i < f1; ++i) { noise_e = fmin(noise_e, s_e[i]); noise_z = fmin(noise_z, (double)s_z[i]); }
+      if (wid == 0) {
+        const int nf = min(5, f1 / 10);
+        uint64_t ka, kb;
+        const double v = (double)(f1 - 1) * (90.0 / 100.0);
+        auto get = [&](int i) { return f64_key(s_e[i]); };
+        const bool top = v >= (double)(f1 - 1);
+        warp_select_pair(get, f1, top ? f1 - 1 : (int)floor(v), s_hist, s_cand, &ka, &kb);
+        if (top) kb = ka;
+        if (lane == 0) {
+          const double* part = reinterpret_cast<const double*>(s_sh);
+          double emx = 0.0, amx = 0.0;
+          for (int w = 0; w < kWarps; ++w) { emx = fmax(emx, part[w]); amx = fmax(amx, part[kWarps + w]); }
+          const double speech = np_lerp(key_f64(ka), key_f64(kb), v - floor(v));
+          double noise_e, noise_z;
+          if (nf > 0) {
+            auto te = [&](int64_t i) { return i < nf ? s_e[i] : s_e[f1 - 2 * nf + i]; };
+            auto tz = [&](int64_t i) { return (double)(i < nf ? s_z[i] : s_z[f1 - 2 * nf + i]); };
+            noise_e = np_pairwise_leaf(te, 0, 2 * nf) / (double)(2 * nf);
+            noise_z = np_pairwise_leaf(tz, 0, 2 * nf) / (double)(2 * nf);
+          } else {
+            noise_e = s_e[0]; noise_z = (double)s_z[0];
+            for (int i = 1; i < f1; ++i) { noise_e = fmin(noise_e, s_e[i]); noise_z = fmin(noise_z, (double)s_z[i]); }
+          }
+          const double t1 = speech * a.hr;
+          const double t2 = noise_e + (speech - noise_e) * a.lr;
+          const double t3 = noise_z * a.zr;
+          s_dbl[3] = t1; s_dbl[4] = t2; s_dbl[5] = t3;
+          // Slack on the thresholds (DESIGN.md "numerics"): 2^-40 relative, the rounding of our own
+          // three-term energy formula at its largest magnitude, and the reference's mean-rounding
+          // term |mu| * sqrt(fl * E) / m at E_max, each with a >= 4x margin.
+          const double eps = 1.0 / 1099511627776.0;  // 2^-40
+          const double smax = ldexp(fabs(uc.mu) * sqrt((double)fl * emx) * uc.inv_m + amx * uc.inv_m * uc.inv_m, -50);
+          const double tol1 = eps * fabs(t1) + fabs(a.hr) * smax;
+          const double tol2 = eps * (fabs(noise_e) + fabs(a.lr) * (fabs(speech) + fabs(noise_e))) +
+                              (fabs(1.0 - a.lr) + fabs(a.lr)) * smax;
+          s_dbl[6] = tol1 + smax + eps * emx;      // per-frame slack bounded at its utterance maximum
+          s_dbl[7] = tol2 + smax + eps * emx;
+          s_int[6] = 0; s_int[7] = f1 - 1; s_int[8] = 0; s_int[9] = f1 - 1;
         }
-        const double t1 = speech * a.hr;
-        const double t2 = noise_e + (speech - noise_e) * a.lr;
-        const double t3 = noise_z * a.zr;
-        s_dbl[3] = t1; s_dbl[4] = t2; s_dbl[5] = t3;
-        // slack on the thresholds: relative part plus the reference's mean-rounding term at E_max
-        const double eps = 1.0 / 1099511627776.0;  // 2^-40
-        const double smax = ldexp(fabs(uc.mu) * sqrt((double)fl * emx) * uc.inv_m, -50);
-        s_dbl[6] = eps * fabs(t1) + fabs(a.hr) * smax;
-        s_dbl[7] = eps * (fabs(noise_e) + fabs(a.lr) * (fabs(speech) + fabs(noise_e))) +
-                   (fabs(1.0 - a.lr) + fabs(a.lr)) * smax;
       }
       __syncthreads();
       const double t1 = s_dbl[3], t2 = s_dbl[4], t3 = s_dbl[5];
       const double tol1 = s_dbl[6], tol2 = s_dbl[7];
-      const double eps = 1.0 / 1099511627776.0;
       {
         int n3 = f1, n4 = -1, flag = 0;
         for (int f = tid; f < f1; f += kPcmThreads) {
           const double e = s_e[f];
           if (e > t1) { n3 = min(n3, f); n4 = max(n4, f); }
-          // |mu| * sqrt(fl * E') / m^2 with E' = E * m^2  ->  |mu| * sqrt(fl*E) / m
-          const double sf = ldexp(fabs(uc.mu) * sqrt((double)fl * e) * uc.inv_m, -50) + eps * e;
-          if (!(e == 0.0 && t1 == 0.0) && fabs(e - t1) <= sf + tol1) flag = 1;
-          if (!(e == 0.0 && t2 == 0.0) && fabs(e - t2) <= sf + tol2) flag = 1;
+          if (fabs(e - t1) <= tol1 && !(e == 0.0 && t1 == 0.0)) flag = 1;
+          if (fabs(e - t2) <= tol2 && !(e == 0.0 && t2 == 0.0)) flag = 1;
         }
         n3 = warp_reduce(n3, OpMinI()); n4 = warp_reduce(n4, OpMaxI());
         flag = warp_reduce(flag, OpMaxI());
-        if (lane_id() == 0) {
+        if (lane == 0) {
           if (n3 < f1) atomicMin(&s_int[4], n3);
           if (n4 >= 0) atomicMax(&s_int[5], n4);
           if (flag) atomicOr(&s_int[3], 1);
         }
-        if (tid == 0) { s_int[6] = 0; s_int[7] = f1 - 1; s_int[8] = 0; s_int[9] = f1 - 1; }
       }
       __syncthreads();
       const int n3 = s_int[4], n4 = s_int[5];
@@ -396,7 +529,7 @@ frontend_pcm_kernel(const PcmArgs a) {
           for (int f = tid; f < f1; f += kPcmThreads)
             if (s_e[f] <= t2) { if (f < n3) n2 = max(n2, f + 1); if (f > n4) n5 = min(n5, f - 1); }
           n2 = warp_reduce(n2, OpMaxI()); n5 = warp_reduce(n5, OpMinI());
-          if (lane_id() == 0) { if (n2 > 0) atomicMax(&s_int[6], n2); if (n5 < f1 - 1) atomicMin(&s_int[7], n5); }
+          if (lane == 0) { if (n2 > 0) atomicMax(&s_int[6], n2); if (n5 < f1 - 1) atomicMin(&s_int[7], n5); }
         }
         __syncthreads();
         const int n2 = s_int[6], n5 = s_int[7];
@@ -405,7 +538,7 @@ frontend_pcm_kernel(const PcmArgs a) {
           for (int f = tid; f < f1; f += kPcmThreads)
             if ((double)s_z[f] <= t3) { if (f < n2) n1 = max(n1, f + 1); if (f > n5) n6 = min(n6, f - 1); }
           n1 = warp_reduce(n1, OpMaxI()); n6 = warp_reduce(n6, OpMinI());
-          if (lane_id() == 0) { if (n1 > 0) atomicMax(&s_int[8], n1); if (n6 < f1 - 1) atomicMin(&s_int[9], n6); }
+          if (lane == 0) { if (n1 > 0) atomicMax(&s_int[8], n1); if (n6 < f1 - 1) atomicMin(&s_int[9], n6); }
         }
         __syncthreads();
         start = s_int[8] * fs;
@@ -426,13 +559,54 @@ frontend_pcm_kernel(const PcmArgs a) {
     // =========================== P4: windowed frame features =========================
     const int seg = end - start;
     const int f2 = (int)frame_count_host_device(seg, fl, fs);
-    {
+    int f2_chain = 0;      // frames [0, f2_chain) done by the chain path, the rest generically
+    if (chain_cfg && (start & 127) == 0 && seg >= 256) f2_chain = (seg - 256) / 128 + 1;
+    if (f2_chain > f2) f2_chain = f2;
+    if (f2_chain > 0) {
+      // 16 lanes per chain; a chain covers `per` consecutive frames = per + 1 hop blocks.
+      constexpr int kChains = kPcmThreads / 16;
+      const int chain = tid >> 4, sub = tid & 15;
+      const int per = (f2_chain + kChains - 1) / kChains;
+      const int fa = chain * per, fb = min(fa + per, f2_chain);
+      const float phi = uc.phi;
+      float ce = 0.f, cm = 0.f;                       // first-half partials of the previous block
+      const bool hi8 = (sub & 8) != 0;
+      for (int i = 0; i <= per; ++i) {             // uniform trip count: the shuffles below are warp-wide
+        const int b = fa + i;
+        const bool live = (fa < fb) && (b <= fb);
+        int4 q = make_int4(0, 0, 0, 0);
+        if (live) q = *reinterpret_cast<const int4*>(s_x + start + b * 128 + 8 * sub);
+        const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+        float e0 = 0.f, m0 = 0.f, e1 = ce, m1 = cm;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float dlo = (float)(sext16(w[k]) - uc.thr) - phi;
+          const float dhi = (float)(((int)w[k] >> 16) - uc.thr) - phi;
+          const float qlo = dlo * dlo, qhi = dhi * dhi;
+          const float alo = fabsf(dlo), ahi = fabsf(dhi);
+          e0 = fmaf(cw2[0][2 * k], qlo, e0); m0 = fmaf(cw[0][2 * k], alo, m0);
+          e1 = fmaf(cw2[1][2 * k], qlo, e1); m1 = fmaf(cw[1][2 * k], alo, m1);
+          e0 = fmaf(cw2[0][2 * k + 1], qhi, e0); m0 = fmaf(cw[0][2 * k + 1], ahi, m0);
+          e1 = fmaf(cw2[1][2 * k + 1], qhi, e1); m1 = fmaf(cw[1][2 * k + 1], ahi, m1);
+        }
+        ce = e0; cm = m0;
+        // frame b-1 = first half carried from the previous block (in e1/m1 through ce/cm) + this
+        // block as its second half: transposed reduction of (e1, m1) over the chain's 16 lanes
+        const float send = hi8 ? e1 : m1, keep = hi8 ? m1 : e1;
+        float v = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        if (live && b > fa && (sub & 7) == 0) (hi8 ? s_fm : s_fe)[b - 1] = v;    // raw sums, scaled below
+      }
+    }
+    if (f2_chain < f2) {
       const int sub = tid & (kLanesPerFrame - 1);
       const int slot = tid / kLanesPerFrame;
       constexpr int kSlots = kPcmThreads / kLanesPerFrame;
       const bool vec_ok = ((start & 7) == 0) && ((fs & 7) == 0);
       const float phi = uc.phi;
-      for (int t0 = 0; t0 < f2; t0 += kSlots) {
+      for (int t0 = f2_chain; t0 < f2; t0 += kSlots) {
         const int t = t0 + slot;
         float e = 0.f, m = 0.f;
         int p = 0, valid = 0;
@@ -451,8 +625,8 @@ frontend_pcm_kernel(const PcmArgs a) {
               const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const float dlo = (float)(sext16(w[k]) - uc.mu_int) - phi;
-                const float dhi = (float)(((int)w[k] >> 16) - uc.mu_int) - phi;
+                const float dlo = (float)(sext16(w[k]) - uc.thr) - phi;
+                const float dhi = (float)(((int)w[k] >> 16) - uc.thr) - phi;
                 const float alo = ww[2 * k] * dlo, ahi = ww[2 * k + 1] * dhi;
                 e = fmaf(alo, alo, e); m += fabsf(alo);
                 e = fmaf(ahi, ahi, e); m += fabsf(ahi);
@@ -461,7 +635,7 @@ frontend_pcm_kernel(const PcmArgs a) {
             jdone = nv << 3;
           }
           for (int j = jdone + sub; j < valid; j += kLanesPerFrame) {
-            const float d = (float)((int)s_x[p + j] - uc.mu_int) - phi;
+            const float d = (float)((int)s_x[p + j] - uc.thr) - phi;
             const float av = s_win[j] * d;
             e = fmaf(av, av, e); m += fabsf(av);
           }
@@ -471,15 +645,30 @@ frontend_pcm_kernel(const PcmArgs a) {
           e += __shfl_xor_sync(0xffffffffu, e, o);
           m += __shfl_xor_sync(0xffffffffu, m, o);
         }
-        if (t < f2) {
-          if (sub == 0) {
-            s_fe[t] = (float)((double)e * uc.inv_m * uc.inv_m);
-            s_fm[t] = (float)((double)m * uc.inv_m);
-          } else if (sub == 1) {
-            s_fz[t] = (float)frame_zcr(s_bits, p, valid, fl, hann);
-          }
-        }
+        if (t < f2 && sub == 0) { s_fe[t] = e; s_fm[t] = m; }                      // raw sums, scaled below
       }
+    }
+    __syncthreads();
+    // peak normalisation (1/m^2, 1/m) and zero crossings, one frame per thread.  A full frame of
+    // the trimmed segment IS an endpoint-detection frame (start is a multiple of the hop), so its
+    // crossing count is already in s_z; only Hanning's zeroed end points need patching.
+    for (int t = tid; t < f2; t += kPcmThreads) {
+      const int p = start + t * fs;
+      const int valid = min(fl, end - p);
+      s_fe[t] = (float)((double)s_fe[t] * uc.inv_m * uc.inv_m);
+      s_fm[t] = (float)((double)s_fm[t] * uc.inv_m);
+      int zc;
+      if (f1 > 0 && valid == fl && !(hann && fl <= 2)) {
+        zc = s_z[p / fs];
+        if (hann) {
+          const int s0 = bit_at(s_bits, p), s1 = bit_at(s_bits, p + 1);
+          const int sl = bit_at(s_bits, p + fl - 1), sp = bit_at(s_bits, p + fl - 2);
+          zc += (s1 - (s0 ^ s1)) + (sp - (sp ^ sl));
+        }
+      } else {
+        zc = frame_zcr(s_bits, p, valid, fl, hann);
+      }
+      s_fz[t] = (float)zc;
     }
     __syncthreads();   // samples / sign bits are dead: the next utterance may be loaded
 
@@ -489,9 +678,8 @@ frontend_pcm_kernel(const PcmArgs a) {
     if (u_next < a.n_utts) issue_load(u_next);
 
     // =========================== P5: statistics, one warp per sequence ===============
-    if (f2 > 0 && a.out.stats && warp_id() < 3) {
-      const int wq = warp_id(), lane = lane_id();
-      const float* seq = wq == 0 ? s_fe : (wq == 1 ? s_fm : s_fz);
+    if (f2 > 0 && a.out.stats && wid < 3) {
+      const float* seq = wid == 0 ? s_fe : (wid == 1 ? s_fm : s_fz);
       double sum = 0.0; float mx = -INFINITY, mn = INFINITY;
       for (int i = lane; i < f2; i += 32) { const float x = seq[i]; sum += (double)x; mx = fmaxf(mx, x); mn = fminf(mn, x); }
       sum = warp_reduce(sum, OpAddD());
@@ -501,47 +689,15 @@ frontend_pcm_kernel(const PcmArgs a) {
       double ss = 0.0;
       for (int i = lane; i < f2; i += 32) { const double d = (double)seq[i] - mean; ss += d * d; }
       ss = warp_reduce(ss, OpAddD());
-      // median: warp-level MSD radix select on the (non-negative) float bit patterns
-      int* hist = s_hist + 256 * wq;
-      uint32_t prefix = 0, mask = 0;
-      int rank = (f2 - 1) / 2;
-      for (int shift = 24; shift >= 0; shift -= 8) {
-        for (int i = lane; i < 256; i += 32) hist[i] = 0;
-        __syncwarp();
-        for (int i = lane; i < f2; i += 32) {
-          const uint32_t k = __float_as_uint(seq[i]);
-          if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 0xff], 1);
-        }
-        __syncwarp();
-        int c[8], tot = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { c[j] = hist[lane * 8 + j]; tot += c[j]; }
-        int incl = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int tt = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += tt; }
-        int run = incl - tot, digit = -1, newrank = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { if (digit < 0 && rank >= run && rank < run + c[j]) { digit = lane * 8 + j; newrank = rank - run; } run += c[j]; }
-        const unsigned who = __ballot_sync(0xffffffffu, digit >= 0);
-        const int src = __ffs(who) - 1;
-        digit = __shfl_sync(0xffffffffu, digit, src);
-        rank = __shfl_sync(0xffffffffu, newrank, src);
-        prefix |= (uint32_t)digit << shift; mask |= 0xffu << shift;
-        __syncwarp();
-      }
-      const float med_lo = __uint_as_float(prefix);
-      int le = 0; float nxt = INFINITY;
-      for (int i = lane; i < f2; i += 32) { const float x = seq[i]; if (x <= med_lo) ++le; else nxt = fminf(nxt, x); }
-      le = warp_reduce(le, OpAddI());
-      nxt = warp_reduce(nxt, [](float x, float y) { return fminf(x, y); });
-      const int r = (f2 - 1) / 2;
-      const float med_hi = (le >= r + 2 || nxt == INFINITY) ? med_lo : nxt;
+      uint64_t ka, kb;
+      auto get = [&](int i) { return f64_key((double)seq[i]); };
+      warp_select_pair(get, f2, (f2 - 1) / 2, s_hist + 256 * wid, s_cand + 32 * wid, &ka, &kb);
       if (lane == 0) {
-        float* o = a.out.stats + (int64_t)u * kStats + 5 * wq;
+        float* o = a.out.stats + (int64_t)u * kStats + 5 * wid;
         o[0] = (float)mean;
         o[1] = (float)sqrt(ss / (double)f2);
         o[2] = mx; o[3] = mn;
-        o[4] = (f2 & 1) ? med_lo : (float)(((double)med_lo + (double)med_hi) * 0.5);
+        o[4] = (f2 & 1) ? (float)key_f64(ka) : (float)((key_f64(ka) + key_f64(kb)) * 0.5);
       }
     }
 

@@ -52,6 +52,7 @@ struct PcmArgs {
   const float* win_f32;         // [fl] window as float
   int cap_samples;              // shared-memory capacity in samples (multiple of 64)
   int cap_frames;               // capacity for per-frame arrays
+  int tma_chunk;                // bytes per bulk copy (multiple of 16)
   unsigned int* work_counter;   // dynamic utterance scheduler
   int32_t* flag_list;           // utterances that need the float64 replay
   int32_t* flag_count;
@@ -68,6 +69,9 @@ __global__ void sequence_stats_kernel(const double* s0, const double* s1, const 
 size_t pcm_kernel_smem_bytes(int cap_samples, int cap_frames, int fl);
 cudaError_t launch_frontend_pcm(const PcmArgs& a, int grid, size_t smem, cudaStream_t st);
 int pcm_kernel_max_ctas_per_sm(size_t smem);
-constexpr int kPcmThreads = 256;
+#ifndef DSP_PCM_THREADS
+#define DSP_PCM_THREADS 256
+#endif
+constexpr int kPcmThreads = DSP_PCM_THREADS;
 
 }  // namespace dsp
