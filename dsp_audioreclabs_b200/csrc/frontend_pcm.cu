@@ -55,9 +55,9 @@ __host__ __device__ inline SmemLayout make_layout(int cap_samples, int cap_frame
   L.z = o;       o += align16(4 * cap_frames);
   L.win = o;     o += align16(4 * fl);
   L.hist = o;    o += 3 * 256 * 4;
-  L.cand = o;    o += 3 * 32 * 8;
+  L.cand = o;    o += 3 * 64 * 4;
   L.sh = o;      o += 64 * 8;
-  L.misc = o;    o += 256;
+  L.misc = o;    o += 384;
   L.total = o;
   return L;
 }
@@ -152,81 +152,133 @@ struct UttConst {
   double mu;       // S/N
 };
 
+// ---- named barriers (warp-specialised roles) --------------------------------------------
+constexpr int kStatsWarps = 2;
+constexpr int kMainWarps = kWarps - kStatsWarps;
+constexpr int kMainThreads = kMainWarps * 32;
+constexpr int kBarMain = 1;       // main warps only
+constexpr int kBarFeatFull = 2;   // main arrive, stats wait: feature sequences are in shared memory
+constexpr int kBarFeatEmpty = 3;  // stats arrive, main wait: feature sequences have been consumed
+constexpr int kStatsRegs = 11;    // feature frames per lane held in registers by the stats warps
+
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void main_sync() { bar_sync(kBarMain, kMainThreads); }
+
+// Radix-select bookkeeping shared by the block- and warp-level selects: after the 256-bin
+// histogram of (key - lo) >> s is in `hist`, one warp finds the bin holding `rank`.
+__device__ __forceinline__ void scan_bins(const int* hist, int lane, int rank, int* digit_out, int* rank_out, int* cnt_out) {
+  int c[8], tot = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { c[j] = hist[lane * 8 + j]; tot += c[j]; }
+  int incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  int run = incl - tot, digit = -1, newrank = 0, newcnt = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (digit < 0 && rank >= run && rank < run + c[j]) { digit = lane * 8 + j; newrank = rank - run; newcnt = c[j]; }
+    run += c[j];
+  }
+  const int src = __ffs(__ballot_sync(0xffffffffu, digit >= 0)) - 1;
+  *digit_out = __shfl_sync(0xffffffffu, digit, src);
+  *rank_out = __shfl_sync(0xffffffffu, newrank, src);
+  *cnt_out = __shfl_sync(0xffffffffu, newcnt, src);
+}
+
+__device__ __forceinline__ int first_shift(uint32_t kmin, uint32_t kmax) {
+  const uint32_t span = kmax - kmin;
+  const int bits = 32 - __clz(span);          // 0 when all keys are equal
+  return bits > 8 ? bits - 8 : 0;
+}
+
 // ---------------------------------------------------------------------------------------
-// Warp-level order statistics: the keys of rank r and r+1 (ascending, 0-based) among n
-// 64-bit monotone keys.  MSD radix select, 8 bits per pass, that stops as soon as at most 32
-// candidates share the prefix and finishes by ranking those in registers.  One warp; `hist`
-// holds 256 ints and `cand` 32 keys of that warp's shared memory.
+// Statistics of one non-negative float sequence by ONE warp (compute_statistics,
+// feature_extraction.py:46-62): mean, population std, max, min and the median by a radix select
+// whose first pass spreads 256 bins over [min, max] of the float bit patterns.  acc(j) returns
+// element lane + 32*j; NJ > 0 = that many register-resident elements per lane, NJ == 0 = loop.
 // ---------------------------------------------------------------------------------------
-template <class Get>
-__device__ void warp_select_pair(Get get, int n, int r, int* hist, unsigned long long* cand,
-                                 uint64_t* k_lo, uint64_t* k_hi) {
+template <int NJ, class Acc>
+__device__ void warp_sequence_stats(Acc acc, int n, int* hist, float* cand, float* out5) {
   const int lane = threadIdx.x & 31;
-  uint64_t prefix = 0, mask = 0;
-  int rank = r, cnt = n;
-  for (int shift = 56; shift >= 0 && cnt > 32; shift -= 8) {
+  const int nj = NJ ? NJ : (n + 31) / 32;
+  double sum = 0.0;
+  float mx = 0.f, mn = INFINITY;
+#pragma unroll
+  for (int j = 0; j < nj; ++j) if (lane + 32 * j < n) { const float x = acc(j); sum += (double)x; mx = fmaxf(mx, x); mn = fminf(mn, x); }
+  sum = warp_reduce(sum, OpAddD());
+  mx = warp_reduce(mx, [](float x, float y) { return fmaxf(x, y); });
+  mn = warp_reduce(mn, [](float x, float y) { return fminf(x, y); });
+  const double mean = sum / (double)n;
+  double ss = 0.0;
+#pragma unroll
+  for (int j = 0; j < nj; ++j) if (lane + 32 * j < n) { const double d = (double)acc(j) - mean; ss += d * d; }
+  ss = warp_reduce(ss, OpAddD());
+
+  uint32_t lo = __float_as_uint(mn);
+  int s = first_shift(lo, __float_as_uint(mx));
+  int s_used = 32, rank = (n - 1) / 2, cnt = n;
+  if (n > 32) { s_used = s; }
+  while (cnt > 32) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) hist[lane * 8 + j] = 0;
     __syncwarp();
-    for (int i = lane; i < n; i += 32) {
-      const uint64_t k = get(i);
-      if ((k & mask) == prefix) atomicAdd(&hist[(int)((k >> shift) & 0xff)], 1);
+#pragma unroll
+    for (int j = 0; j < nj; ++j) if (lane + 32 * j < n) {
+      const uint32_t k = __float_as_uint(acc(j));
+      if (k >= lo) { const uint32_t d = (k - lo) >> s; if (d < 256u) atomicAdd(&hist[d], 1); }
     }
     __syncwarp();
-    int c[8], tot = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { c[j] = hist[lane * 8 + j]; tot += c[j]; }
-    int incl = tot;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    int run = incl - tot, digit = -1, newrank = 0, newcnt = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      if (digit < 0 && rank >= run && rank < run + c[j]) { digit = lane * 8 + j; newrank = rank - run; newcnt = c[j]; }
-      run += c[j];
-    }
-    const int src = __ffs(__ballot_sync(0xffffffffu, digit >= 0)) - 1;
-    digit = __shfl_sync(0xffffffffu, digit, src);
-    rank = __shfl_sync(0xffffffffu, newrank, src);
-    cnt = __shfl_sync(0xffffffffu, newcnt, src);
-    prefix |= (uint64_t)digit << shift;
-    mask |= 0xffull << shift;
+    int digit;
+    scan_bins(hist, lane, rank, &digit, &rank, &cnt);
+    lo += (uint32_t)digit << s;
+    s_used = s;
     __syncwarp();
+    if (s == 0) break;
+    s = s > 8 ? s - 8 : 0;
   }
-  uint64_t sel, sel2;
-  bool have2 = false;
-  if (cnt > 32) {            // all 64 bits consumed: every remaining candidate equals the prefix
-    sel = prefix; sel2 = prefix; have2 = (rank + 1 < cnt);
+  const unsigned long long span = 1ull << s_used;
+  float sel, sel2;
+  bool have2;
+  if (cnt > 32) {                     // s == 0: every candidate has the same bit pattern
+    sel = sel2 = __uint_as_float(lo);
+    have2 = rank + 1 < cnt;
   } else {
-    // gather the (<= 32) candidates, one per lane, then rank them in registers
     if (lane == 0) hist[0] = 0;
     __syncwarp();
-    for (int i = lane; i < n; i += 32) {
-      const uint64_t k = get(i);
-      if ((k & mask) == prefix) cand[atomicAdd(&hist[0], 1)] = k;
+#pragma unroll
+    for (int j = 0; j < nj; ++j) if (lane + 32 * j < n) {
+      const float x = acc(j);
+      const uint32_t k = __float_as_uint(x);
+      if (n <= 32 || (k >= lo && (unsigned long long)(k - lo) < span)) cand[atomicAdd(&hist[0], 1)] = x;
     }
     __syncwarp();
-    const uint64_t mine = lane < cnt ? cand[lane] : ~0ull;
+    const float mine = lane < cnt ? cand[lane] : INFINITY;
     int below = 0;
     for (int j = 0; j < cnt; ++j) {
-      const uint64_t o = __shfl_sync(0xffffffffu, mine, j);
+      const float o = __shfl_sync(0xffffffffu, mine, j);
       below += (o < mine) || (o == mine && j < lane);
     }
     const unsigned m1 = __ballot_sync(0xffffffffu, lane < cnt && below == rank);
     const unsigned m2 = __ballot_sync(0xffffffffu, lane < cnt && below == rank + 1);
     sel = __shfl_sync(0xffffffffu, mine, __ffs(m1) - 1);
-    have2 = (m2 != 0);
+    have2 = m2 != 0;
     sel2 = have2 ? __shfl_sync(0xffffffffu, mine, __ffs(m2) - 1) : sel;
     __syncwarp();
   }
-  if (!have2) {              // rank r+1 lies outside the candidate set: smallest key above sel
-    unsigned long long nxt = ~0ull;
-    for (int i = lane; i < n; i += 32) { const uint64_t k = get(i); if (k > sel && k < nxt) nxt = k; }
-    nxt = warp_reduce(nxt, OpMinU64());
-    sel2 = (nxt == ~0ull) ? sel : (uint64_t)nxt;
+  if (!have2 && !(n & 1)) {           // upper middle lies above the candidate bin
+    float nxt = INFINITY;
+#pragma unroll
+    for (int j = 0; j < nj; ++j) if (lane + 32 * j < n) { const float x = acc(j); if (x > sel) nxt = fminf(nxt, x); }
+    nxt = warp_reduce(nxt, [](float x, float y) { return fminf(x, y); });
+    sel2 = nxt == INFINITY ? sel : nxt;
   }
-  *k_lo = sel;
-  *k_hi = sel2;
+  if (lane == 0) {
+    out5[0] = (float)mean;
+    out5[1] = (float)sqrt(ss / (double)n);
+    out5[2] = mx; out5[3] = mn;
+    out5[4] = (n & 1) ? sel : (float)(((double)sel + (double)sel2) * 0.5);
+  }
 }
 
 }  // namespace
@@ -249,13 +301,14 @@ frontend_pcm_kernel(const PcmArgs a) {
   double* s_e = reinterpret_cast<double*>(smem + L.e);
   int* s_z = reinterpret_cast<int*>(smem + L.z);
   float* s_win = reinterpret_cast<float*>(smem + L.win);
-  int* s_hist = reinterpret_cast<int*>(smem + L.hist);
-  unsigned long long* s_cand = reinterpret_cast<unsigned long long*>(smem + L.cand);
+  int* s_hist = reinterpret_cast<int*>(smem + L.hist);            // [0] main, [1],[2] stats warps
+  float* s_cand = reinterpret_cast<float*>(smem + L.cand);        // 3 x 64 floats
   unsigned long long* s_sh = reinterpret_cast<unsigned long long*>(smem + L.sh);
-  // misc block: [0] mbarrier, then scalars
+  // misc block: [0] mbarrier, scalars, mailbox main -> stats
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + L.misc);
   int* s_int = reinterpret_cast<int*>(smem + L.misc + 16);         // 24 ints
   double* s_dbl = reinterpret_cast<double*>(smem + L.misc + 128);  // 16 doubles
+  int* s_mail = reinterpret_cast<int*>(smem + L.misc + 256);       // 2 x 8 ints
 
   const int tid = threadIdx.x;
   const int lane = tid & 31, wid = tid >> 5;
@@ -269,8 +322,73 @@ frontend_pcm_kernel(const PcmArgs a) {
     s_int[0] = (int)atomicAdd(a.work_counter, 1u);
   }
   __syncthreads();
+
+  // =========================================================================================
+  // STATS WARPS: statistics + outputs of utterance i while the main warps work on utterance i+1
+  // =========================================================================================
+  if (wid >= kMainWarps) {
+    const int sw = wid - kMainWarps;                       // 0: energy, 1: magnitude + zcr
+    int* hist = s_hist + 256 * (1 + sw);
+    float* cand = s_cand + 64 * (1 + sw);
+    for (int it = 0;; ++it) {
+      bar_sync(kBarFeatFull, kPcmThreads);
+      const int* mb = s_mail + 8 * (it & 1);
+      const int u = mb[0], f2 = mb[1];
+      if (u < 0) break;
+      const int64_t fo = a.feat_offsets[u];
+      float* stats = a.out.stats ? a.out.stats + (int64_t)u * kStats : nullptr;
+      float st[5];
+      if (f2 <= 32 * kStatsRegs) {
+        // copy this warp's sequences to registers so the main warps can reuse the buffers at once
+        float r0[kStatsRegs], r1[kStatsRegs];
+        const float* q0 = sw == 0 ? s_fe : s_fm;
+#pragma unroll
+        for (int j = 0; j < kStatsRegs; ++j) {
+          const int i = lane + 32 * j;
+          r0[j] = i < f2 ? q0[i] : 0.f;
+          r1[j] = (sw == 1 && i < f2) ? s_fz[i] : 0.f;
+        }
+        bar_arrive(kBarFeatEmpty, kPcmThreads);
+        float* g0 = sw == 0 ? a.out.energy : a.out.magnitude;
+#pragma unroll
+        for (int j = 0; j < kStatsRegs; ++j) {
+          const int i = lane + 32 * j;
+          if (i < f2) { if (g0) g0[fo + i] = r0[j]; if (sw == 1 && a.out.zcr) a.out.zcr[fo + i] = r1[j]; }
+        }
+        if (f2 > 0 && stats) {
+          warp_sequence_stats<kStatsRegs>([&](int j) { return r0[j]; }, f2, hist, cand, st);
+          if (lane == 0) { float* o = stats + (sw == 0 ? 0 : 5); for (int k = 0; k < 5; ++k) o[k] = st[k]; }
+          if (sw == 1) {
+            warp_sequence_stats<kStatsRegs>([&](int j) { return r1[j]; }, f2, hist, cand, st);
+            if (lane == 0) for (int k = 0; k < 5; ++k) stats[10 + k] = st[k];
+          }
+        }
+      } else {
+        // long sequences: work from shared memory, release the buffers afterwards
+        const float* q0 = sw == 0 ? s_fe : s_fm;
+        float* g0 = sw == 0 ? a.out.energy : a.out.magnitude;
+        for (int i = lane; i < f2; i += 32) { if (g0) g0[fo + i] = q0[i]; if (sw == 1 && a.out.zcr) a.out.zcr[fo + i] = s_fz[i]; }
+        if (stats) {
+          warp_sequence_stats<0>([&](int j) { return q0[lane + 32 * j]; }, f2, hist, cand, st);
+          if (lane == 0) { float* o = stats + (sw == 0 ? 0 : 5); for (int k = 0; k < 5; ++k) o[k] = st[k]; }
+          if (sw == 1) {
+            warp_sequence_stats<0>([&](int j) { return s_fz[lane + 32 * j]; }, f2, hist, cand, st);
+            if (lane == 0) for (int k = 0; k < 5; ++k) stats[10 + k] = st[k];
+          }
+        }
+        __syncwarp();
+        bar_arrive(kBarFeatEmpty, kPcmThreads);
+      }
+    }
+    return;
+  }
+
+  // =========================================================================================
+  // MAIN WARPS
+  // =========================================================================================
   uint32_t parity = 0;
   int u = s_int[0];
+  int iter = 0;
 
   // window coefficients of the hop-128 / length-256 chain (P4 fast path): lane owns samples
   // 8*(lane&15) .. +8 of every hop block; c = 0 is the first half of a frame, c = 1 the second
@@ -286,7 +404,7 @@ frontend_pcm_kernel(const PcmArgs a) {
       }
   }
 
-  // issue the load of utterance `uu` (thread-block uniform)
+  // issue the load of utterance `uu` (uniform over the main warps)
   auto issue_load = [&](int uu) {
     const int64_t off = a.offsets[uu];
     const int n = (int)(a.offsets[uu + 1] - off);
@@ -311,10 +429,10 @@ frontend_pcm_kernel(const PcmArgs a) {
     } else if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
       const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
       uint32_t* d32 = reinterpret_cast<uint32_t*>(s_x);
-      for (int i = tid; i < (n >> 1); i += kPcmThreads) d32[i] = __ldg(s32 + i);
+      for (int i = tid; i < (n >> 1); i += kMainThreads) d32[i] = __ldg(s32 + i);
       if ((n & 1) && tid == 0) s_x[n - 1] = src[n - 1];
     } else {
-      for (int i = tid; i < n; i += kPcmThreads) s_x[i] = src[i];
+      for (int i = tid; i < n; i += kMainThreads) s_x[i] = src[i];
     }
   };
   auto wait_load = [&](int uu) {
@@ -322,7 +440,7 @@ frontend_pcm_kernel(const PcmArgs a) {
     const int n = (int)(a.offsets[uu + 1] - off);
     const bool tma = ((reinterpret_cast<uintptr_t>(a.samples + off) & 15) == 0);
     if (tma && (((uint32_t)n * 2u) & ~15u) > 0) { mbar_wait(s_bar, parity); parity ^= 1; }
-    __syncthreads();
+    main_sync();
   };
 
   if (u < a.n_utts) issue_load(u);
@@ -331,6 +449,7 @@ frontend_pcm_kernel(const PcmArgs a) {
     const int64_t off = a.offsets[u];
     const int n = (int)(a.offsets[u + 1] - off);
     wait_load(u);
+    if (tid == 0) s_int[0] = (int)atomicAdd(a.work_counter, 1u);   // next utterance, consumed after P4
 
     // =========================== P1: sum, min, max ===================================
     {
@@ -338,7 +457,7 @@ frontend_pcm_kernel(const PcmArgs a) {
       uint32_t mn2 = 0x7fff7fffu, mx2 = 0x80008000u;
       const int nvec = n >> 3;
       const int4* xv = reinterpret_cast<const int4*>(s_x);
-      for (int v = tid; v < nvec; v += kPcmThreads) {
+      for (int v = tid; v < nvec; v += kMainThreads) {
         const int4 q = xv[v];
         sum = __dp2a_lo(q.x, 0x0101, sum); sum = __dp2a_lo(q.y, 0x0101, sum);
         sum = __dp2a_lo(q.z, 0x0101, sum); sum = __dp2a_lo(q.w, 0x0101, sum);
@@ -349,16 +468,16 @@ frontend_pcm_kernel(const PcmArgs a) {
       }
       int mn = min(sext16(mn2), (int)mn2 >> 16), mx = max(sext16(mx2), (int)mx2 >> 16);
       if (tid < (n & 7)) { const int k = s_x[(nvec << 3) + tid]; sum += k; mn = min(mn, k); mx = max(mx, k); }
-      // one barrier: per-warp partials, then every thread of warp 0 combines them
-      sum = warp_reduce(sum, OpAddI());     // |sum| <= 32 lanes * 173 samples * 2^15 < 2^31
+      // per-warp partials (a warp sees < 2^31 / 2^15 samples: the utterance fits shared memory)
+      sum = warp_reduce(sum, OpAddI());
       mn = warp_reduce(mn, OpMinI());
       mx = warp_reduce(mx, OpMaxI());
       int* part = reinterpret_cast<int*>(s_sh);
       if (lane == 0) { part[wid] = sum; part[kWarps + wid] = mn; part[2 * kWarps + wid] = mx; }
-      __syncthreads();
+      main_sync();
       if (tid == 0) {
         long long S = 0; int gmn = 32767, gmx = -32768;
-        for (int w = 0; w < kWarps; ++w) { S += part[w]; gmn = min(gmn, part[kWarps + w]); gmx = max(gmx, part[2 * kWarps + w]); }
+        for (int w = 0; w < kMainWarps; ++w) { S += part[w]; gmn = min(gmn, part[kWarps + w]); gmx = max(gmx, part[2 * kWarps + w]); }
         const long long N = n > 0 ? n : 1;
         long long q = S / N; if ((S % N) != 0 && (S < 0)) --q;      // floor(S/N)
         const long long thr = q + 1;
@@ -372,17 +491,20 @@ frontend_pcm_kernel(const PcmArgs a) {
         s_int[4] = n;   // n3 (min)      -- initial values for the searches
         s_int[5] = -1;  // n4 (max)
       }
-      __syncthreads();
+      main_sync();
     }
     UttConst uc;
     uc.thr = s_int[1]; uc.phi_d = s_dbl[0]; uc.phi = (float)uc.phi_d;
     uc.inv_m = s_dbl[1]; uc.mu = s_dbl[2];
 
+    // the group-sum region doubles as the feature buffers the stats warps may still be reading
+    if (iter > 0) bar_sync(kBarFeatEmpty, kPcmThreads);
+
     // =========================== P2: group sums + sign bits ==========================
     const int ng = (n + kGroup - 1) / kGroup;
     {
       const int rot = tid & 7;               // == g & 7 for every group this thread owns
-      for (int g = tid; g < ng; g += kPcmThreads) {
+      for (int g = tid; g < ng; g += kMainThreads) {
         int s1 = 0;
         unsigned long long s2 = 0;
         uint32_t b0, b1;
@@ -423,14 +545,14 @@ frontend_pcm_kernel(const PcmArgs a) {
       }
     }
     if (tid < 4) s_bits[2 * ng + tid] = 0;
-    __syncthreads();
+    main_sync();
 
     // =========================== P2b: EPD frame energies / crossings =================
     int f1 = 0;
     if (a.do_epd && n >= fl) f1 = (n - fl) / fs + 1;
     {
-      double emx = 0.0, amx = 0.0;
-      for (int f = tid; f < f1; f += kPcmThreads) {
+      double emx = 0.0, emn = INFINITY, amx = 0.0;
+      for (int f = tid; f < f1; f += kMainThreads) {
         const int p = f * fs, q = p + fl;
         long long s1 = 0; unsigned long long s2 = 0;
         const int ga = (p + kGroup - 1) / kGroup, gb = q / kGroup;
@@ -443,38 +565,119 @@ frontend_pcm_kernel(const PcmArgs a) {
           direct(p, ga * kGroup);
           direct(gb * kGroup, q);
         }
-        // sum (d - phi)^2 from exact integer sums; `mag` bounds the rounding of the three terms
+        // sum (d - phi)^2 from exact integer sums; `amx` bounds the rounding of the three terms
         const double t1 = 2.0 * uc.phi_d * (double)s1, t2 = (double)fl * uc.phi_d * uc.phi_d;
         const double ep = ((double)s2 - t1) + t2;
         const double e = ep * uc.inv_m * uc.inv_m;
         s_e[f] = e;
         s_z[f] = count_changes(s_bits, p, q);
-        emx = fmax(emx, e);
+        emx = fmax(emx, e); emn = fmin(emn, e);
         amx = fmax(amx, ((double)s2 + fabs(t1)) + t2);
       }
       emx = warp_reduce(emx, OpMaxD());
+      emn = warp_reduce(emn, OpMinD());
       amx = warp_reduce(amx, OpMaxD());
       double* part = reinterpret_cast<double*>(s_sh);
-      if (lane == 0) { part[wid] = emx; part[kWarps + wid] = amx; }
+      if (lane == 0) { part[wid] = emx; part[kWarps + wid] = amx; part[2 * kWarps + wid] = emn; }
     }
-    __syncthreads();
+    main_sync();
 
     // =========================== P3: endpoint decision ===============================
     int start = 0, end = n;
     if (f1 > 0) {
+      // ---- 90th percentile: block-parallel radix select on float projections of E, first pass
+      //      spread over [E_min, E_max]; the (<= 32) survivors are ranked in float64 by warp 0
+      const double v = (double)(f1 - 1) * (90.0 / 100.0);
+      const bool top = v >= (double)(f1 - 1);
+      int* hist = s_hist;
+      int* sel_state = s_int + 12;        // [0] lo  [1] shift  [2] rank  [3] cnt  [4] shift used  [5] cand count
+      int* cand_idx = reinterpret_cast<int*>(s_cand);
+      if (tid == 0) {
+        const double* part = reinterpret_cast<const double*>(s_sh);
+        double emx = 0.0, emn = INFINITY;
+        for (int w = 0; w < kMainWarps; ++w) { emx = fmax(emx, part[w]); emn = fmin(emn, part[2 * kWarps + w]); }
+        const uint32_t kmin = __float_as_uint((float)emn), kmax = __float_as_uint((float)emx);
+        sel_state[0] = (int)kmin;
+        sel_state[1] = first_shift(kmin, kmax);
+        sel_state[2] = top ? f1 - 1 : (int)floor(v);
+        sel_state[3] = f1;
+        sel_state[4] = 32;
+        sel_state[5] = 0;
+      }
+      main_sync();
+      while (sel_state[3] > 32) {
+        const uint32_t lo = (uint32_t)sel_state[0];
+        const int s = sel_state[1];
+        for (int i = tid; i < 256; i += kMainThreads) hist[i] = 0;
+        main_sync();
+        for (int f = tid; f < f1; f += kMainThreads) {
+          const uint32_t k = __float_as_uint((float)s_e[f]);
+          if (k >= lo) { const uint32_t d = (k - lo) >> s; if (d < 256u) atomicAdd(&hist[d], 1); }
+        }
+        main_sync();
+        if (wid == 0) {
+          int digit, rank, cnt;
+          scan_bins(hist, lane, sel_state[2], &digit, &rank, &cnt);
+          __syncwarp();
+          if (lane == 0) {
+            sel_state[0] = (int)(lo + ((uint32_t)digit << s));
+            sel_state[4] = s;
+            sel_state[2] = rank;
+            sel_state[3] = (s == 0 && cnt > 32) ? -cnt : cnt;     // negative: cannot be split further
+            sel_state[1] = s > 8 ? s - 8 : 0;
+          }
+        }
+        main_sync();
+      }
+      {
+        // gather the candidate frames of the final bin
+        const uint32_t lo = (uint32_t)sel_state[0];
+        const unsigned long long span = 1ull << sel_state[4];
+        const bool all = f1 <= 32;
+        for (int f = tid; f < f1; f += kMainThreads) {
+          const uint32_t k = __float_as_uint((float)s_e[f]);
+          if (all || (k >= lo && (unsigned long long)(k - lo) < span)) {
+            const int slot = atomicAdd(&sel_state[5], 1);
+            if (slot < 32) cand_idx[slot] = f;
+          }
+        }
+      }
+      main_sync();
       if (wid == 0) {
         const int nf = min(5, f1 / 10);
-        uint64_t ka, kb;
-        const double v = (double)(f1 - 1) * (90.0 / 100.0);
-        auto get = [&](int i) { return f64_key(s_e[i]); };
-        const bool top = v >= (double)(f1 - 1);
-        warp_select_pair(get, f1, top ? f1 - 1 : (int)floor(v), s_hist, s_cand, &ka, &kb);
+        int cnt = sel_state[3];
+        const int rank = sel_state[2];
+        bool unresolved = false;
+        if (cnt < 0) { cnt = 32; unresolved = true; }     // > 32 frames share one float: replay in float64
+        const double mine = lane < cnt ? s_e[cand_idx[lane]] : INFINITY;
+        int below = 0;
+        for (int j = 0; j < cnt; ++j) {
+          const double o = __shfl_sync(0xffffffffu, mine, j);
+          below += (o < mine) || (o == mine && j < lane);
+        }
+        const int r1 = unresolved ? 0 : rank;
+        const unsigned m1 = __ballot_sync(0xffffffffu, lane < cnt && below == r1);
+        const unsigned m2 = __ballot_sync(0xffffffffu, lane < cnt && below == r1 + 1);
+        const double ka = __shfl_sync(0xffffffffu, mine, __ffs(m1) - 1);
+        double kb = m2 ? __shfl_sync(0xffffffffu, mine, __ffs(m2) - 1) : ka;
+        if (!m2 && !top) {               // rank + 1 lies above the candidate bin
+          const uint32_t lo = (uint32_t)sel_state[0];
+          const unsigned long long span = 1ull << sel_state[4];
+          double nxt = INFINITY;
+          for (int f = lane; f < f1; f += 32) {
+            const double e = s_e[f];
+            const uint32_t k = __float_as_uint((float)e);
+            if (k >= lo && (unsigned long long)(k - lo) >= span) nxt = fmin(nxt, e);
+          }
+          nxt = warp_reduce(nxt, OpMinD());
+          kb = nxt == INFINITY ? ka : nxt;
+        }
         if (top) kb = ka;
         if (lane == 0) {
           const double* part = reinterpret_cast<const double*>(s_sh);
           double emx = 0.0, amx = 0.0;
-          for (int w = 0; w < kWarps; ++w) { emx = fmax(emx, part[w]); amx = fmax(amx, part[kWarps + w]); }
-          const double speech = np_lerp(key_f64(ka), key_f64(kb), v - floor(v));
+          for (int w = 0; w < kMainWarps; ++w) { emx = fmax(emx, part[w]); amx = fmax(amx, part[kWarps + w]); }
+          const double speech = np_lerp(ka, kb, v - floor(v));
           double noise_e, noise_z;
           if (nf > 0) {
             auto te = [&](int64_t i) { return i < nf ? s_e[i] : s_e[f1 - 2 * nf + i]; };
@@ -500,14 +703,15 @@ frontend_pcm_kernel(const PcmArgs a) {
           s_dbl[6] = tol1 + smax + eps * emx;      // per-frame slack bounded at its utterance maximum
           s_dbl[7] = tol2 + smax + eps * emx;
           s_int[6] = 0; s_int[7] = f1 - 1; s_int[8] = 0; s_int[9] = f1 - 1;
+          if (unresolved) s_int[3] = 1;
         }
       }
-      __syncthreads();
+      main_sync();
       const double t1 = s_dbl[3], t2 = s_dbl[4], t3 = s_dbl[5];
       const double tol1 = s_dbl[6], tol2 = s_dbl[7];
       {
         int n3 = f1, n4 = -1, flag = 0;
-        for (int f = tid; f < f1; f += kPcmThreads) {
+        for (int f = tid; f < f1; f += kMainThreads) {
           const double e = s_e[f];
           if (e > t1) { n3 = min(n3, f); n4 = max(n4, f); }
           if (fabs(e - t1) <= tol1 && !(e == 0.0 && t1 == 0.0)) flag = 1;
@@ -521,40 +725,39 @@ frontend_pcm_kernel(const PcmArgs a) {
           if (flag) atomicOr(&s_int[3], 1);
         }
       }
-      __syncthreads();
+      main_sync();
       const int n3 = s_int[4], n4 = s_int[5];
       if (n4 >= 0) {
         {
           int n2 = 0, n5 = f1 - 1;
-          for (int f = tid; f < f1; f += kPcmThreads)
+          for (int f = tid; f < f1; f += kMainThreads)
             if (s_e[f] <= t2) { if (f < n3) n2 = max(n2, f + 1); if (f > n4) n5 = min(n5, f - 1); }
           n2 = warp_reduce(n2, OpMaxI()); n5 = warp_reduce(n5, OpMinI());
           if (lane == 0) { if (n2 > 0) atomicMax(&s_int[6], n2); if (n5 < f1 - 1) atomicMin(&s_int[7], n5); }
         }
-        __syncthreads();
+        main_sync();
         const int n2 = s_int[6], n5 = s_int[7];
         {
           int n1 = 0, n6 = f1 - 1;
-          for (int f = tid; f < f1; f += kPcmThreads)
+          for (int f = tid; f < f1; f += kMainThreads)
             if ((double)s_z[f] <= t3) { if (f < n2) n1 = max(n1, f + 1); if (f > n5) n6 = min(n6, f - 1); }
           n1 = warp_reduce(n1, OpMaxI()); n6 = warp_reduce(n6, OpMinI());
           if (lane == 0) { if (n1 > 0) atomicMax(&s_int[8], n1); if (n6 < f1 - 1) atomicMin(&s_int[9], n6); }
         }
-        __syncthreads();
+        main_sync();
         start = s_int[8] * fs;
         end = min(s_int[9] * fs + fl, n);
       }
       // EPD lists out (the group-sum region is dead from here on; E/Z stay valid)
       if (a.out.epd_energy || a.out.epd_zcr) {
         const int64_t eo = a.epd_offsets[u];
-        for (int f = tid; f < f1; f += kPcmThreads) {
+        for (int f = tid; f < f1; f += kMainThreads) {
           if (a.out.epd_energy) a.out.epd_energy[eo + f] = s_e[f];
           if (a.out.epd_zcr) a.out.epd_zcr[eo + f] = (float)s_z[f];
         }
       }
     }
     const int flagged = s_int[3];
-    __syncthreads();
 
     // =========================== P4: windowed frame features =========================
     const int seg = end - start;
@@ -564,7 +767,7 @@ frontend_pcm_kernel(const PcmArgs a) {
     if (f2_chain > f2) f2_chain = f2;
     if (f2_chain > 0) {
       // 16 lanes per chain; a chain covers `per` consecutive frames = per + 1 hop blocks.
-      constexpr int kChains = kPcmThreads / 16;
+      constexpr int kChains = kMainThreads / 16;
       const int chain = tid >> 4, sub = tid & 15;
       const int per = (f2_chain + kChains - 1) / kChains;
       const int fa = chain * per, fb = min(fa + per, f2_chain);
@@ -593,17 +796,17 @@ frontend_pcm_kernel(const PcmArgs a) {
         // frame b-1 = first half carried from the previous block (in e1/m1 through ce/cm) + this
         // block as its second half: transposed reduction of (e1, m1) over the chain's 16 lanes
         const float send = hi8 ? e1 : m1, keep = hi8 ? m1 : e1;
-        float v = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 2);
-        v += __shfl_xor_sync(0xffffffffu, v, 1);
-        if (live && b > fa && (sub & 7) == 0) (hi8 ? s_fm : s_fe)[b - 1] = v;    // raw sums, scaled below
+        float vv = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        vv += __shfl_xor_sync(0xffffffffu, vv, 4);
+        vv += __shfl_xor_sync(0xffffffffu, vv, 2);
+        vv += __shfl_xor_sync(0xffffffffu, vv, 1);
+        if (live && b > fa && (sub & 7) == 0) (hi8 ? s_fm : s_fe)[b - 1] = vv;    // raw sums, scaled below
       }
     }
     if (f2_chain < f2) {
       const int sub = tid & (kLanesPerFrame - 1);
       const int slot = tid / kLanesPerFrame;
-      constexpr int kSlots = kPcmThreads / kLanesPerFrame;
+      constexpr int kSlots = kMainThreads / kLanesPerFrame;
       const bool vec_ok = ((start & 7) == 0) && ((fs & 7) == 0);
       const float phi = uc.phi;
       for (int t0 = f2_chain; t0 < f2; t0 += kSlots) {
@@ -618,9 +821,9 @@ frontend_pcm_kernel(const PcmArgs a) {
             const int nv = valid >> 3;
             const int4* xv = reinterpret_cast<const int4*>(s_x + p);
             const float4* wv = reinterpret_cast<const float4*>(s_win);
-            for (int v = sub; v < nv; v += kLanesPerFrame) {
-              const int4 q = xv[v];
-              const float4 wa = wv[2 * v], wb = wv[2 * v + 1];
+            for (int vq = sub; vq < nv; vq += kLanesPerFrame) {
+              const int4 q = xv[vq];
+              const float4 wa = wv[2 * vq], wb = wv[2 * vq + 1];
               const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
               const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
@@ -648,11 +851,11 @@ frontend_pcm_kernel(const PcmArgs a) {
         if (t < f2 && sub == 0) { s_fe[t] = e; s_fm[t] = m; }                      // raw sums, scaled below
       }
     }
-    __syncthreads();
+    main_sync();
     // peak normalisation (1/m^2, 1/m) and zero crossings, one frame per thread.  A full frame of
     // the trimmed segment IS an endpoint-detection frame (start is a multiple of the hop), so its
     // crossing count is already in s_z; only Hanning's zeroed end points need patching.
-    for (int t = tid; t < f2; t += kPcmThreads) {
+    for (int t = tid; t < f2; t += kMainThreads) {
       const int p = start + t * fs;
       const int valid = min(fl, end - p);
       s_fe[t] = (float)((double)s_fe[t] * uc.inv_m * uc.inv_m);
@@ -670,59 +873,32 @@ frontend_pcm_kernel(const PcmArgs a) {
       }
       s_fz[t] = (float)zc;
     }
-    __syncthreads();   // samples / sign bits are dead: the next utterance may be loaded
+    // per-utterance scalars, mailbox for the stats warps
+    if (tid == 0) {
+      int status = DSP_UTT_OK;
+      if (seg <= 0) status = DSP_UTT_EMPTY; else if (f2 == 0) status = DSP_UTT_NO_FRAMES;
+      if (a.out.start) a.out.start[u] = start;
+      if (a.out.end) a.out.end[u] = end;
+      if (a.out.n_epd_frames) a.out.n_epd_frames[u] = f1;
+      if (a.out.n_frames) a.out.n_frames[u] = f2;
+      if (a.out.status) a.out.status[u] = status;
+      if (flagged) { const int slot = atomicAdd(a.flag_count, 1); a.flag_list[slot] = u; }
+      int* mb = s_mail + 8 * (iter & 1);
+      mb[0] = u; mb[1] = f2;
+    }
+    main_sync();   // samples / sign bits are dead, features + mailbox are complete
+    bar_arrive(kBarFeatFull, kPcmThreads);
 
-    if (tid == 0) s_int[0] = (int)atomicAdd(a.work_counter, 1u);
-    __syncthreads();
     const int u_next = s_int[0];
     if (u_next < a.n_utts) issue_load(u_next);
-
-    // =========================== P5: statistics, one warp per sequence ===============
-    if (f2 > 0 && a.out.stats && wid < 3) {
-      const float* seq = wid == 0 ? s_fe : (wid == 1 ? s_fm : s_fz);
-      double sum = 0.0; float mx = -INFINITY, mn = INFINITY;
-      for (int i = lane; i < f2; i += 32) { const float x = seq[i]; sum += (double)x; mx = fmaxf(mx, x); mn = fminf(mn, x); }
-      sum = warp_reduce(sum, OpAddD());
-      mx = warp_reduce(mx, [](float x, float y) { return fmaxf(x, y); });
-      mn = warp_reduce(mn, [](float x, float y) { return fminf(x, y); });
-      const double mean = sum / (double)f2;
-      double ss = 0.0;
-      for (int i = lane; i < f2; i += 32) { const double d = (double)seq[i] - mean; ss += d * d; }
-      ss = warp_reduce(ss, OpAddD());
-      uint64_t ka, kb;
-      auto get = [&](int i) { return f64_key((double)seq[i]); };
-      warp_select_pair(get, f2, (f2 - 1) / 2, s_hist + 256 * wid, s_cand + 32 * wid, &ka, &kb);
-      if (lane == 0) {
-        float* o = a.out.stats + (int64_t)u * kStats + 5 * wid;
-        o[0] = (float)mean;
-        o[1] = (float)sqrt(ss / (double)f2);
-        o[2] = mx; o[3] = mn;
-        o[4] = (f2 & 1) ? (float)key_f64(ka) : (float)((key_f64(ka) + key_f64(kb)) * 0.5);
-      }
-    }
-
-    // =========================== P6: outputs =========================================
-    {
-      const int64_t fo = a.feat_offsets[u];
-      for (int t = tid; t < f2; t += kPcmThreads) {
-        if (a.out.energy) a.out.energy[fo + t] = s_fe[t];
-        if (a.out.magnitude) a.out.magnitude[fo + t] = s_fm[t];
-        if (a.out.zcr) a.out.zcr[fo + t] = s_fz[t];
-      }
-      if (tid == 0) {
-        int status = DSP_UTT_OK;
-        if (seg <= 0) status = DSP_UTT_EMPTY; else if (f2 == 0) status = DSP_UTT_NO_FRAMES;
-        if (a.out.start) a.out.start[u] = start;
-        if (a.out.end) a.out.end[u] = end;
-        if (a.out.n_epd_frames) a.out.n_epd_frames[u] = f1;
-        if (a.out.n_frames) a.out.n_frames[u] = f2;
-        if (a.out.status) a.out.status[u] = status;
-        if (flagged) { const int slot = atomicAdd(a.flag_count, 1); a.flag_list[slot] = u; }
-      }
-    }
-    __syncthreads();
     u = u_next;
+    ++iter;
   }
+  // tell the stats warps to stop
+  if (iter > 0) bar_sync(kBarFeatEmpty, kPcmThreads);
+  if (tid == 0) s_mail[8 * (iter & 1)] = -1;
+  main_sync();
+  bar_arrive(kBarFeatFull, kPcmThreads);
 }
 
 cudaError_t launch_frontend_pcm(const PcmArgs& a, int grid, size_t smem, cudaStream_t st) {
