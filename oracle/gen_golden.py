@@ -222,8 +222,27 @@ def main():
         ks[f"{tag}/fit_method"] = np.array(clf.model._fit_method)
     np.savez_compressed(os.path.join(OUT, "knn_golden.npz"), **ks)
 
+    # ---- the Python call surface itself -------------------------
+    import inspect
+    import json
+    import config as ref_config
+    sig = {}
+    for mod, names in ((ap, ["load_wav", "remove_dc", "normalize_audio", "preprocess", "compute_short_time_energy",
+                             "compute_short_time_magnitude", "compute_zero_crossing_rate", "endpoint_detection",
+                             "create_window", "frame_signal", "process_audio_file"]),
+                       (fe, ["extract_frame_features", "compute_statistics", "extract_statistical_features",
+                             "extract_features_from_frames", "pad_or_truncate_sequence", "normalize_features"]),
+                       (mo, ["create_classifier"])):
+        for n in names:
+            sig[f"{mod.__name__}.{n}"] = str(inspect.signature(getattr(mod, n)))
+    cfg = {k: getattr(ref_config, k) for k in dir(ref_config)
+           if k.isupper() and k not in ("BASE_DIR", "DATA_DIR", "RESULTS_DIR", "DATASET_PATHS", "DATASET_TYPE")}
+    with open(os.path.join(OUT, "surface.json"), "w") as f:
+        json.dump({"signatures": sig, "config": cfg,
+                   "config_names": sorted(k for k in dir(ref_config) if k.isupper())}, f, indent=1, sort_keys=True)
+
     shutil.rmtree(tmp, ignore_errors=True)
-    for f in ("frontend_golden.npz", "knn_golden.npz"):
+    for f in ("frontend_golden.npz", "knn_golden.npz", "surface.json"):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 
 

@@ -1,0 +1,83 @@
+"""CPU, world_size 2 over gloo: the host-side logic of the multi-GPU path (sharding, candidate
+exchange, merge).  The compute callbacks are the oracle here -- the product has no CPU path."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import GOLDEN
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _oracle_topk(train, labels, queries, k, index_base):
+    from oracle import knn_oracle as ko
+    idx, d2 = ko.knn_topk(train.numpy(), queries.numpy(), k)
+    lab = labels.numpy()[idx]
+    return torch.from_numpy(d2), torch.from_numpy(idx + index_base), torch.from_numpy(lab.astype(np.int32))
+
+
+def _oracle_merge(cd, ci, cl):
+    from oracle import knn_oracle as ko
+    mi, _ = ko.merge_candidates(cd.numpy(), ci.numpy(), cd.shape[2])
+    flat_i = np.transpose(ci.numpy(), (1, 0, 2)).reshape(ci.shape[1], -1)
+    flat_l = np.transpose(cl.numpy(), (1, 0, 2)).reshape(ci.shape[1], -1)
+    lab = np.stack([[flat_l[q][np.where(flat_i[q] == i)[0][0]] for i in mi[q]] for q in range(len(mi))]) \
+        if len(mi) else np.zeros((0, cd.shape[2]), np.int32)
+    classes = np.unique(cl.numpy())
+    return torch.from_numpy(ko.vote(lab, classes).astype(np.int32))
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dsp_audioreclabs_b200 import dist as ddist
+    k = np.load(os.path.join(GOLDEN, "knn_golden.npz"))
+    xn, y, qn = k["d15/train_norm"], k["d15/train_labels"].astype(np.int32), k["d15/query_norm"][:120]
+    tb = ddist.balanced_bounds(len(xn), world)
+    qb = ddist.balanced_bounds(len(qn), world)
+    knn = ddist.ShardedKNN(3, local_topk=_oracle_topk, merge_vote=_oracle_merge)
+    knn.fit(torch.from_numpy(xn[tb[rank]:tb[rank + 1]]), torch.from_numpy(y[tb[rank]:tb[rank + 1]]))
+    assert knn.index_base == tb[rank]
+    q_local = torch.from_numpy(qn[qb[rank]:qb[rank + 1]])
+    a = knn.predict(q_local).numpy()
+    b = knn.predict_replicated(q_local).numpy()
+    mean, std = ddist.zscore_stats_allreduce(torch.from_numpy(k["d15/train"][tb[rank]:tb[rank + 1]]))
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), a=a, b=b, lo=qb[rank], hi=qb[rank + 1],
+             mean=mean.numpy(), std=std.numpy())
+    dist.destroy_process_group()
+
+
+def test_sharded_knn_world2_matches_single_rank(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    k = np.load(os.path.join(GOLDEN, "knn_golden.npz"))
+    for r in range(world):
+        o = np.load(tmp_path / f"r{r}.npz")
+        ref = k["d15/pred"][int(o["lo"]):int(o["hi"])]
+        assert np.array_equal(o["a"], ref)          # candidate all-gather path
+        assert np.array_equal(o["b"], ref)          # train all-gather fast path
+        assert np.allclose(o["mean"], k["d15/mean"], rtol=1e-12, atol=1e-14)
+        assert np.allclose(o["std"], k["d15/std"], rtol=1e-12)
+
+
+def test_utterance_shards_balance_by_samples():
+    from dsp_audioreclabs_b200 import dist as ddist
+    rng = np.random.default_rng(0)
+    lens = rng.integers(30000, 53000, 1000)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    for world in (1, 2, 4, 8):
+        b = ddist.utterance_shards(off, world)
+        assert b[0] == 0 and b[-1] == 1000 and np.all(np.diff(b) >= 0)
+        per = np.array([off[b[r + 1]] - off[b[r]] for r in range(world)])
+        assert per.max() - per.min() <= 2 * lens.max()
+    assert list(ddist.balanced_bounds(10, 4)) == [0, 3, 6, 8, 10]
