@@ -131,10 +131,12 @@ class FrontendResult:
 def frontend_batch(samples, offsets, frame_length, frame_shift, window_type="hamming",
                    do_endpoint_detection=True, energy_high_ratio=0.5, energy_low_ratio=0.1,
                    zcr_threshold_ratio=1.5, channels=1, emit_epd_lists=False, force_exact=False,
-                   ctx=None):
+                   emit_frames=True, ctx=None):
     """preprocess -> endpoint_detection -> frame_signal -> extract_frame_features -> 15 statistics
     for every utterance of a packed batch (src/audio_processing.py:364-394 and
-    src/feature_extraction.py:91-112, batched).  `samples` is int16 / uint8 PCM or float32/64."""
+    src/feature_extraction.py:91-112, batched).  `samples` is int16 / uint8 PCM or float32/64.
+    emit_frames=False skips the download of the per-frame sequences (the callers of the
+    'statistical' method only consume the 15 statistics, run_experiments.py:102-107)."""
     ctx = _host_ctx(ctx)
     samples = np.ascontiguousarray(samples)
     if samples.dtype not in _DTYPES:
@@ -149,8 +151,9 @@ def frontend_batch(samples, offsets, frame_length, frame_shift, window_type="ham
     res = FrontendResult(
         start=np.zeros(b, np.int32), end=np.zeros(b, np.int32), n_epd_frames=np.zeros(b, np.int32),
         n_frames=np.zeros(b, np.int32), status=np.zeros(b, np.int32),
-        energy=np.zeros(int(fo[-1]), np.float32), magnitude=np.zeros(int(fo[-1]), np.float32),
-        zcr=np.zeros(int(fo[-1]), np.float32), stats=np.zeros((b, 15), np.float32),
+        energy=np.zeros(int(fo[-1]), np.float32) if emit_frames else None,
+        magnitude=np.zeros(int(fo[-1]), np.float32) if emit_frames else None,
+        zcr=np.zeros(int(fo[-1]), np.float32) if emit_frames else None, stats=np.zeros((b, 15), np.float32),
         feat_offsets=fo, epd_offsets=eo, max_len=max_len,
         epd_energy=np.zeros(int(eo[-1]), np.float64) if emit_epd_lists else None,
         epd_zcr=np.zeros(int(eo[-1]), np.float32) if emit_epd_lists else None)
