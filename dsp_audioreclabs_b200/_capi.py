@@ -26,7 +26,7 @@ class FrontendParams(C.Structure):
         ("do_endpoint_detection", C.c_int32),
         ("energy_high_ratio", C.c_double), ("energy_low_ratio", C.c_double),
         ("zcr_threshold_ratio", C.c_double),
-        ("channels", C.c_int32), ("force_exact", C.c_int32),
+        ("channels", C.c_int32), ("force_exact", C.c_int32), ("aligned16", C.c_int32),
     ]
 
 
@@ -50,6 +50,7 @@ SIGNATURES = {
     "dsp_destroy": (C.c_int, [_P]),
     "dsp_set_stream": (C.c_int, [_P, _P]),
     "dsp_use_own_stream": (C.c_int, [_P]),
+    "dsp_set_tuning": (C.c_int, [_P, C.c_char_p, C.c_int]),
     "dsp_sync": (C.c_int, [_P]),
     "dsp_launch_count": (_I64, [_P]),
     "dsp_device_sm_count": (C.c_int, [_P]),

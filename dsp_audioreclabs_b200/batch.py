@@ -50,6 +50,9 @@ class Context:
     def use_own_stream(self):
         check(self.lib.dsp_use_own_stream(self.handle))
 
+    def set_tuning(self, key, value):
+        check(self.lib.dsp_set_tuning(self.handle, key.encode(), int(value)))
+
     def sync(self):
         check(self.lib.dsp_sync(self.handle))
 
@@ -90,7 +93,7 @@ def make_params(frame_length, frame_shift, window_type="hamming", do_endpoint_de
     return FrontendParams(int(frame_length), int(frame_shift), WINDOW_IDS[window_type],
                           int(bool(do_endpoint_detection)), float(energy_high_ratio),
                           float(energy_low_ratio), float(zcr_threshold_ratio), int(channels),
-                          int(bool(force_exact)))
+                          int(bool(force_exact)), 0)
 
 
 def plan(offsets, params):

@@ -102,6 +102,9 @@ struct dsp_context {
   DevBuf counters;   // [0] work counter (u32)  [1] flag count (i32)
   DevBuf flag_list, zbuf, seqbuf;
   size_t occ_smem = 0;
+  int occ_variant = -1;
+  int pcm_variant = -1;         // -1 automatic; else a build of frontend_pcm.cu's kVariants (dsp_set_tuning / DSP_PCM_VARIANT)
+  int stagger_ns = 0;           // DSP_STAGGER_NS (tuning knob)
   int tma_chunk = 4096;         // bytes per bulk copy; DSP_TMA_CHUNK overrides (tuning knob)
   int occ = 0;
   Slot slot[2];
@@ -217,9 +220,15 @@ int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_
               feat_offsets;
   size_t smem = 0;
   int cap_samples = 0;
+  // automatic choice: the streaming build when the caller vouches for 16-byte aligned utterances,
+  // the shared-memory-resident build (any alignment) otherwise
+  constexpr int kAutoStream = 2, kAutoResident = 0;
+  int variant = c->pcm_variant >= 0 ? c->pcm_variant : (p->aligned16 ? kAutoStream : kAutoResident);
+  if (pcm_variant_streams(variant) && !p->aligned16 && c->pcm_variant < 0) variant = kAutoResident;
   if (fast) {
     cap_samples = (int)((std::max<int64_t>(max_len, 1) + 63) / 64 * 64);
-    smem = pcm_kernel_smem_bytes(cap_samples, (int)cap_frames64, fl);
+    smem = pcm_kernel_smem_bytes(cap_samples, (int)cap_frames64, fl, !pcm_variant_streams(variant));
+    if (smem > kMaxSmemPerCta && !pcm_variant_streams(variant)) fast = false;
     if (smem > kMaxSmemPerCta) fast = false;
   }
   if (!fast) {
@@ -228,9 +237,10 @@ int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_
     return launch_exact(c, samples, dtype, offsets, feat_offsets, epd_offsets, nullptr, nullptr, B, max_len,
                         p, out, ex, grid);
   }
-  if (c->occ_smem != smem) {
-    c->occ = pcm_kernel_max_ctas_per_sm(smem);
+  if (c->occ_smem != smem || c->occ_variant != variant) {
+    c->occ = pcm_kernel_max_ctas_per_sm(variant, smem);
     c->occ_smem = smem;
+    c->occ_variant = variant;
     if (c->occ < 1) return fail(DSP_ERR_CUDA, "fast kernel does not fit: %zu bytes of shared memory", smem);
   }
   CU(c->counters.ensure(64));
@@ -244,12 +254,14 @@ int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_
   a.win_f32 = c->win32.as<float>();
   a.cap_samples = cap_samples; a.cap_frames = (int)cap_frames64;
   a.tma_chunk = c->tma_chunk;
+  a.stagger_ns = c->stagger_ns;
+  a.sm_count = c->sm_count;
   a.work_counter = c->counters.as<unsigned int>();
   a.flag_count = c->counters.as<int32_t>() + 1;
   a.flag_list = c->flag_list.as<int32_t>();
   a.out = *out;
   const int grid = (int)std::min<int64_t>(B, (int64_t)c->sm_count * c->occ);
-  CU(launch_frontend_pcm(a, grid, smem, c->stream));
+  CU(launch_frontend_pcm(variant, a, grid, smem, c->stream));
   c->launches++;
   // float64 replay of the utterances whose threshold margins could not be certified
   ExactExtras ex;
@@ -298,6 +310,8 @@ int dsp_create(int device, dsp_context** out) {
   CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
   c->stream = c->own;
+  if (const char* e = std::getenv("DSP_PCM_VARIANT")) { int v = std::atoi(e); if (v >= -1 && v < pcm_num_variants()) c->pcm_variant = v; }
+  if (const char* e = std::getenv("DSP_STAGGER_NS")) c->stagger_ns = std::atoi(e);
   if (const char* e = std::getenv("DSP_TMA_CHUNK")) { int v = std::atoi(e); if (v >= 16 && v % 16 == 0) c->tma_chunk = v; }
   for (auto& s : c->slot) {
     CU(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
@@ -338,6 +352,22 @@ int dsp_set_stream(dsp_context* c, void* cuda_stream) {
 int dsp_use_own_stream(dsp_context* c) {
   if (!c) return fail(DSP_ERR_INVALID, "context is NULL");
   c->stream = c->own;
+  return DSP_OK;
+}
+
+int dsp_set_tuning(dsp_context* c, const char* key, int value) {
+  if (!c || !key) return fail(DSP_ERR_INVALID, "bad argument");
+  if (!std::strcmp(key, "pcm_variant")) {
+    if (value < -1 || value >= pcm_num_variants()) return fail(DSP_ERR_INVALID, "pcm_variant out of range (%d builds)", pcm_num_variants());
+    c->pcm_variant = value;
+  } else if (!std::strcmp(key, "tma_chunk")) {
+    if (value < 16 || value % 16) return fail(DSP_ERR_INVALID, "tma_chunk must be a positive multiple of 16");
+    c->tma_chunk = value;
+  } else if (!std::strcmp(key, "stagger_ns")) {
+    c->stagger_ns = value;
+  } else {
+    return fail(DSP_ERR_INVALID, "unknown tuning key '%s'", key);
+  }
   return DSP_OK;
 }
 
@@ -457,7 +487,10 @@ int dsp_frontend_batch_host(dsp_context* c, const void* samples, int dtype, cons
     o.epd_energy = out->epd_energy ? s.epd_e.as<double>() : nullptr;
     o.epd_zcr = out->epd_zcr ? s.epd_z.as<float>() : nullptr;
     const int64_t* doff = s.off.as<int64_t>();
-    rc = frontend_device(c, s.samples.p, dtype, doff, doff + (bc + 1), doff + 2 * (bc + 1), bc, chunk_max, p, &o);
+    dsp_frontend_params pc = *p;
+    pc.aligned16 = 1;                               // staging buffers come from cudaMalloc (256-byte aligned)
+    for (int64_t i = 0; i < bc && pc.aligned16; ++i) if ((size_t)h[i] * esz % 16) pc.aligned16 = 0;
+    rc = frontend_device(c, s.samples.p, dtype, doff, doff + (bc + 1), doff + 2 * (bc + 1), bc, chunk_max, &pc, &o);
     if (rc) return rc;
     CU(cudaEventRecord(s.ev_k, c->stream));
     CU(cudaStreamWaitEvent(c->s_out, s.ev_k, 0));

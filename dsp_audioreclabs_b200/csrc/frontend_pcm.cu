@@ -32,7 +32,6 @@ namespace {
 
 constexpr int kGroup = 64;          // samples per group-sum record
 constexpr int kLanesPerFrame = 8;   // generic P4: lanes cooperating on one frame
-constexpr int kWarps = kPcmThreads / 32;
 
 struct SmemLayout {
   int samples, bits, g2, g1, e, z, win, hist, cand, sh, misc, total;
@@ -40,11 +39,11 @@ struct SmemLayout {
 
 __host__ __device__ inline int align16(int x) { return (x + 15) & ~15; }
 
-__host__ __device__ inline SmemLayout make_layout(int cap_samples, int cap_frames, int fl) {
+__host__ __device__ inline SmemLayout make_layout(int cap_samples, int cap_frames, int fl, bool resident) {
   SmemLayout L;
   const int ng = cap_samples / kGroup;
   int o = 0;
-  L.samples = o; o += align16(2 * cap_samples + 32);
+  L.samples = o; o += resident ? align16(2 * cap_samples + 32) : 0;
   L.bits = o;    o += align16(4 * (cap_samples / 32 + 4));
   // group sums; the same region later holds the three float feature sequences
   const int gbytes = 12 * ng, fbytes = 12 * cap_frames;
@@ -153,9 +152,6 @@ struct UttConst {
 };
 
 // ---- named barriers (warp-specialised roles) --------------------------------------------
-constexpr int kStatsWarps = 2;
-constexpr int kMainWarps = kWarps - kStatsWarps;
-constexpr int kMainThreads = kMainWarps * 32;
 constexpr int kBarMain = 1;       // main warps only
 constexpr int kBarFeatFull = 2;   // main arrive, stats wait: feature sequences are in shared memory
 constexpr int kBarFeatEmpty = 3;  // stats arrive, main wait: feature sequences have been consumed
@@ -163,7 +159,6 @@ constexpr int kStatsRegs = 11;    // feature frames per lane held in registers b
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void main_sync() { bar_sync(kBarMain, kMainThreads); }
 
 // Radix-select bookkeeping shared by the block- and warp-level selects: after the 256-bin
 // histogram of (key - lo) >> s is in `hist`, one warp finds the bin holding `rank`.
@@ -283,14 +278,23 @@ __device__ void warp_sequence_stats(Acc acc, int n, int* hist, float* cand, floa
 
 }  // namespace
 
-size_t pcm_kernel_smem_bytes(int cap_samples, int cap_frames, int fl) {
-  return (size_t)make_layout(cap_samples, cap_frames, fl).total;
+size_t pcm_kernel_smem_bytes(int cap_samples, int cap_frames, int fl, bool resident) {
+  return (size_t)make_layout(cap_samples, cap_frames, fl, resident).total;
 }
 
-__global__ void __launch_bounds__(kPcmThreads, 2)
+// kStream: samples are read straight from global memory (pass P1 from HBM, the later passes hit
+// L2) instead of being staged in shared memory: ~20 KB of shared memory per CTA instead of
+// ~112 KB, so more independent utterance pipelines fit on an SM.  Requires 16-byte aligned
+// utterance starts (layout_hint); anything else is replayed by the float64 kernel.
+template <bool kStream, int kThreads, int kStatsWarps, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 frontend_pcm_kernel(const PcmArgs a) {
+  constexpr int kWarps = kThreads / 32;
+  constexpr int kMainWarps = kWarps - kStatsWarps;
+  constexpr int kMainThreads = kMainWarps * 32;
+  auto main_sync = [&]() { bar_sync(kBarMain, kMainThreads); };
   extern __shared__ __align__(128) unsigned char smem[];
-  const SmemLayout L = make_layout(a.cap_samples, a.cap_frames, a.fl);
+  const SmemLayout L = make_layout(a.cap_samples, a.cap_frames, a.fl, !kStream);
   int16_t* s_x = reinterpret_cast<int16_t*>(smem + L.samples);
   uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + L.bits);
   unsigned long long* s_g2 = reinterpret_cast<unsigned long long*>(smem + L.g2);
@@ -315,23 +319,29 @@ frontend_pcm_kernel(const PcmArgs a) {
   const int fl = a.fl, fs = a.fs;
   const bool hann = (a.window == DSP_WIN_HANNING);
 
-  for (int j = tid; j < fl; j += kPcmThreads) s_win[j] = a.win_f32[j];
+  for (int j = tid; j < fl; j += kThreads) s_win[j] = a.win_f32[j];
   if (tid == 0) {
     mbar_init(s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     s_int[0] = (int)atomicAdd(a.work_counter, 1u);
   }
   __syncthreads();
+  // de-phase the CTAs that share an SM: identical utterances make them run in lockstep otherwise,
+  // so that their barrier / load bubbles coincide instead of filling one another
+  if (a.stagger_ns > 0) {
+    const unsigned wave = blockIdx.x / (unsigned)a.sm_count;
+    if (wave > 0) { long long t0 = clock64(); const long long target = (long long)wave * a.stagger_ns * 2; while (clock64() - t0 < target) __nanosleep(200); }
+  }
 
   // =========================================================================================
   // STATS WARPS: statistics + outputs of utterance i while the main warps work on utterance i+1
   // =========================================================================================
   if (wid >= kMainWarps) {
-    const int sw = wid - kMainWarps;                       // 0: energy, 1: magnitude + zcr
+    const int sw = wid - kMainWarps;                       // owns sequences q with q % kStatsWarps == sw
     int* hist = s_hist + 256 * (1 + sw);
     float* cand = s_cand + 64 * (1 + sw);
     for (int it = 0;; ++it) {
-      bar_sync(kBarFeatFull, kPcmThreads);
+      bar_sync(kBarFeatFull, kThreads);
       const int* mb = s_mail + 8 * (it & 1);
       const int u = mb[0], f2 = mb[1];
       if (u < 0) break;
@@ -340,44 +350,39 @@ frontend_pcm_kernel(const PcmArgs a) {
       float st[5];
       if (f2 <= 32 * kStatsRegs) {
         // copy this warp's sequences to registers so the main warps can reuse the buffers at once
-        float r0[kStatsRegs], r1[kStatsRegs];
-        const float* q0 = sw == 0 ? s_fe : s_fm;
+        float r[3][kStatsRegs];
 #pragma unroll
-        for (int j = 0; j < kStatsRegs; ++j) {
-          const int i = lane + 32 * j;
-          r0[j] = i < f2 ? q0[i] : 0.f;
-          r1[j] = (sw == 1 && i < f2) ? s_fz[i] : 0.f;
-        }
-        bar_arrive(kBarFeatEmpty, kPcmThreads);
-        float* g0 = sw == 0 ? a.out.energy : a.out.magnitude;
+        for (int q = 0; q < 3; ++q) {
+          const float* src = q == 0 ? s_fe : (q == 1 ? s_fm : s_fz);
+          const bool mine = (q % kStatsWarps) == sw;
 #pragma unroll
-        for (int j = 0; j < kStatsRegs; ++j) {
-          const int i = lane + 32 * j;
-          if (i < f2) { if (g0) g0[fo + i] = r0[j]; if (sw == 1 && a.out.zcr) a.out.zcr[fo + i] = r1[j]; }
+          for (int j = 0; j < kStatsRegs; ++j) { const int i = lane + 32 * j; r[q][j] = (mine && i < f2) ? src[i] : 0.f; }
         }
-        if (f2 > 0 && stats) {
-          warp_sequence_stats<kStatsRegs>([&](int j) { return r0[j]; }, f2, hist, cand, st);
-          if (lane == 0) { float* o = stats + (sw == 0 ? 0 : 5); for (int k = 0; k < 5; ++k) o[k] = st[k]; }
-          if (sw == 1) {
-            warp_sequence_stats<kStatsRegs>([&](int j) { return r1[j]; }, f2, hist, cand, st);
-            if (lane == 0) for (int k = 0; k < 5; ++k) stats[10 + k] = st[k];
+        bar_arrive(kBarFeatEmpty, kThreads);
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          if ((q % kStatsWarps) != sw) continue;
+          float* g = q == 0 ? a.out.energy : (q == 1 ? a.out.magnitude : a.out.zcr);
+#pragma unroll
+          for (int j = 0; j < kStatsRegs; ++j) { const int i = lane + 32 * j; if (g && i < f2) g[fo + i] = r[q][j]; }
+          if (f2 > 0 && stats) {
+            warp_sequence_stats<kStatsRegs>([&](int j) { return r[q][j]; }, f2, hist, cand, st);
+            if (lane == 0) for (int k = 0; k < 5; ++k) stats[5 * q + k] = st[k];
           }
         }
       } else {
         // long sequences: work from shared memory, release the buffers afterwards
-        const float* q0 = sw == 0 ? s_fe : s_fm;
-        float* g0 = sw == 0 ? a.out.energy : a.out.magnitude;
-        for (int i = lane; i < f2; i += 32) { if (g0) g0[fo + i] = q0[i]; if (sw == 1 && a.out.zcr) a.out.zcr[fo + i] = s_fz[i]; }
-        if (stats) {
-          warp_sequence_stats<0>([&](int j) { return q0[lane + 32 * j]; }, f2, hist, cand, st);
-          if (lane == 0) { float* o = stats + (sw == 0 ? 0 : 5); for (int k = 0; k < 5; ++k) o[k] = st[k]; }
-          if (sw == 1) {
-            warp_sequence_stats<0>([&](int j) { return s_fz[lane + 32 * j]; }, f2, hist, cand, st);
-            if (lane == 0) for (int k = 0; k < 5; ++k) stats[10 + k] = st[k];
+        for (int q = sw; q < 3; q += kStatsWarps) {
+          const float* src = q == 0 ? s_fe : (q == 1 ? s_fm : s_fz);
+          float* g = q == 0 ? a.out.energy : (q == 1 ? a.out.magnitude : a.out.zcr);
+          for (int i = lane; i < f2; i += 32) if (g) g[fo + i] = src[i];
+          if (stats) {
+            warp_sequence_stats<0>([&](int j) { return src[lane + 32 * j]; }, f2, hist, cand, st);
+            if (lane == 0) for (int k = 0; k < 5; ++k) stats[5 * q + k] = st[k];
           }
         }
         __syncwarp();
-        bar_arrive(kBarFeatEmpty, kPcmThreads);
+        bar_arrive(kBarFeatEmpty, kThreads);
       }
     }
     return;
@@ -387,10 +392,11 @@ frontend_pcm_kernel(const PcmArgs a) {
   // MAIN WARPS
   // =========================================================================================
   uint32_t parity = 0;
+  (void)parity;
   int u = s_int[0];
   int iter = 0;
 
-  // window coefficients of the hop-128 / length-256 chain (P4 fast path): lane owns samples
+  // window coefficients of the hop-128 / length-256 chain (P4 fast path): a lane owns samples
   // 8*(lane&15) .. +8 of every hop block; c = 0 is the first half of a frame, c = 1 the second
   const bool chain_cfg = (fs == 128 && fl == 256);
   float cw[2][8], cw2[2][8];
@@ -398,10 +404,7 @@ frontend_pcm_kernel(const PcmArgs a) {
 #pragma unroll
     for (int c = 0; c < 2; ++c)
 #pragma unroll
-      for (int s = 0; s < 8; ++s) {
-        const float w = s_win[c * 128 + 8 * (lane & 15) + s];
-        cw[c][s] = w; cw2[c][s] = w * w;
-      }
+      for (int q8 = 0; q8 < 8; ++q8) { const float w = s_win[c * 128 + 8 * (lane & 15) + q8]; cw[c][q8] = w; cw2[c][q8] = w * w; }
   }
 
   // issue the load of utterance `uu` (uniform over the main warps)
@@ -443,12 +446,33 @@ frontend_pcm_kernel(const PcmArgs a) {
     main_sync();
   };
 
-  if (u < a.n_utts) issue_load(u);
+  auto ld16 = [&](const void* p) -> int4 {
+    if constexpr (kStream) return __ldg(reinterpret_cast<const int4*>(p));
+    else return *reinterpret_cast<const int4*>(p);
+  };
+
+  if (!kStream && u < a.n_utts) issue_load(u);
 
   while (u < a.n_utts) {
     const int64_t off = a.offsets[u];
     const int n = (int)(a.offsets[u + 1] - off);
-    wait_load(u);
+    const int16_t* x = kStream ? a.samples + off : s_x;
+    if constexpr (kStream) {
+      if (reinterpret_cast<uintptr_t>(x) & 15) {
+        // misaligned start: not this kernel's layout -- hand the utterance to the float64 replay
+        if (tid == 0) {
+          const int slot = atomicAdd(a.flag_count, 1); a.flag_list[slot] = u;
+          s_int[0] = (int)atomicAdd(a.work_counter, 1u);
+        }
+        main_sync();
+        u = s_int[0];
+        main_sync();
+        continue;
+      }
+      main_sync();
+    } else {
+      wait_load(u);
+    }
     if (tid == 0) s_int[0] = (int)atomicAdd(a.work_counter, 1u);   // next utterance, consumed after P4
 
     // =========================== P1: sum, min, max ===================================
@@ -456,18 +480,25 @@ frontend_pcm_kernel(const PcmArgs a) {
       int sum = 0;
       uint32_t mn2 = 0x7fff7fffu, mx2 = 0x80008000u;
       const int nvec = n >> 3;
-      const int4* xv = reinterpret_cast<const int4*>(s_x);
-      for (int v = tid; v < nvec; v += kMainThreads) {
-        const int4 q = xv[v];
+      const int4* xv = reinterpret_cast<const int4*>(x);
+      auto acc1 = [&](const int4& q) {
         sum = __dp2a_lo(q.x, 0x0101, sum); sum = __dp2a_lo(q.y, 0x0101, sum);
         sum = __dp2a_lo(q.z, 0x0101, sum); sum = __dp2a_lo(q.w, 0x0101, sum);
         mn2 = __vmins2(mn2, q.x); mx2 = __vmaxs2(mx2, q.x);
         mn2 = __vmins2(mn2, q.y); mx2 = __vmaxs2(mx2, q.y);
         mn2 = __vmins2(mn2, q.z); mx2 = __vmaxs2(mx2, q.z);
         mn2 = __vmins2(mn2, q.w); mx2 = __vmaxs2(mx2, q.w);
+      };
+      int v = tid;
+      if constexpr (kStream)
+      for (; v + 3 * kMainThreads < nvec; v += 4 * kMainThreads) {       // 4 loads in flight per thread
+        const int4 q0 = ld16(xv + v), q1 = ld16(xv + v + kMainThreads);
+        const int4 q2 = ld16(xv + v + 2 * kMainThreads), q3 = ld16(xv + v + 3 * kMainThreads);
+        acc1(q0); acc1(q1); acc1(q2); acc1(q3);
       }
+      for (; v < nvec; v += kMainThreads) acc1(ld16(xv + v));
       int mn = min(sext16(mn2), (int)mn2 >> 16), mx = max(sext16(mx2), (int)mx2 >> 16);
-      if (tid < (n & 7)) { const int k = s_x[(nvec << 3) + tid]; sum += k; mn = min(mn, k); mx = max(mx, k); }
+      if (tid < (n & 7)) { const int k = x[(nvec << 3) + tid]; sum += k; mn = min(mn, k); mx = max(mx, k); }
       // per-warp partials (a warp sees < 2^31 / 2^15 samples: the utterance fits shared memory)
       sum = warp_reduce(sum, OpAddI());
       mn = warp_reduce(mn, OpMinI());
@@ -498,24 +529,26 @@ frontend_pcm_kernel(const PcmArgs a) {
     uc.inv_m = s_dbl[1]; uc.mu = s_dbl[2];
 
     // the group-sum region doubles as the feature buffers the stats warps may still be reading
-    if (iter > 0) bar_sync(kBarFeatEmpty, kPcmThreads);
+    if (iter > 0) bar_sync(kBarFeatEmpty, kThreads);
 
     // =========================== P2: group sums + sign bits ==========================
     const int ng = (n + kGroup - 1) / kGroup;
     {
-      const int rot = tid & 7;               // == g & 7 for every group this thread owns
+      // resident mode: rotated vector order keeps the 16-byte shared-memory accesses conflict-free;
+      // streaming mode reads its own 128-byte line through L1 and needs no rotation
+      const int rot = kStream ? 0 : (tid & 7);               // == g & 7 for every group this thread owns
       for (int g = tid; g < ng; g += kMainThreads) {
         int s1 = 0;
         unsigned long long s2 = 0;
         uint32_t b0, b1;
         const int base = g * kGroup;
         if (base + kGroup <= n) {
-          const unsigned char* gp = reinterpret_cast<const unsigned char*>(s_x + base);
+          const unsigned char* gp = reinterpret_cast<const unsigned char*>(x + base);
           uint32_t nlo = 0, nhi = 0;         // "below the mean" bits, MSB-first, in processing order
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const int vi = (j + rot) & 7;    // rotated start: conflict-free 16-byte accesses
-            const int4 q = *reinterpret_cast<const int4*>(gp + 16 * vi);
+            const int vi = (j + rot) & 7;
+            const int4 q = ld16(gp + 16 * vi);
             const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -534,7 +567,7 @@ frontend_pcm_kernel(const PcmArgs a) {
         } else {
           b0 = 0; b1 = 0;
           for (int i = 0; i < kGroup && base + i < n; ++i) {
-            const int d = (int)s_x[base + i] - uc.thr;
+            const int d = (int)x[base + i] - uc.thr;
             s1 += d; s2 += (unsigned long long)((long long)d * d);
             const uint32_t bit = (d >= 0);
             if (i < 32) b0 |= bit << i; else b1 |= bit << (i - 32);
@@ -557,7 +590,7 @@ frontend_pcm_kernel(const PcmArgs a) {
         long long s1 = 0; unsigned long long s2 = 0;
         const int ga = (p + kGroup - 1) / kGroup, gb = q / kGroup;
         auto direct = [&](int i0, int i1) {
-          for (int i = i0; i < i1; ++i) { const int d = (int)s_x[i] - uc.thr; s1 += d; s2 += (unsigned long long)((long long)d * d); }
+          for (int i = i0; i < i1; ++i) { const int d = (int)x[i] - uc.thr; s1 += d; s2 += (unsigned long long)((long long)d * d); }
         };
         if (ga > gb) direct(p, q);
         else {
@@ -774,11 +807,17 @@ frontend_pcm_kernel(const PcmArgs a) {
       const float phi = uc.phi;
       float ce = 0.f, cm = 0.f;                       // first-half partials of the previous block
       const bool hi8 = (sub & 8) != 0;
+      int4 qn = make_int4(0, 0, 0, 0);
+      if (kStream && fa < fb) qn = ld16(x + start + fa * 128 + 8 * sub);
       for (int i = 0; i <= per; ++i) {             // uniform trip count: the shuffles below are warp-wide
         const int b = fa + i;
         const bool live = (fa < fb) && (b <= fb);
-        int4 q = make_int4(0, 0, 0, 0);
-        if (live) q = *reinterpret_cast<const int4*>(s_x + start + b * 128 + 8 * sub);
+        int4 q = qn;
+        if constexpr (kStream) {                   // global loads: fetch the next block one step ahead
+          if ((fa < fb) && (b + 1 <= fb)) qn = ld16(x + start + (b + 1) * 128 + 8 * sub);
+        } else {
+          if (live) q = ld16(x + start + b * 128 + 8 * sub);
+        }
         const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
         float e0 = 0.f, m0 = 0.f, e1 = ce, m1 = cm;
 #pragma unroll
@@ -819,10 +858,10 @@ frontend_pcm_kernel(const PcmArgs a) {
           int jdone = 0;
           if (vec_ok) {
             const int nv = valid >> 3;
-            const int4* xv = reinterpret_cast<const int4*>(s_x + p);
+            const int4* xv = reinterpret_cast<const int4*>(x + p);
             const float4* wv = reinterpret_cast<const float4*>(s_win);
             for (int vq = sub; vq < nv; vq += kLanesPerFrame) {
-              const int4 q = xv[vq];
+              const int4 q = ld16(xv + vq);
               const float4 wa = wv[2 * vq], wb = wv[2 * vq + 1];
               const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
               const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
@@ -838,7 +877,7 @@ frontend_pcm_kernel(const PcmArgs a) {
             jdone = nv << 3;
           }
           for (int j = jdone + sub; j < valid; j += kLanesPerFrame) {
-            const float d = (float)((int)s_x[p + j] - uc.thr) - phi;
+            const float d = (float)((int)x[p + j] - uc.thr) - phi;
             const float av = s_win[j] * d;
             e = fmaf(av, av, e); m += fabsf(av);
           }
@@ -887,35 +926,54 @@ frontend_pcm_kernel(const PcmArgs a) {
       mb[0] = u; mb[1] = f2;
     }
     main_sync();   // samples / sign bits are dead, features + mailbox are complete
-    bar_arrive(kBarFeatFull, kPcmThreads);
+    bar_arrive(kBarFeatFull, kThreads);
 
     const int u_next = s_int[0];
-    if (u_next < a.n_utts) issue_load(u_next);
+    if (!kStream && u_next < a.n_utts) issue_load(u_next);
     u = u_next;
     ++iter;
   }
   // tell the stats warps to stop
-  if (iter > 0) bar_sync(kBarFeatEmpty, kPcmThreads);
+  if (iter > 0) bar_sync(kBarFeatEmpty, kThreads);
   if (tid == 0) s_mail[8 * (iter & 1)] = -1;
   main_sync();
-  bar_arrive(kBarFeatFull, kPcmThreads);
+  bar_arrive(kBarFeatFull, kThreads);
 }
 
-cudaError_t launch_frontend_pcm(const PcmArgs& a, int grid, size_t smem, cudaStream_t st) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(frontend_pcm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = smem;
-  }
-  frontend_pcm_kernel<<<grid, kPcmThreads, smem, st>>>(a);
+namespace {
+using PcmKernel = void (*)(const PcmArgs);
+struct Variant { PcmKernel fn; int threads; bool stream; const char* name; };
+// [0] is the shared-memory-resident kernel (any alignment); the rest are streaming builds
+const Variant kVariants[] = {
+    {frontend_pcm_kernel<false, 256, 2, 2>, 256, false, "resident 256x2"},
+    {frontend_pcm_kernel<true, 128, 1, 4>, 128, true, "stream 128 thr, >=4 CTAs/SM"},
+    {frontend_pcm_kernel<true, 128, 1, 5>, 128, true, "stream 128 thr, >=5 CTAs/SM"},
+    {frontend_pcm_kernel<true, 128, 1, 6>, 128, true, "stream 128 thr, >=6 CTAs/SM"},
+    {frontend_pcm_kernel<true, 256, 2, 2>, 256, true, "stream 256 thr, >=2 CTAs/SM"},
+    {frontend_pcm_kernel<true, 256, 2, 3>, 256, true, "stream 256 thr, >=3 CTAs/SM"},
+    {frontend_pcm_kernel<true, 192, 2, 4>, 192, true, "stream 192 thr, >=4 CTAs/SM"},
+    {frontend_pcm_kernel<true, 160, 1, 4>, 160, true, "stream 160 thr, >=4 CTAs/SM"},
+};
+constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+}  // namespace
+
+int pcm_num_variants() { return kNumVariants; }
+bool pcm_variant_streams(int v) { return kVariants[v].stream; }
+const char* pcm_variant_name(int v) { return kVariants[v].name; }
+
+cudaError_t launch_frontend_pcm(int variant, const PcmArgs& a, int grid, size_t smem, cudaStream_t st) {
+  const Variant& v = kVariants[variant];
+  cudaError_t e = cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  v.fn<<<grid, v.threads, smem, st>>>(a);
   return cudaGetLastError();
 }
 
-int pcm_kernel_max_ctas_per_sm(size_t smem) {
+int pcm_kernel_max_ctas_per_sm(int variant, size_t smem) {
+  const Variant& v = kVariants[variant];
   int n = 0;
-  cudaFuncSetAttribute(frontend_pcm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frontend_pcm_kernel, kPcmThreads, smem) != cudaSuccess) return 0;
+  cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, v.fn, v.threads, smem) != cudaSuccess) return 0;
   return n;
 }
 

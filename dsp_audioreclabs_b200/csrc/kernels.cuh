@@ -53,6 +53,8 @@ struct PcmArgs {
   int cap_samples;              // shared-memory capacity in samples (multiple of 64)
   int cap_frames;               // capacity for per-frame arrays
   int tma_chunk;                // bytes per bulk copy (multiple of 16)
+  int stagger_ns;               // start-up delay per co-resident CTA index (0 = none)
+  int sm_count;
   unsigned int* work_counter;   // dynamic utterance scheduler
   int32_t* flag_list;           // utterances that need the float64 replay
   int32_t* flag_count;
@@ -66,9 +68,12 @@ __global__ void sequence_stats_kernel(const double* s0, const double* s1, const 
                                       double* out);
 
 // frontend_pcm.cu
-size_t pcm_kernel_smem_bytes(int cap_samples, int cap_frames, int fl);
-cudaError_t launch_frontend_pcm(const PcmArgs& a, int grid, size_t smem, cudaStream_t st);
-int pcm_kernel_max_ctas_per_sm(size_t smem);
+size_t pcm_kernel_smem_bytes(int cap_samples, int cap_frames, int fl, bool resident);
+cudaError_t launch_frontend_pcm(int variant, const PcmArgs& a, int grid, size_t smem, cudaStream_t st);
+int pcm_kernel_max_ctas_per_sm(int variant, size_t smem);
+int pcm_num_variants();
+bool pcm_variant_streams(int variant);
+const char* pcm_variant_name(int variant);
 #ifndef DSP_PCM_THREADS
 #define DSP_PCM_THREADS 256
 #endif

@@ -77,6 +77,9 @@ class DeviceFrontend:
         `stream` (default: torch's current stream).  Asynchronous."""
         if not samples.is_cuda or samples.dtype not in _TORCH_DTYPES:
             raise ValueError("samples must be a CUDA tensor of int16 / uint8 / float32 / float64")
+        # utterances that all start on 16-byte boundaries may use the streaming build of the kernel
+        self.params.aligned16 = int(samples.data_ptr() % 16 == 0 and
+                                    bool(np.all(self.h_offsets[:-1] * samples.element_size() % 16 == 0)))
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
         self.ctx.set_stream(st.cuda_stream)
         check(self.ctx.lib.dsp_frontend_batch_device(

@@ -67,6 +67,10 @@ typedef struct {
   double zcr_threshold_ratio;  /* config.ZCR_THRESHOLD_RATIO */
   int32_t channels;            /* 1, or 2 = interleaved stereo averaged per frame (:43-44) */
   int32_t force_exact;         /* 1: run every utterance through the float64 replay kernel */
+  int32_t aligned16;           /* device entry point only: 1 = the caller guarantees that every utterance
+                                * starts on a 16-byte boundary (offsets multiples of 8 samples, 16-byte
+                                * aligned buffer), which lets the streaming build of the fused kernel run;
+                                * 0 = unknown (shared-memory-resident build, any alignment) */
 } dsp_frontend_params;
 
 /* Output pointers of one front-end batch.  Any pointer may be NULL to skip
@@ -101,6 +105,9 @@ int dsp_destroy(dsp_context* ctx);
 int dsp_set_stream(dsp_context* ctx, void* cuda_stream);
 int dsp_use_own_stream(dsp_context* ctx);
 int dsp_sync(dsp_context* ctx);
+/* Tuning knobs (not needed for correctness): "pcm_variant" = -1 automatic, 0 the shared-memory
+ * resident build of the fused kernel, 1.. the streaming builds; "tma_chunk" = bytes per bulk copy. */
+int dsp_set_tuning(dsp_context* ctx, const char* key, int value);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t dsp_launch_count(dsp_context* ctx);
 int dsp_device_sm_count(dsp_context* ctx);
