@@ -256,12 +256,23 @@ int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_
   a.tma_chunk = c->tma_chunk;
   a.stagger_ns = c->stagger_ns;
   a.sm_count = c->sm_count;
+  a.prof = nullptr;
+  static long long* d_prof = nullptr;
+  if (std::getenv("DSP_PROF")) {
+    if (!d_prof) cudaMalloc(&d_prof, 16 * sizeof(long long));
+    cudaMemsetAsync(d_prof, 0, 16 * sizeof(long long), c->stream);
+    a.prof = d_prof;
+  }
   a.work_counter = c->counters.as<unsigned int>();
   a.flag_count = c->counters.as<int32_t>() + 1;
   a.flag_list = c->flag_list.as<int32_t>();
   a.out = *out;
   const int grid = (int)std::min<int64_t>(B, (int64_t)c->sm_count * c->occ);
   CU(launch_frontend_pcm(variant, a, grid, smem, c->stream));
+  if (a.prof) { long long h[16]; cudaMemcpyAsync(h, d_prof, sizeof h, cudaMemcpyDeviceToHost, c->stream); cudaStreamSynchronize(c->stream);
+    const char* nm[12] = {"load_wait", "P1", "feat_empty_wait", "P2", "P2b", "P3tail(searches)", "P4", "fixup+handoff", "P3a(select passes)", "P3b(gather)", "P3c(rank+thresholds)", "P3d(N3N4)"};
+    double tot = 0; for (int i = 0; i < 12; ++i) tot += (double)h[i];
+    fprintf(stderr, "[prof] utterances=%lld", h[15]); for (int i = 0; i < 12; ++i) fprintf(stderr, "  %s=%.0f", nm[i], (double)h[i] / (double)h[15]); fprintf(stderr, "  total=%.0f cycles/utt\n", tot / (double)h[15]); }
   c->launches++;
   // float64 replay of the utterances whose threshold margins could not be certified
   ExactExtras ex;

@@ -113,6 +113,7 @@ __device__ __forceinline__ int count_changes(const uint32_t* bits, int p, int q)
   }
   const int last = q - 2;  // last pair start
   const int w0 = p >> 5, w1 = last >> 5;
+  #pragma unroll 1
   for (int w = w0; w <= w1; ++w) {
     const uint32_t cur = bits[w], nxt = bits[w + 1];
     uint32_t x = cur ^ __funnelshift_r(cur, nxt, 1);
@@ -126,7 +127,7 @@ __device__ __forceinline__ int count_changes(const uint32_t* bits, int p, int q)
 // zero crossings of one windowed frame (compute_zero_crossing_rate on frame*window,
 // audio_processing.py:119-132): zero-padded samples and Hanning's exact-zero end points count
 // as negative.
-__device__ __forceinline__ int frame_zcr(const uint32_t* bits, int p, int valid, int fl, bool hann) {
+__device__ __noinline__ int frame_zcr(const uint32_t* bits, int p, int valid, int fl, bool hann) {
   if (hann && fl <= 2) return 0;
   int zc = count_changes(bits, p, p + valid);
   if (valid < fl) zc += bit_at(bits, p + valid - 1);
@@ -190,37 +191,37 @@ __device__ __forceinline__ int first_shift(uint32_t kmin, uint32_t kmax) {
 // ---------------------------------------------------------------------------------------
 // Statistics of one non-negative float sequence by ONE warp (compute_statistics,
 // feature_extraction.py:46-62): mean, population std, max, min and the median by a radix select
-// whose first pass spreads 256 bins over [min, max] of the float bit patterns.  acc(j) returns
-// element lane + 32*j; NJ > 0 = that many register-resident elements per lane, NJ == 0 = loop.
+// whose first pass spreads 256 bins over [min, max] of the float bit patterns.  vals[j * stride]
+// is element lane + 32*j of the sequence (a per-lane array in local memory, or the sequence itself
+// in shared memory).  Deliberately NOT inlined: it runs on the statistics warps only, once per
+// sequence, and three unrolled copies of it used to blow the instruction cache for the main warps.
 // ---------------------------------------------------------------------------------------
-template <int NJ, class Acc>
-__device__ void warp_sequence_stats(Acc acc, int n, int* hist, float* cand, float* out5) {
+__device__ __noinline__ void warp_sequence_stats(const float* vals, int stride, int n, int* hist, float* cand, float* out5) {
   const int lane = threadIdx.x & 31;
-  const int nj = NJ ? NJ : (n + 31) / 32;
+  const int nj = (n + 31) / 32;
   double sum = 0.0;
   float mx = 0.f, mn = INFINITY;
-#pragma unroll
-  for (int j = 0; j < nj; ++j) if (lane + 32 * j < n) { const float x = acc(j); sum += (double)x; mx = fmaxf(mx, x); mn = fminf(mn, x); }
+#pragma unroll 1
+  for (int j = 0; j < nj; ++j) if (lane + 32 * j < n) { const float x = vals[j * stride]; sum += (double)x; mx = fmaxf(mx, x); mn = fminf(mn, x); }
   sum = warp_reduce(sum, OpAddD());
   mx = warp_reduce(mx, [](float x, float y) { return fmaxf(x, y); });
   mn = warp_reduce(mn, [](float x, float y) { return fminf(x, y); });
   const double mean = sum / (double)n;
   double ss = 0.0;
-#pragma unroll
-  for (int j = 0; j < nj; ++j) if (lane + 32 * j < n) { const double d = (double)acc(j) - mean; ss += d * d; }
+#pragma unroll 1
+  for (int j = 0; j < nj; ++j) if (lane + 32 * j < n) { const double d = (double)vals[j * stride] - mean; ss += d * d; }
   ss = warp_reduce(ss, OpAddD());
 
   uint32_t lo = __float_as_uint(mn);
   int s = first_shift(lo, __float_as_uint(mx));
   int s_used = 32, rank = (n - 1) / 2, cnt = n;
-  if (n > 32) { s_used = s; }
   while (cnt > 32) {
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < 8; ++j) hist[lane * 8 + j] = 0;
     __syncwarp();
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < nj; ++j) if (lane + 32 * j < n) {
-      const uint32_t k = __float_as_uint(acc(j));
+      const uint32_t k = __float_as_uint(vals[j * stride]);
       if (k >= lo) { const uint32_t d = (k - lo) >> s; if (d < 256u) atomicAdd(&hist[d], 1); }
     }
     __syncwarp();
@@ -241,15 +242,16 @@ __device__ void warp_sequence_stats(Acc acc, int n, int* hist, float* cand, floa
   } else {
     if (lane == 0) hist[0] = 0;
     __syncwarp();
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < nj; ++j) if (lane + 32 * j < n) {
-      const float x = acc(j);
+      const float x = vals[j * stride];
       const uint32_t k = __float_as_uint(x);
       if (n <= 32 || (k >= lo && (unsigned long long)(k - lo) < span)) cand[atomicAdd(&hist[0], 1)] = x;
     }
     __syncwarp();
     const float mine = lane < cnt ? cand[lane] : INFINITY;
     int below = 0;
+#pragma unroll 1
     for (int j = 0; j < cnt; ++j) {
       const float o = __shfl_sync(0xffffffffu, mine, j);
       below += (o < mine) || (o == mine && j < lane);
@@ -263,8 +265,8 @@ __device__ void warp_sequence_stats(Acc acc, int n, int* hist, float* cand, floa
   }
   if (!have2 && !(n & 1)) {           // upper middle lies above the candidate bin
     float nxt = INFINITY;
-#pragma unroll
-    for (int j = 0; j < nj; ++j) if (lane + 32 * j < n) { const float x = acc(j); if (x > sel) nxt = fminf(nxt, x); }
+#pragma unroll 1
+    for (int j = 0; j < nj; ++j) if (lane + 32 * j < n) { const float x = vals[j * stride]; if (x > sel) nxt = fminf(nxt, x); }
     nxt = warp_reduce(nxt, [](float x, float y) { return fminf(x, y); });
     sel2 = nxt == INFINITY ? sel : nxt;
   }
@@ -274,6 +276,15 @@ __device__ void warp_sequence_stats(Acc acc, int n, int* hist, float* cand, floa
     out5[2] = mx; out5[3] = mn;
     out5[4] = (n & 1) ? sel : (float)(((double)sel + (double)sel2) * 0.5);
   }
+}
+
+// np.mean of the <= 10 noise frames in NumPy's association (pairwise: < 8 terms sequential, else
+// eight accumulators combined as a tree, then the tail) -- compact, it is cold code.
+__device__ __noinline__ double noise_mean(const double* v, int n) {
+  double r;
+  if (n < 8) { r = 0.0; for (int i = 0; i < n; ++i) r += v[i]; }
+  else { r = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])); for (int i = 8; i < n; ++i) r += v[i]; }
+  return r / (double)n;
 }
 
 }  // namespace
@@ -293,6 +304,10 @@ frontend_pcm_kernel(const PcmArgs a) {
   constexpr int kMainWarps = kWarps - kStatsWarps;
   constexpr int kMainThreads = kMainWarps * 32;
   auto main_sync = [&]() { bar_sync(kBarMain, kMainThreads); };
+  // Serial sections run on the LAST main warp: the warp scheduler favours higher warp ids, and a lone
+  // low-id warp is starved by the other CTA's busy warps (measured: 7.8k cycles for ~300 instructions)
+  constexpr int kLeadWarp = kMainWarps - 1;
+  constexpr int kLeadTid = kLeadWarp * 32;
   extern __shared__ __align__(128) unsigned char smem[];
   const SmemLayout L = make_layout(a.cap_samples, a.cap_frames, a.fl, !kStream);
   int16_t* s_x = reinterpret_cast<int16_t*>(smem + L.samples);
@@ -319,6 +334,7 @@ frontend_pcm_kernel(const PcmArgs a) {
   const int fl = a.fl, fs = a.fs;
   const bool hann = (a.window == DSP_WIN_HANNING);
 
+  #pragma unroll 1
   for (int j = tid; j < fl; j += kThreads) s_win[j] = a.win_f32[j];
   if (tid == 0) {
     mbar_init(s_bar, 1);
@@ -349,35 +365,36 @@ frontend_pcm_kernel(const PcmArgs a) {
       float* stats = a.out.stats ? a.out.stats + (int64_t)u * kStats : nullptr;
       float st[5];
       if (f2 <= 32 * kStatsRegs) {
-        // copy this warp's sequences to registers so the main warps can reuse the buffers at once
+        // copy this warp's sequences to a per-lane array so the main warps can reuse the buffers at once
         float r[3][kStatsRegs];
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
+#pragma unroll 1
+        for (int q = sw; q < 3; q += kStatsWarps) {
           const float* src = q == 0 ? s_fe : (q == 1 ? s_fm : s_fz);
-          const bool mine = (q % kStatsWarps) == sw;
-#pragma unroll
-          for (int j = 0; j < kStatsRegs; ++j) { const int i = lane + 32 * j; r[q][j] = (mine && i < f2) ? src[i] : 0.f; }
+#pragma unroll 1
+          for (int j = 0; j < kStatsRegs; ++j) { const int i = lane + 32 * j; r[q][j] = i < f2 ? src[i] : 0.f; }
         }
         bar_arrive(kBarFeatEmpty, kThreads);
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          if ((q % kStatsWarps) != sw) continue;
+#pragma unroll 1
+        for (int q = sw; q < 3; q += kStatsWarps) {
           float* g = q == 0 ? a.out.energy : (q == 1 ? a.out.magnitude : a.out.zcr);
-#pragma unroll
-          for (int j = 0; j < kStatsRegs; ++j) { const int i = lane + 32 * j; if (g && i < f2) g[fo + i] = r[q][j]; }
+          if (g) {
+#pragma unroll 1
+            for (int j = 0; j < kStatsRegs; ++j) { const int i = lane + 32 * j; if (i < f2) g[fo + i] = r[q][j]; }
+          }
           if (f2 > 0 && stats) {
-            warp_sequence_stats<kStatsRegs>([&](int j) { return r[q][j]; }, f2, hist, cand, st);
+            warp_sequence_stats(r[q], 1, f2, hist, cand, st);
             if (lane == 0) for (int k = 0; k < 5; ++k) stats[5 * q + k] = st[k];
           }
         }
       } else {
         // long sequences: work from shared memory, release the buffers afterwards
+#pragma unroll 1
         for (int q = sw; q < 3; q += kStatsWarps) {
           const float* src = q == 0 ? s_fe : (q == 1 ? s_fm : s_fz);
           float* g = q == 0 ? a.out.energy : (q == 1 ? a.out.magnitude : a.out.zcr);
           for (int i = lane; i < f2; i += 32) if (g) g[fo + i] = src[i];
           if (stats) {
-            warp_sequence_stats<0>([&](int j) { return src[lane + 32 * j]; }, f2, hist, cand, st);
+            warp_sequence_stats(src + lane, 32, f2, hist, cand, st);
             if (lane == 0) for (int k = 0; k < 5; ++k) stats[5 * q + k] = st[k];
           }
         }
@@ -393,6 +410,9 @@ frontend_pcm_kernel(const PcmArgs a) {
   // =========================================================================================
   uint32_t parity = 0;
   (void)parity;
+  __shared__ long long s_prof[16];
+  long long t_prev = clock64();
+  if (tid < 16) s_prof[tid] = 0;
   int u = s_int[0];
   int iter = 0;
 
@@ -432,9 +452,11 @@ frontend_pcm_kernel(const PcmArgs a) {
     } else if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) {
       const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
       uint32_t* d32 = reinterpret_cast<uint32_t*>(s_x);
+      #pragma unroll 1
       for (int i = tid; i < (n >> 1); i += kMainThreads) d32[i] = __ldg(s32 + i);
       if ((n & 1) && tid == 0) s_x[n - 1] = src[n - 1];
     } else {
+      #pragma unroll 1
       for (int i = tid; i < n; i += kMainThreads) s_x[i] = src[i];
     }
   };
@@ -460,7 +482,7 @@ frontend_pcm_kernel(const PcmArgs a) {
     if constexpr (kStream) {
       if (reinterpret_cast<uintptr_t>(x) & 15) {
         // misaligned start: not this kernel's layout -- hand the utterance to the float64 replay
-        if (tid == 0) {
+        if (tid == kLeadTid) {
           const int slot = atomicAdd(a.flag_count, 1); a.flag_list[slot] = u;
           s_int[0] = (int)atomicAdd(a.work_counter, 1u);
         }
@@ -475,6 +497,7 @@ frontend_pcm_kernel(const PcmArgs a) {
     }
     if (tid == 0) s_int[0] = (int)atomicAdd(a.work_counter, 1u);   // next utterance, consumed after P4
 
+    if (a.prof && tid == 0) { const long long t_ = clock64(); s_prof[0] += t_ - t_prev; t_prev = t_; }
     // =========================== P1: sum, min, max ===================================
     {
       int sum = 0;
@@ -490,13 +513,15 @@ frontend_pcm_kernel(const PcmArgs a) {
         mn2 = __vmins2(mn2, q.w); mx2 = __vmaxs2(mx2, q.w);
       };
       int v = tid;
-      if constexpr (kStream)
-      for (; v + 3 * kMainThreads < nvec; v += 4 * kMainThreads) {       // 4 loads in flight per thread
-        const int4 q0 = ld16(xv + v), q1 = ld16(xv + v + kMainThreads);
-        const int4 q2 = ld16(xv + v + 2 * kMainThreads), q3 = ld16(xv + v + 3 * kMainThreads);
-        acc1(q0); acc1(q1); acc1(q2); acc1(q3);
+      if constexpr (kStream) {
+        for (; v + 3 * kMainThreads < nvec; v += 4 * kMainThreads) {     // 4 loads in flight per thread
+          const int4 q0 = ld16(xv + v), q1 = ld16(xv + v + kMainThreads);
+          const int4 q2 = ld16(xv + v + 2 * kMainThreads), q3 = ld16(xv + v + 3 * kMainThreads);
+          acc1(q0); acc1(q1); acc1(q2); acc1(q3);
+        }
       }
-      for (; v < nvec; v += kMainThreads) acc1(ld16(xv + v));
+#pragma unroll 1
+      for (; v < nvec; v += kMainThreads) { const int4 q = ld16(xv + v); acc1(q); }
       int mn = min(sext16(mn2), (int)mn2 >> 16), mx = max(sext16(mx2), (int)mx2 >> 16);
       if (tid < (n & 7)) { const int k = x[(nvec << 3) + tid]; sum += k; mn = min(mn, k); mx = max(mx, k); }
       // per-warp partials (a warp sees < 2^31 / 2^15 samples: the utterance fits shared memory)
@@ -506,8 +531,9 @@ frontend_pcm_kernel(const PcmArgs a) {
       int* part = reinterpret_cast<int*>(s_sh);
       if (lane == 0) { part[wid] = sum; part[kWarps + wid] = mn; part[2 * kWarps + wid] = mx; }
       main_sync();
-      if (tid == 0) {
+      if (tid == kLeadTid) {
         long long S = 0; int gmn = 32767, gmx = -32768;
+        #pragma unroll 1
         for (int w = 0; w < kMainWarps; ++w) { S += part[w]; gmn = min(gmn, part[kWarps + w]); gmx = max(gmx, part[2 * kWarps + w]); }
         const long long N = n > 0 ? n : 1;
         long long q = S / N; if ((S % N) != 0 && (S < 0)) --q;      // floor(S/N)
@@ -528,9 +554,11 @@ frontend_pcm_kernel(const PcmArgs a) {
     uc.thr = s_int[1]; uc.phi_d = s_dbl[0]; uc.phi = (float)uc.phi_d;
     uc.inv_m = s_dbl[1]; uc.mu = s_dbl[2];
 
+    if (a.prof && tid == 0) { const long long t_ = clock64(); s_prof[1] += t_ - t_prev; t_prev = t_; }
     // the group-sum region doubles as the feature buffers the stats warps may still be reading
     if (iter > 0) bar_sync(kBarFeatEmpty, kThreads);
 
+    if (a.prof && tid == 0) { const long long t_ = clock64(); s_prof[2] += t_ - t_prev; t_prev = t_; }
     // =========================== P2: group sums + sign bits ==========================
     const int ng = (n + kGroup - 1) / kGroup;
     {
@@ -545,20 +573,27 @@ frontend_pcm_kernel(const PcmArgs a) {
         if (base + kGroup <= n) {
           const unsigned char* gp = reinterpret_cast<const unsigned char*>(x + base);
           uint32_t nlo = 0, nhi = 0;         // "below the mean" bits, MSB-first, in processing order
+          int s1b = 0;
+          unsigned long long s2b = 0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int vi = (j + rot) & 7;
-            const int4 q = ld16(gp + 16 * vi);
-            const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+          for (int j = 0; j < 4; ++j) {
+            // vectors j and j+4 of the (rotated) order feed two independent dependency chains
+            const int4 qa = ld16(gp + 16 * ((j + rot) & 7));
+            const int4 qb = ld16(gp + 16 * ((j + 4 + rot) & 7));
+            const uint32_t wa[4] = {(uint32_t)qa.x, (uint32_t)qa.y, (uint32_t)qa.z, (uint32_t)qa.w};
+            const uint32_t wb[4] = {(uint32_t)qb.x, (uint32_t)qb.y, (uint32_t)qb.z, (uint32_t)qb.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const int lo = sext16(w[k]) - uc.thr, hi = ((int)w[k] >> 16) - uc.thr;
-              s1 += lo + hi;
-              s2 += (unsigned long long)((long long)lo * lo) + (unsigned long long)((long long)hi * hi);
-              if (j < 4) { nhi = __funnelshift_l((uint32_t)lo, nhi, 1); nhi = __funnelshift_l((uint32_t)hi, nhi, 1); }
-              else       { nlo = __funnelshift_l((uint32_t)lo, nlo, 1); nlo = __funnelshift_l((uint32_t)hi, nlo, 1); }
+              const int alo = sext16(wa[k]) - uc.thr, ahi = ((int)wa[k] >> 16) - uc.thr;
+              const int blo = sext16(wb[k]) - uc.thr, bhi = ((int)wb[k] >> 16) - uc.thr;
+              s1 += alo + ahi; s1b += blo + bhi;
+              s2 += (unsigned long long)((long long)alo * alo) + (unsigned long long)((long long)ahi * ahi);
+              s2b += (unsigned long long)((long long)blo * blo) + (unsigned long long)((long long)bhi * bhi);
+              nhi = __funnelshift_l((uint32_t)alo, nhi, 1); nhi = __funnelshift_l((uint32_t)ahi, nhi, 1);
+              nlo = __funnelshift_l((uint32_t)blo, nlo, 1); nlo = __funnelshift_l((uint32_t)bhi, nlo, 1);
             }
           }
+          s1 += s1b; s2 += s2b;
           // stream (nhi:nlo) holds vector rot first (at the top); reverse to LSB-first, undo the rotation
           const unsigned long long y = ((unsigned long long)__brev(nlo) << 32) | (unsigned long long)__brev(nhi);
           const int sh = 8 * rot;
@@ -566,6 +601,7 @@ frontend_pcm_kernel(const PcmArgs a) {
           b0 = ~(uint32_t)z; b1 = ~(uint32_t)(z >> 32);
         } else {
           b0 = 0; b1 = 0;
+          #pragma unroll 1
           for (int i = 0; i < kGroup && base + i < n; ++i) {
             const int d = (int)x[base + i] - uc.thr;
             s1 += d; s2 += (unsigned long long)((long long)d * d);
@@ -580,6 +616,7 @@ frontend_pcm_kernel(const PcmArgs a) {
     if (tid < 4) s_bits[2 * ng + tid] = 0;
     main_sync();
 
+    if (a.prof && tid == 0) { const long long t_ = clock64(); s_prof[3] += t_ - t_prev; t_prev = t_; }
     // =========================== P2b: EPD frame energies / crossings =================
     int f1 = 0;
     if (a.do_epd && n >= fl) f1 = (n - fl) / fs + 1;
@@ -590,6 +627,7 @@ frontend_pcm_kernel(const PcmArgs a) {
         long long s1 = 0; unsigned long long s2 = 0;
         const int ga = (p + kGroup - 1) / kGroup, gb = q / kGroup;
         auto direct = [&](int i0, int i1) {
+          #pragma unroll 1
           for (int i = i0; i < i1; ++i) { const int d = (int)x[i] - uc.thr; s1 += d; s2 += (unsigned long long)((long long)d * d); }
         };
         if (ga > gb) direct(p, q);
@@ -612,9 +650,12 @@ frontend_pcm_kernel(const PcmArgs a) {
       amx = warp_reduce(amx, OpMaxD());
       double* part = reinterpret_cast<double*>(s_sh);
       if (lane == 0) { part[wid] = emx; part[kWarps + wid] = amx; part[2 * kWarps + wid] = emn; }
+      for (int i = tid; i < 256; i += kMainThreads) s_hist[i] = 0;     // first pass of the p90 select
+      if (tid == 0) s_int[12 + 5] = 0;                                  // candidate counter
     }
     main_sync();
 
+    if (a.prof && tid == 0) { const long long t_ = clock64(); s_prof[4] += t_ - t_prev; t_prev = t_; }
     // =========================== P3: endpoint decision ===============================
     int start = 0, end = n;
     if (f1 > 0) {
@@ -625,48 +666,79 @@ frontend_pcm_kernel(const PcmArgs a) {
       int* hist = s_hist;
       int* sel_state = s_int + 12;        // [0] lo  [1] shift  [2] rank  [3] cnt  [4] shift used  [5] cand count
       int* cand_idx = reinterpret_cast<int*>(s_cand);
-      if (tid == 0) {
+      {
+        // every thread derives the select state from the per-warp partials: no broadcast barrier
         const double* part = reinterpret_cast<const double*>(s_sh);
         double emx = 0.0, emn = INFINITY;
+        #pragma unroll 1
         for (int w = 0; w < kMainWarps; ++w) { emx = fmax(emx, part[w]); emn = fmin(emn, part[2 * kWarps + w]); }
         const uint32_t kmin = __float_as_uint((float)emn), kmax = __float_as_uint((float)emx);
-        sel_state[0] = (int)kmin;
-        sel_state[1] = first_shift(kmin, kmax);
-        sel_state[2] = top ? f1 - 1 : (int)floor(v);
-        sel_state[3] = f1;
-        sel_state[4] = 32;
-        sel_state[5] = 0;
-      }
-      main_sync();
-      while (sel_state[3] > 32) {
-        const uint32_t lo = (uint32_t)sel_state[0];
-        const int s = sel_state[1];
-        for (int i = tid; i < 256; i += kMainThreads) hist[i] = 0;
-        main_sync();
-        for (int f = tid; f < f1; f += kMainThreads) {
-          const uint32_t k = __float_as_uint((float)s_e[f]);
-          if (k >= lo) { const uint32_t d = (k - lo) >> s; if (d < 256u) atomicAdd(&hist[d], 1); }
+        if (tid == kLeadTid) {
+          sel_state[0] = (int)kmin;
+          sel_state[1] = first_shift(kmin, kmax);
+          sel_state[2] = top ? f1 - 1 : (int)floor(v);
+          sel_state[3] = f1;
+          sel_state[4] = 32;
         }
-        main_sync();
-        if (wid == 0) {
-          int digit, rank, cnt;
-          scan_bins(hist, lane, sel_state[2], &digit, &rank, &cnt);
-          __syncwarp();
-          if (lane == 0) {
-            sel_state[0] = (int)(lo + ((uint32_t)digit << s));
-            sel_state[4] = s;
-            sel_state[2] = rank;
-            sel_state[3] = (s == 0 && cnt > 32) ? -cnt : cnt;     // negative: cannot be split further
-            sel_state[1] = s > 8 ? s - 8 : 0;
+        // noise floors (first/last min(5, F1/10) frames, :188-195, :241-247) by another warp meanwhile
+        if (wid == (kMainWarps > 1 ? kLeadWarp - 1 : 0) && lane == 0) {
+          const int nf = min(5, f1 / 10);
+          double noise_e, noise_z;
+          if (nf > 0) {
+            double ve[10], vz[10];
+            for (int i = 0; i < 2 * nf; ++i) {
+              const int f = i < nf ? i : f1 - 2 * nf + i;
+              ve[i] = s_e[f]; vz[i] = (double)s_z[f];
+            }
+            noise_e = noise_mean(ve, 2 * nf);
+            noise_z = noise_mean(vz, 2 * nf);
+          } else {
+            noise_e = s_e[0]; noise_z = (double)s_z[0];
+            #pragma unroll 1
+            for (int i = 1; i < f1; ++i) { noise_e = fmin(noise_e, s_e[i]); noise_z = fmin(noise_z, (double)s_z[i]); }
           }
+          s_dbl[8] = noise_e; s_dbl[9] = noise_z;
         }
-        main_sync();
+        // first pass inline (histogram zeroed before the P2b barrier, state known to every thread)
+        int pass_s = first_shift(kmin, kmax);
+        uint32_t pass_lo = kmin;
+        bool first = true;
+        while (first ? f1 > 32 : sel_state[3] > 32) {
+          if (!first) {
+            pass_lo = (uint32_t)sel_state[0]; pass_s = sel_state[1];
+            for (int i = tid; i < 256; i += kMainThreads) hist[i] = 0;
+            main_sync();
+          }
+          #pragma unroll 1
+          for (int f = tid; f < f1; f += kMainThreads) {
+            const uint32_t k = __float_as_uint((float)s_e[f]);
+            if (k >= pass_lo) { const uint32_t d = (k - pass_lo) >> pass_s; if (d < 256u) atomicAdd(&hist[d], 1); }
+          }
+          main_sync();
+          if (wid == kLeadWarp) {
+            int digit, rank, cnt;
+            scan_bins(hist, lane, first ? (top ? f1 - 1 : (int)floor(v)) : sel_state[2], &digit, &rank, &cnt);
+            __syncwarp();
+            if (lane == 0) {
+              sel_state[0] = (int)(pass_lo + ((uint32_t)digit << pass_s));
+              sel_state[4] = pass_s;
+              sel_state[2] = rank;
+              sel_state[3] = (pass_s == 0 && cnt > 32) ? -cnt : cnt;     // negative: cannot be split further
+              sel_state[1] = pass_s > 8 ? pass_s - 8 : 0;
+            }
+          }
+          main_sync();
+          first = false;
+        }
+        if (f1 <= 32) main_sync();      // publish sel_state / noise floors written above
       }
+      if (a.prof && tid == 0) { const long long t_ = clock64(); s_prof[8] += t_ - t_prev; t_prev = t_; }
       {
         // gather the candidate frames of the final bin
         const uint32_t lo = (uint32_t)sel_state[0];
         const unsigned long long span = 1ull << sel_state[4];
         const bool all = f1 <= 32;
+        #pragma unroll 1
         for (int f = tid; f < f1; f += kMainThreads) {
           const uint32_t k = __float_as_uint((float)s_e[f]);
           if (all || (k >= lo && (unsigned long long)(k - lo) < span)) {
@@ -676,14 +748,15 @@ frontend_pcm_kernel(const PcmArgs a) {
         }
       }
       main_sync();
-      if (wid == 0) {
-        const int nf = min(5, f1 / 10);
+      if (a.prof && tid == 0) { const long long t_ = clock64(); s_prof[9] += t_ - t_prev; t_prev = t_; }
+      if (wid == kLeadWarp) {
         int cnt = sel_state[3];
         const int rank = sel_state[2];
         bool unresolved = false;
         if (cnt < 0) { cnt = 32; unresolved = true; }     // > 32 frames share one float: replay in float64
         const double mine = lane < cnt ? s_e[cand_idx[lane]] : INFINITY;
         int below = 0;
+        #pragma unroll 1
         for (int j = 0; j < cnt; ++j) {
           const double o = __shfl_sync(0xffffffffu, mine, j);
           below += (o < mine) || (o == mine && j < lane);
@@ -697,6 +770,7 @@ frontend_pcm_kernel(const PcmArgs a) {
           const uint32_t lo = (uint32_t)sel_state[0];
           const unsigned long long span = 1ull << sel_state[4];
           double nxt = INFINITY;
+          #pragma unroll 1
           for (int f = lane; f < f1; f += 32) {
             const double e = s_e[f];
             const uint32_t k = __float_as_uint((float)e);
@@ -709,18 +783,10 @@ frontend_pcm_kernel(const PcmArgs a) {
         if (lane == 0) {
           const double* part = reinterpret_cast<const double*>(s_sh);
           double emx = 0.0, amx = 0.0;
+          #pragma unroll 1
           for (int w = 0; w < kMainWarps; ++w) { emx = fmax(emx, part[w]); amx = fmax(amx, part[kWarps + w]); }
           const double speech = np_lerp(ka, kb, v - floor(v));
-          double noise_e, noise_z;
-          if (nf > 0) {
-            auto te = [&](int64_t i) { return i < nf ? s_e[i] : s_e[f1 - 2 * nf + i]; };
-            auto tz = [&](int64_t i) { return (double)(i < nf ? s_z[i] : s_z[f1 - 2 * nf + i]); };
-            noise_e = np_pairwise_leaf(te, 0, 2 * nf) / (double)(2 * nf);
-            noise_z = np_pairwise_leaf(tz, 0, 2 * nf) / (double)(2 * nf);
-          } else {
-            noise_e = s_e[0]; noise_z = (double)s_z[0];
-            for (int i = 1; i < f1; ++i) { noise_e = fmin(noise_e, s_e[i]); noise_z = fmin(noise_z, (double)s_z[i]); }
-          }
+          const double noise_e = s_dbl[8], noise_z = s_dbl[9];
           const double t1 = speech * a.hr;
           const double t2 = noise_e + (speech - noise_e) * a.lr;
           const double t3 = noise_z * a.zr;
@@ -729,7 +795,9 @@ frontend_pcm_kernel(const PcmArgs a) {
           // three-term energy formula at its largest magnitude, and the reference's mean-rounding
           // term |mu| * sqrt(fl * E) / m at E_max, each with a >= 4x margin.
           const double eps = 1.0 / 1099511627776.0;  // 2^-40
-          const double smax = ldexp(fabs(uc.mu) * sqrt((double)fl * emx) * uc.inv_m + amx * uc.inv_m * uc.inv_m, -50);
+          // sqrt(y) <= (y + 1) / 2: an upper bound is all a slack needs
+          const double smax = 8.881784197001252e-16 /* 2^-50 */ *
+                              (fabs(uc.mu) * 0.5 * ((double)fl * emx + 1.0) * uc.inv_m + amx * uc.inv_m * uc.inv_m);
           const double tol1 = eps * fabs(t1) + fabs(a.hr) * smax;
           const double tol2 = eps * (fabs(noise_e) + fabs(a.lr) * (fabs(speech) + fabs(noise_e))) +
                               (fabs(1.0 - a.lr) + fabs(a.lr)) * smax;
@@ -740,6 +808,7 @@ frontend_pcm_kernel(const PcmArgs a) {
         }
       }
       main_sync();
+      if (a.prof && tid == 0) { const long long t_ = clock64(); s_prof[10] += t_ - t_prev; t_prev = t_; }
       const double t1 = s_dbl[3], t2 = s_dbl[4], t3 = s_dbl[5];
       const double tol1 = s_dbl[6], tol2 = s_dbl[7];
       {
@@ -759,6 +828,7 @@ frontend_pcm_kernel(const PcmArgs a) {
         }
       }
       main_sync();
+      if (a.prof && tid == 0) { const long long t_ = clock64(); s_prof[11] += t_ - t_prev; t_prev = t_; }
       const int n3 = s_int[4], n4 = s_int[5];
       if (n4 >= 0) {
         {
@@ -784,12 +854,14 @@ frontend_pcm_kernel(const PcmArgs a) {
       // EPD lists out (the group-sum region is dead from here on; E/Z stay valid)
       if (a.out.epd_energy || a.out.epd_zcr) {
         const int64_t eo = a.epd_offsets[u];
+        #pragma unroll 1
         for (int f = tid; f < f1; f += kMainThreads) {
           if (a.out.epd_energy) a.out.epd_energy[eo + f] = s_e[f];
           if (a.out.epd_zcr) a.out.epd_zcr[eo + f] = (float)s_z[f];
         }
       }
     }
+    if (a.prof && tid == 0) { const long long t_ = clock64(); s_prof[5] += t_ - t_prev; t_prev = t_; }
     const int flagged = s_int[3];
 
     // =========================== P4: windowed frame features =========================
@@ -876,6 +948,7 @@ frontend_pcm_kernel(const PcmArgs a) {
             }
             jdone = nv << 3;
           }
+          #pragma unroll 1
           for (int j = jdone + sub; j < valid; j += kLanesPerFrame) {
             const float d = (float)((int)x[p + j] - uc.thr) - phi;
             const float av = s_win[j] * d;
@@ -891,9 +964,11 @@ frontend_pcm_kernel(const PcmArgs a) {
       }
     }
     main_sync();
+    if (a.prof && tid == 0) { const long long t_ = clock64(); s_prof[6] += t_ - t_prev; t_prev = t_; }
     // peak normalisation (1/m^2, 1/m) and zero crossings, one frame per thread.  A full frame of
     // the trimmed segment IS an endpoint-detection frame (start is a multiple of the hop), so its
     // crossing count is already in s_z; only Hanning's zeroed end points need patching.
+    #pragma unroll 1
     for (int t = tid; t < f2; t += kMainThreads) {
       const int p = start + t * fs;
       const int valid = min(fl, end - p);
@@ -928,11 +1003,13 @@ frontend_pcm_kernel(const PcmArgs a) {
     main_sync();   // samples / sign bits are dead, features + mailbox are complete
     bar_arrive(kBarFeatFull, kThreads);
 
+    if (a.prof && tid == 0) { const long long t_ = clock64(); s_prof[7] += t_ - t_prev; t_prev = t_; }
     const int u_next = s_int[0];
     if (!kStream && u_next < a.n_utts) issue_load(u_next);
     u = u_next;
     ++iter;
   }
+  if (a.prof && tid == 0) { for (int i = 0; i < 12; ++i) atomicAdd((unsigned long long*)&a.prof[i], (unsigned long long)s_prof[i]); atomicAdd((unsigned long long*)&a.prof[15], (unsigned long long)iter); }
   // tell the stats warps to stop
   if (iter > 0) bar_sync(kBarFeatEmpty, kThreads);
   if (tid == 0) s_mail[8 * (iter & 1)] = -1;

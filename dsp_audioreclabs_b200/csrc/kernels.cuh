@@ -55,6 +55,7 @@ struct PcmArgs {
   int tma_chunk;                // bytes per bulk copy (multiple of 16)
   int stagger_ns;               // start-up delay per co-resident CTA index (0 = none)
   int sm_count;
+  long long* prof;              // debug: per-phase cycle counters (NULL normally)
   unsigned int* work_counter;   // dynamic utterance scheduler
   int32_t* flag_list;           // utterances that need the float64 replay
   int32_t* flag_count;
