@@ -54,11 +54,11 @@ SIGNATURES = {
     "dsp_sync": (C.c_int, [_P]),
     "dsp_launch_count": (_I64, [_P]),
     "dsp_device_sm_count": (C.c_int, [_P]),
-    "dsp_frontend_plan": (C.c_int, [_P, _I64, C.POINTER(FrontendParams), _P, _P, C.POINTER(_I64)]),
+    "dsp_frontend_plan": (C.c_int, [_P, _P, _I64, C.POINTER(FrontendParams), _P, _P, C.POINTER(_I64)]),
     "dsp_window": (C.c_int, [C.c_int, _I32, _P]),
-    "dsp_frontend_batch_device": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _I64, _I64,
+    "dsp_frontend_batch_device": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, _P, _I64, _I64,
                                             C.POINTER(FrontendParams), C.POINTER(FrontendOutputs)]),
-    "dsp_frontend_batch_host": (C.c_int, [_P, _P, C.c_int, _P, _I64, C.POINTER(FrontendParams),
+    "dsp_frontend_batch_host": (C.c_int, [_P, _P, C.c_int, _P, _P, _I64, C.POINTER(FrontendParams),
                                           C.POINTER(FrontendOutputs)]),
     "dsp_preprocess_host": (C.c_int, [_P, _P, _I64, C.c_int, _P]),
     "dsp_endpoint_detection_host": (C.c_int, [_P, _P, _I64, C.POINTER(FrontendParams), C.POINTER(_I32),

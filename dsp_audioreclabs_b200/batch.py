@@ -96,15 +96,17 @@ def make_params(frame_length, frame_shift, window_type="hamming", do_endpoint_de
                           int(bool(force_exact)), 0)
 
 
-def plan(offsets, params):
+def plan(offsets, params, lengths=None):
     """(feat_offsets, epd_offsets, max_len) -- host arithmetic only (dsp_frontend_plan)."""
     lib = load_library()
     offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    if lengths is not None:
+        lengths = np.ascontiguousarray(lengths, dtype=np.int32)
     b = len(offsets) - 1
     fo = np.zeros(b + 1, dtype=np.int64)
     eo = np.zeros(b + 1, dtype=np.int64)
     mx = C.c_int64(0)
-    check(lib.dsp_frontend_plan(_ptr(offsets), b, C.byref(params), _ptr(fo), _ptr(eo), C.byref(mx)))
+    check(lib.dsp_frontend_plan(_ptr(offsets), _ptr(lengths), b, C.byref(params), _ptr(fo), _ptr(eo), C.byref(mx)))
     return fo, eo, int(mx.value)
 
 
@@ -131,10 +133,25 @@ class FrontendResult:
         return self.epd_energy[o:o + n], self.epd_zcr[o:o + n]
 
 
+def pack_aligned(utterances, align=8):
+    """Concatenate PCM utterances with every start rounded up to a multiple of `align` samples
+    (16 bytes for int16): returns (samples, offsets[B+1], lengths[B]) for frontend_batch(...,
+    lengths=...), the layout on which the aligned TMA / streaming loads apply to ragged data."""
+    lengths = np.array([len(u) for u in utterances], dtype=np.int32)
+    room = (lengths.astype(np.int64) + align - 1) // align * align
+    offsets = np.zeros(len(utterances) + 1, dtype=np.int64)
+    np.cumsum(room, out=offsets[1:])
+    dtype = utterances[0].dtype if len(utterances) else np.int16
+    samples = np.zeros(int(offsets[-1]), dtype=dtype)
+    for u, o in zip(utterances, offsets[:-1]):
+        samples[o:o + len(u)] = u
+    return samples, offsets, lengths
+
+
 def frontend_batch(samples, offsets, frame_length, frame_shift, window_type="hamming",
                    do_endpoint_detection=True, energy_high_ratio=0.5, energy_low_ratio=0.1,
                    zcr_threshold_ratio=1.5, channels=1, emit_epd_lists=False, force_exact=False,
-                   emit_frames=True, ctx=None):
+                   emit_frames=True, lengths=None, ctx=None):
     """preprocess -> endpoint_detection -> frame_signal -> extract_frame_features -> 15 statistics
     for every utterance of a packed batch (src/audio_processing.py:364-394 and
     src/feature_extraction.py:91-112, batched).  `samples` is int16 / uint8 PCM or float32/64.
@@ -148,7 +165,9 @@ def frontend_batch(samples, offsets, frame_length, frame_shift, window_type="ham
     b = len(offsets) - 1
     p = make_params(frame_length, frame_shift, window_type, do_endpoint_detection, energy_high_ratio,
                     energy_low_ratio, zcr_threshold_ratio, channels, force_exact)
-    fo, eo, max_len = plan(offsets, p)
+    if lengths is not None:
+        lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+    fo, eo, max_len = plan(offsets, p, lengths)
     if b and (offsets[0] < 0 or offsets[-1] > samples.size):
         raise ValueError("offsets exceed the sample buffer")
     res = FrontendResult(
@@ -164,7 +183,7 @@ def frontend_batch(samples, offsets, frame_length, frame_shift, window_type="ham
                           _ptr(res.status), _ptr(res.energy), _ptr(res.magnitude), _ptr(res.zcr),
                           _ptr(res.stats), _ptr(res.epd_energy), _ptr(res.epd_zcr))
     check(ctx.lib.dsp_frontend_batch_host(ctx.handle, _ptr(samples), _DTYPES[samples.dtype],
-                                          _ptr(offsets), b, C.byref(p), C.byref(out)))
+                                          _ptr(offsets), _ptr(lengths), b, C.byref(p), C.byref(out)))
     return res
 
 

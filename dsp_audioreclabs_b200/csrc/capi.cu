@@ -169,7 +169,7 @@ struct ExactExtras {
   double* stats_f64 = nullptr;
 };
 
-int launch_exact(dsp_context* c, const void* samples, int dtype, const int64_t* offsets,
+int launch_exact(dsp_context* c, const void* samples, int dtype, const int64_t* offsets, const int32_t* lengths,
                  const int64_t* feat_offsets, const int64_t* epd_offsets, const int32_t* list,
                  const int32_t* list_count, int64_t n_items, int64_t max_len, const dsp_frontend_params* p,
                  const dsp_frontend_outputs* out, const ExactExtras& ex, int grid) {
@@ -179,7 +179,7 @@ int launch_exact(dsp_context* c, const void* samples, int dtype, const int64_t* 
   CU(c->seqbuf.ensure(sizeof(double) * (size_t)grid * 5 * (size_t)cap_frames));
   ExactArgs a{};
   a.samples = samples; a.dtype = dtype; a.channels = p->channels;
-  a.offsets = offsets; a.feat_offsets = feat_offsets; a.epd_offsets = epd_offsets;
+  a.offsets = offsets; a.lengths = lengths; a.feat_offsets = feat_offsets; a.epd_offsets = epd_offsets;
   a.list = list; a.list_count = list_count; a.n_items = n_items;
   a.fl = p->frame_length; a.fs = p->frame_shift;
   a.do_epd = p->do_endpoint_detection; a.pre_mode = ex.pre_mode; a.do_features = ex.do_features;
@@ -197,7 +197,7 @@ int launch_exact(dsp_context* c, const void* samples, int dtype, const int64_t* 
   return DSP_OK;
 }
 
-int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_t* offsets,
+int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_t* offsets, const int32_t* lengths,
                     const int64_t* feat_offsets, const int64_t* epd_offsets, int64_t B, int64_t max_len,
                     const dsp_frontend_params* p, const dsp_frontend_outputs* out) {
   int rc = check_params(p);
@@ -234,7 +234,7 @@ int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_
   if (!fast) {
     const int grid = (int)std::min<int64_t>(B, (int64_t)c->sm_count * 4);
     ExactExtras ex;
-    return launch_exact(c, samples, dtype, offsets, feat_offsets, epd_offsets, nullptr, nullptr, B, max_len,
+    return launch_exact(c, samples, dtype, offsets, lengths, feat_offsets, epd_offsets, nullptr, nullptr, B, max_len,
                         p, out, ex, grid);
   }
   if (c->occ_smem != smem || c->occ_variant != variant) {
@@ -248,7 +248,7 @@ int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_
   CU(cudaMemsetAsync(c->counters.p, 0, 64, c->stream));
   PcmArgs a{};
   a.samples = reinterpret_cast<const int16_t*>(samples);
-  a.offsets = offsets; a.feat_offsets = feat_offsets; a.epd_offsets = epd_offsets;
+  a.offsets = offsets; a.lengths = lengths; a.feat_offsets = feat_offsets; a.epd_offsets = epd_offsets;
   a.n_utts = B; a.fl = fl; a.fs = fs; a.window = p->window; a.do_epd = p->do_endpoint_detection;
   a.hr = p->energy_high_ratio; a.lr = p->energy_low_ratio; a.zr = p->zcr_threshold_ratio;
   a.win_f32 = c->win32.as<float>();
@@ -277,7 +277,7 @@ int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_
   // float64 replay of the utterances whose threshold margins could not be certified
   ExactExtras ex;
   const int xgrid = (int)std::min<int64_t>(B, (int64_t)c->sm_count);
-  return launch_exact(c, samples, dtype, offsets, feat_offsets, epd_offsets, a.flag_list, a.flag_count, 0,
+  return launch_exact(c, samples, dtype, offsets, lengths, feat_offsets, epd_offsets, a.flag_list, a.flag_count, 0,
                       max_len, p, out, ex, xgrid);
 }
 
@@ -397,15 +397,17 @@ int64_t dsp_frame_count(int64_t n, int32_t fl, int32_t fs) {
   return frame_count_host_device(n, fl, fs);
 }
 
-int dsp_frontend_plan(const int64_t* offsets, int64_t B, const dsp_frontend_params* p, int64_t* feat_offsets,
-                      int64_t* epd_offsets, int64_t* max_len) {
+int dsp_frontend_plan(const int64_t* offsets, const int32_t* lengths, int64_t B, const dsp_frontend_params* p,
+                      int64_t* feat_offsets, int64_t* epd_offsets, int64_t* max_len) {
   int rc = check_params(p);
   if (rc) return rc;
   if (!offsets || B < 0) return fail(DSP_ERR_INVALID, "bad offsets");
   int64_t fo = 0, eo = 0, mx = 0;
   for (int64_t b = 0; b < B; ++b) {
-    const int64_t len = offsets[b + 1] - offsets[b];
-    if (len < 0 || len % p->channels) return fail(DSP_ERR_INVALID, "offsets must be non-decreasing and a multiple of channels (utterance %lld)", (long long)b);
+    const int64_t room = offsets[b + 1] - offsets[b];
+    const int64_t len = lengths ? (int64_t)lengths[b] : room;
+    if (room < 0 || len < 0 || len > room || len % p->channels)
+      return fail(DSP_ERR_INVALID, "offsets must be non-decreasing, lengths must fit and be a multiple of channels (utterance %lld)", (long long)b);
     const int64_t n = len / p->channels;
     if (n > INT32_MAX / 4) return fail(DSP_ERR_UNSUPPORTED, "utterance %lld is too long", (long long)b);
     if (feat_offsets) feat_offsets[b] = fo;
@@ -430,15 +432,15 @@ int dsp_window(int window_type, int32_t length, double* out) {
 }
 
 int dsp_frontend_batch_device(dsp_context* c, const void* samples, int dtype, const int64_t* offsets,
-                              const int64_t* feat_offsets, const int64_t* epd_offsets, int64_t n_utts,
+                              const int32_t* lengths, const int64_t* feat_offsets, const int64_t* epd_offsets, int64_t n_utts,
                               int64_t max_len, const dsp_frontend_params* p, const dsp_frontend_outputs* out) {
   if (!c) return fail(DSP_ERR_INVALID, "context is NULL");
   CU(cudaSetDevice(c->device));
-  return frontend_device(c, samples, dtype, offsets, feat_offsets, epd_offsets, n_utts, max_len, p, out);
+  return frontend_device(c, samples, dtype, offsets, lengths, feat_offsets, epd_offsets, n_utts, max_len, p, out);
 }
 
 int dsp_frontend_batch_host(dsp_context* c, const void* samples, int dtype, const int64_t* offsets,
-                            int64_t B, const dsp_frontend_params* p, const dsp_frontend_outputs* out) {
+                            const int32_t* lengths, int64_t B, const dsp_frontend_params* p, const dsp_frontend_outputs* out) {
   if (!c) return fail(DSP_ERR_INVALID, "context is NULL");
   int rc = check_params(p);
   if (rc) return rc;
@@ -449,7 +451,7 @@ int dsp_frontend_batch_host(dsp_context* c, const void* samples, int dtype, cons
   CU(cudaSetDevice(c->device));
   std::vector<int64_t> foff((size_t)B + 1), eoff((size_t)B + 1);
   int64_t max_len_all = 0;
-  rc = dsp_frontend_plan(offsets, B, p, foff.data(), eoff.data(), &max_len_all);
+  rc = dsp_frontend_plan(offsets, lengths, B, p, foff.data(), eoff.data(), &max_len_all);
   if (rc) return rc;
   rc = ensure_window(c, p->window, p->frame_length);
   if (rc) return rc;
@@ -466,17 +468,21 @@ int dsp_frontend_batch_host(dsp_context* c, const void* samples, int dtype, cons
     if (s.busy) { CU(cudaEventSynchronize(s.ev_out)); s.busy = false; }
     const int64_t e0 = offsets[b0], e1 = offsets[b1];
     const int64_t f0 = foff[(size_t)b0], f1 = foff[(size_t)b1], g0 = eoff[(size_t)b0], g1 = eoff[(size_t)b1];
-    CU(s.h_off.ensure(sizeof(int64_t) * 3 * (size_t)(bc + 1)));
+    CU(s.h_off.ensure(sizeof(int64_t) * 4 * (size_t)(bc + 1)));
     int64_t* h = s.h_off.as<int64_t>();
     int64_t chunk_max = 0;
     for (int64_t i = 0; i <= bc; ++i) {
       h[i] = offsets[b0 + i] - e0;
       h[(bc + 1) + i] = foff[(size_t)(b0 + i)] - f0;
       h[2 * (bc + 1) + i] = eoff[(size_t)(b0 + i)] - g0;
-      if (i < bc) chunk_max = std::max(chunk_max, (offsets[b0 + i + 1] - offsets[b0 + i]) / p->channels);
+      if (i < bc) {
+        const int64_t len = lengths ? (int64_t)lengths[b0 + i] : offsets[b0 + i + 1] - offsets[b0 + i];
+        chunk_max = std::max(chunk_max, len / p->channels);
+        reinterpret_cast<int32_t*>(h + 3 * (bc + 1))[i] = (int32_t)len;
+      }
     }
     CU(s.samples.ensure((size_t)(e1 - e0) * esz + 64));
-    CU(s.off.ensure(sizeof(int64_t) * 3 * (size_t)(bc + 1)));
+    CU(s.off.ensure(sizeof(int64_t) * 4 * (size_t)(bc + 1)));
     CU(s.ints.ensure(sizeof(int32_t) * 5 * (size_t)bc));
     CU(s.stats.ensure(sizeof(float) * kStats * (size_t)bc));
     CU(s.feat.ensure(sizeof(float) * 3 * (size_t)std::max<int64_t>(f1 - f0, 1)));
@@ -484,7 +490,7 @@ int dsp_frontend_batch_host(dsp_context* c, const void* samples, int dtype, cons
     CU(s.epd_z.ensure(sizeof(float) * (size_t)std::max<int64_t>(g1 - g0, 1)));
     // upload
     CU(cudaMemcpyAsync(s.samples.p, src + (size_t)e0 * esz, (size_t)(e1 - e0) * esz, cudaMemcpyHostToDevice, c->s_in));
-    CU(cudaMemcpyAsync(s.off.p, h, sizeof(int64_t) * 3 * (size_t)(bc + 1), cudaMemcpyHostToDevice, c->s_in));
+    CU(cudaMemcpyAsync(s.off.p, h, sizeof(int64_t) * 4 * (size_t)(bc + 1), cudaMemcpyHostToDevice, c->s_in));
     CU(cudaEventRecord(s.ev_in, c->s_in));
     CU(cudaStreamWaitEvent(c->stream, s.ev_in, 0));
     // kernels
@@ -501,7 +507,8 @@ int dsp_frontend_batch_host(dsp_context* c, const void* samples, int dtype, cons
     dsp_frontend_params pc = *p;
     pc.aligned16 = 1;                               // staging buffers come from cudaMalloc (256-byte aligned)
     for (int64_t i = 0; i < bc && pc.aligned16; ++i) if ((size_t)h[i] * esz % 16) pc.aligned16 = 0;
-    rc = frontend_device(c, s.samples.p, dtype, doff, doff + (bc + 1), doff + 2 * (bc + 1), bc, chunk_max, &pc, &o);
+    const int32_t* dlen = lengths ? reinterpret_cast<const int32_t*>(doff + 3 * (bc + 1)) : nullptr;
+    rc = frontend_device(c, s.samples.p, dtype, doff, dlen, doff + (bc + 1), doff + 2 * (bc + 1), bc, chunk_max, &pc, &o);
     if (rc) return rc;
     CU(cudaEventRecord(s.ev_k, c->stream));
     CU(cudaStreamWaitEvent(c->s_out, s.ev_k, 0));
@@ -543,7 +550,7 @@ static int one_signal(dsp_context* c, const double* x, int64_t n, const dsp_fron
   CU(cudaMemcpyAsync(dx, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
   CU(cudaMemcpyAsync(doff, hoff, sizeof hoff, cudaMemcpyHostToDevice, c->stream));
   CU(cudaStreamSynchronize(c->stream));  // hoff is a stack array
-  return launch_exact(c, dx, DSP_F64, doff, nullptr, nullptr, nullptr, nullptr, 1, n, p, dout, ex_in, 1);
+  return launch_exact(c, dx, DSP_F64, doff, nullptr, nullptr, nullptr, nullptr, nullptr, 1, n, p, dout, ex_in, 1);
 }
 
 int dsp_preprocess_host(dsp_context* c, const double* x, int64_t n, int mode, double* out) {

@@ -182,7 +182,7 @@ frontend_exact_kernel(const ExactArgs a) {
   for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int64_t b = a.list ? (int64_t)a.list[item] : item;
     const int64_t off = a.offsets[b];
-    const int64_t n = (a.offsets[b + 1] - off) / a.channels;
+    const int64_t n = (a.lengths ? (int64_t)a.lengths[b] : a.offsets[b + 1] - off) / a.channels;
     SampleReader rd{a.samples, a.dtype, a.channels, off};
     int status = DSP_UTT_EXACT;
 

@@ -430,7 +430,7 @@ frontend_pcm_kernel(const PcmArgs a) {
   // issue the load of utterance `uu` (uniform over the main warps)
   auto issue_load = [&](int uu) {
     const int64_t off = a.offsets[uu];
-    const int n = (int)(a.offsets[uu + 1] - off);
+    const int n = a.lengths ? a.lengths[uu] : (int)(a.offsets[uu + 1] - off);
     const int16_t* src = a.samples + off;
     const bool tma = ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
     if (tma) {
@@ -462,7 +462,7 @@ frontend_pcm_kernel(const PcmArgs a) {
   };
   auto wait_load = [&](int uu) {
     const int64_t off = a.offsets[uu];
-    const int n = (int)(a.offsets[uu + 1] - off);
+    const int n = a.lengths ? a.lengths[uu] : (int)(a.offsets[uu + 1] - off);
     const bool tma = ((reinterpret_cast<uintptr_t>(a.samples + off) & 15) == 0);
     if (tma && (((uint32_t)n * 2u) & ~15u) > 0) { mbar_wait(s_bar, parity); parity ^= 1; }
     main_sync();
@@ -477,7 +477,7 @@ frontend_pcm_kernel(const PcmArgs a) {
 
   while (u < a.n_utts) {
     const int64_t off = a.offsets[u];
-    const int n = (int)(a.offsets[u + 1] - off);
+    const int n = a.lengths ? a.lengths[u] : (int)(a.offsets[u + 1] - off);
     const int16_t* x = kStream ? a.samples + off : s_x;
     if constexpr (kStream) {
       if (reinterpret_cast<uintptr_t>(x) & 15) {
@@ -1030,6 +1030,8 @@ const Variant kVariants[] = {
     {frontend_pcm_kernel<true, 256, 2, 3>, 256, true, "stream 256 thr, >=3 CTAs/SM"},
     {frontend_pcm_kernel<true, 192, 2, 4>, 192, true, "stream 192 thr, >=4 CTAs/SM"},
     {frontend_pcm_kernel<true, 160, 1, 4>, 160, true, "stream 160 thr, >=4 CTAs/SM"},
+    {frontend_pcm_kernel<false, 256, 1, 2>, 256, false, "resident 256 thr (7 main + 1 stats warps)"},
+    {frontend_pcm_kernel<false, 288, 1, 2>, 288, false, "resident 288 thr (8 main + 1 stats warps)"},
 };
 constexpr int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 }  // namespace

@@ -20,6 +20,7 @@ struct ExactArgs {
   const void* samples;
   int dtype, channels;
   const int64_t* offsets;       // [B+1] element offsets
+  const int32_t* lengths;       // [B] elements per utterance, or null = offsets[b+1] - offsets[b]
   const int64_t* feat_offsets;  // [B+1] or null (single utterance: 0)
   const int64_t* epd_offsets;   // [B+1] or null
   const int32_t* list;          // utterance indices to process, or null = 0..n_items-1
@@ -44,6 +45,7 @@ struct ExactArgs {
 struct PcmArgs {
   const int16_t* samples;
   const int64_t* offsets;
+  const int32_t* lengths;       // [B] or null (packed CSR)
   const int64_t* feat_offsets;
   const int64_t* epd_offsets;
   int64_t n_utts;

@@ -29,7 +29,8 @@ class DeviceFrontend:
 
     def __init__(self, offsets, frame_length, frame_shift, window_type="hamming",
                  do_endpoint_detection=True, energy_high_ratio=0.5, energy_low_ratio=0.1,
-                 zcr_threshold_ratio=1.5, emit_epd_lists=False, force_exact=False, device=None, ctx=None):
+                 zcr_threshold_ratio=1.5, emit_epd_lists=False, force_exact=False, device=None, ctx=None,
+                 lengths=None):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.ctx = ctx or default_context(self.device.index or 0)
         self.params = make_params(frame_length, frame_shift, window_type, do_endpoint_detection,
@@ -37,9 +38,11 @@ class DeviceFrontend:
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)
         self.n_utts = len(offsets) - 1
         self.h_offsets = offsets
-        self.h_feat_offsets, self.h_epd_offsets, self.max_len = plan(offsets, self.params)
+        self.h_lengths = None if lengths is None else np.ascontiguousarray(lengths, dtype=np.int32)
+        self.h_feat_offsets, self.h_epd_offsets, self.max_len = plan(offsets, self.params, self.h_lengths)
         dev = self.device
         self.offsets = torch.from_numpy(offsets).to(dev)
+        self.lengths = None if self.h_lengths is None else torch.from_numpy(self.h_lengths).to(dev)
         self.feat_offsets = torch.from_numpy(self.h_feat_offsets).to(dev)
         self.epd_offsets = torch.from_numpy(self.h_epd_offsets).to(dev)
         b, nf, ne = self.n_utts, int(self.h_feat_offsets[-1]), int(self.h_epd_offsets[-1])
@@ -83,7 +86,7 @@ class DeviceFrontend:
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
         self.ctx.set_stream(st.cuda_stream)
         check(self.ctx.lib.dsp_frontend_batch_device(
-            self.ctx.handle, _dp(samples), _TORCH_DTYPES[samples.dtype], _dp(self.offsets),
+            self.ctx.handle, _dp(samples), _TORCH_DTYPES[samples.dtype], _dp(self.offsets), _dp(self.lengths),
             _dp(self.feat_offsets), _dp(self.epd_offsets), self.n_utts, self.max_len,
             C.byref(self.params), C.byref(self._out)))
         return self

@@ -113,12 +113,18 @@ int64_t dsp_launch_count(dsp_context* ctx);
 int dsp_device_sm_count(dsp_context* ctx);
 
 /* ---- front end --------------------------------------------------------- */
-/* Host arithmetic only.  offsets[B+1] are sample offsets of a packed ragged
- * batch (in samples of one channel times `channels`, i.e. element offsets).
- * Fills feat_offsets[B+1] / epd_offsets[B+1] (capacities: frame counts of the
- * untrimmed utterances) and returns the longest utterance. */
-int dsp_frontend_plan(const int64_t* offsets, int64_t n_utts, const dsp_frontend_params* p,
-                      int64_t* feat_offsets, int64_t* epd_offsets, int64_t* max_len);
+/* Batch layout: utterance b starts at element offsets[b] of the sample buffer (elements =
+ * samples of one channel times `channels`).  lengths == NULL: packed CSR, utterance b is
+ * [offsets[b], offsets[b+1]).  lengths != NULL: utterance b holds lengths[b] elements and
+ * offsets[b+1] - offsets[b] >= lengths[b] may include padding -- e.g. every start rounded up to
+ * a multiple of 8 samples so that the aligned (TMA / streaming) loads apply to ragged data.
+ *
+ * dsp_frontend_plan: host arithmetic only.  Fills feat_offsets[B+1] / epd_offsets[B+1]
+ * (capacities: frame counts of the untrimmed utterances) and returns the longest
+ * utterance. */
+int dsp_frontend_plan(const int64_t* offsets, const int32_t* lengths, int64_t n_utts,
+                      const dsp_frontend_params* p, int64_t* feat_offsets, int64_t* epd_offsets,
+                      int64_t* max_len);
 
 /* create_window (src/audio_processing.py:278-296): float64 window of `length`. */
 int dsp_window(int window_type, int32_t length, double* out);
@@ -127,14 +133,14 @@ int dsp_window(int window_type, int32_t length, double* out);
  * ('statistical'), batched (src/audio_processing.py:364-394,
  * src/feature_extraction.py:91-112).  All pointers are DEVICE pointers. */
 int dsp_frontend_batch_device(dsp_context* ctx, const void* samples, int dtype,
-                              const int64_t* offsets, const int64_t* feat_offsets,
+                              const int64_t* offsets, const int32_t* lengths, const int64_t* feat_offsets,
                               const int64_t* epd_offsets, int64_t n_utts, int64_t max_len,
                               const dsp_frontend_params* p, const dsp_frontend_outputs* out);
 
 /* Same with HOST pointers: stages through pinned memory in chunks, overlapping
  * upload, kernels and download.  This is the call the Python shims make. */
 int dsp_frontend_batch_host(dsp_context* ctx, const void* samples, int dtype,
-                            const int64_t* offsets, int64_t n_utts,
+                            const int64_t* offsets, const int32_t* lengths, int64_t n_utts,
                             const dsp_frontend_params* p, const dsp_frontend_outputs* out);
 
 /* preprocess = remove_dc + normalize_audio (src/audio_processing.py:49-90) for one

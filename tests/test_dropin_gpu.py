@@ -112,3 +112,36 @@ def test_sequence_method_and_per_frame_primitives(mods, golden_fe):
     assert ap.compute_zero_crossing_rate(fr[3]) == g["float/zcr"][3]
     st = fe.compute_statistics(g["float/energy"])
     assert [st[k] for k in ("mean", "std", "max", "min", "median")] == list(g["float/stats"][:5])
+
+
+def test_batched_dataset_loader_equals_per_file_loop(mods, tmp_path):
+    """one fused launch over the decoded tree gives the per-file results; the sweep
+    helper (BASELINE config 4) re-frames without re-decoding."""
+    from dsp_audioreclabs_b200 import dataset
+    from oracle import frontend_oracle as fo, synth
+    ap, fe, cfg = mods["src.audio_processing"], mods["src.feature_extraction"], mods["config"]
+    rng = np.random.default_rng(99)
+    ref = {}
+    for c in range(3):
+        d = tmp_path / f"class{c}"
+        d.mkdir()
+        for i in range(4):
+            pcm = synth.utterance_pcm(7 * i + c, int(rng.uniform(0.3, 0.6) * 44100), seed0=55)
+            write_wav(d / f"{i}.wav", pcm, 2, 1)
+            ref[str(d / f"{i}.wav")] = pcm
+    (tmp_path / ".hidden").mkdir()
+    (tmp_path / "class0" / "broken.wav").write_bytes(b"not a wav")
+    X, y, names, feat = dataset.load_dataset(str(tmp_path), cfg.FRAME_LENGTH, cfg.FRAME_SHIFT, "hamming")
+    assert names == ["class0", "class1", "class2"] and X.shape == (12, 15) and len(feat) == 15
+    assert list(np.bincount(y)) == [4, 4, 4]
+    clips, labels, _, paths = dataset.decode_tree(str(tmp_path))
+    for row, path in zip(X, paths):
+        r = fo.frontend_utterance(ref[path], cfg.FRAME_LENGTH, cfg.FRAME_SHIFT, "hamming")
+        assert np.allclose(row, r["stats"], rtol=2e-5, atol=1e-7 * np.abs(r["stats"]).max())
+        frames, _, _ = ap.process_audio_file(path, cfg.FRAME_LENGTH, cfg.FRAME_SHIFT, "hamming")
+        assert np.allclose(row, fe.extract_features_from_frames(frames)[0], rtol=1e-6)
+    sweep, _ = dataset.ablation_sweep(str(tmp_path), [(352, 441), (1102, 132), (2205, 441)])
+    for (fl, fs), (Xs, ys) in sweep.items():
+        assert Xs.shape == (12, 15)
+        r = fo.frontend_utterance(ref[paths[0]], fl, fs, "hamming")
+        assert np.allclose(Xs[0], r["stats"], rtol=2e-5, atol=1e-7 * np.abs(r["stats"]).max())

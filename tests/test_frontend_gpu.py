@@ -24,38 +24,6 @@ def pack(utts):
     return np.concatenate(utts) if len(utts) else np.zeros(0, np.int16), off
 
 
-def pack_aligned(utts):
-    """Pack with a filler utterance after each real one so that every real utterance starts on a
-    multiple of 8 samples (16 bytes): the layout the streaming build of the fused kernel needs.
-    Returns (samples, offsets, index of each real utterance in the batch)."""
-    parts, idx = [], []
-    pos = 0
-    for u in utts:
-        idx.append(len(parts))
-        parts.append(u)
-        pos += len(u)
-        pad = (-pos) % 8
-        parts.append(np.zeros(pad, np.int16))
-        pos += pad
-    s, off = pack(parts)
-    return s, off, idx
-
-
-class Picked:
-    """View of a FrontendResult restricted to the real utterances of an aligned pack."""
-
-    def __init__(self, res, idx):
-        self.res, self.idx = res, idx
-        self.status, self.start, self.end = res.status[idx], res.start[idx], res.end[idx]
-        self.n_frames, self.stats = res.n_frames[idx], res.stats[idx]
-
-    def frames(self, b):
-        return self.res.frames(self.idx[b])
-
-    def epd_lists(self, b):
-        return self.res.epd_lists(self.idx[b])
-
-
 def assert_stats_close(got, ref, seqs):
     """mean / max / median: 1e-5 relative; std / min: 1e-5 of the sequence's scale (a std that is
     tiny next to the mean cannot be held to a relative bound by any fp32 per-frame pass)."""
@@ -107,11 +75,10 @@ def test_fast_kernel_matches_reference_fixtures(ctx, golden_fe, ci, win, variant
     ctx.set_tuning("pcm_variant", variant)
     try:
         if variant == STREAM:
-            samples, off, idx = pack_aligned(utts)
-            res = batch.frontend_batch(samples, off, fl, fs, win, emit_epd_lists=True, ctx=ctx)
+            samples, off, lengths = batch.pack_aligned(utts)          # 16-byte aligned starts + explicit lengths
+            res = batch.frontend_batch(samples, off, fl, fs, win, emit_epd_lists=True, lengths=lengths, ctx=ctx)
             # the streaming kernel really ran: nothing except certified-margin flags was replayed
-            assert int(((res.status[idx] & 0x100) != 0).sum()) <= 4   # exact-tie fixtures (zeros, constant, square steps)
-            res = Picked(res, idx)
+            assert int(((res.status & 0x100) != 0).sum()) <= 4   # exact-tie fixtures (zeros, constant, square steps)
         else:
             samples, off = pack(utts)
             res = batch.frontend_batch(samples, off, fl, fs, win, emit_epd_lists=True, ctx=ctx)
@@ -208,6 +175,29 @@ def test_misaligned_and_odd_offsets(ctx):
         for x, y in zip(ra.epd_lists(i), rb.epd_lists(j)):
             assert np.array_equal(x, y)
         assert np.array_equal(ra.stats[i], rb.stats[j])
+
+
+def test_padded_layout_with_explicit_lengths_equals_packed(ctx):
+    """offsets + lengths (aligned, padded storage) must give exactly what the packed CSR layout gives."""
+    from dsp_audioreclabs_b200 import batch
+    from oracle import synth
+    utts = [synth.utterance_pcm(70 + i, n, seed0=3) for i, n in enumerate([9001, 12347, 7777, 15003, 8192, 100, 0, 5000])]
+    a_s, a_o = pack(utts)
+    b_s, b_o, b_l = batch.pack_aligned(utts)
+    assert np.all(b_o % 8 == 0) and list(b_l) == [len(u) for u in utts]
+    for exact in (False, True):
+        ra = batch.frontend_batch(a_s, a_o, 256, 128, "hanning", emit_epd_lists=True, force_exact=exact, ctx=ctx)
+        rb = batch.frontend_batch(b_s, b_o, 256, 128, "hanning", emit_epd_lists=True, force_exact=exact, lengths=b_l, ctx=ctx)
+        for name in ("start", "end", "n_frames", "n_epd_frames"):
+            assert np.array_equal(getattr(ra, name), getattr(rb, name)), name
+        assert np.array_equal(ra.status & 0xff, rb.status & 0xff)
+        for i in range(len(utts)):
+            for x, y in zip(ra.frames(i), rb.frames(i)):
+                assert np.array_equal(x, y)
+            for x, y in zip(ra.epd_lists(i), rb.epd_lists(i)):
+                assert np.array_equal(x, y)
+    with pytest.raises(ValueError):
+        batch.frontend_batch(b_s, b_o, 256, 128, lengths=b_l + 9, ctx=ctx)     # length exceeds its slot
 
 
 def test_empty_and_degenerate_inputs(ctx):
