@@ -223,8 +223,54 @@ int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_
   // automatic choice: the streaming build when the caller vouches for 16-byte aligned utterances,
   // the shared-memory-resident build (any alignment) otherwise
   constexpr int kAutoStream = 2, kAutoResident = 0;
-  int variant = c->pcm_variant >= 0 ? c->pcm_variant : (p->aligned16 ? kAutoStream : kAutoResident);
+  int variant = (c->pcm_variant >= 0 && c->pcm_variant < pcm_num_variants()) ? c->pcm_variant : (p->aligned16 ? kAutoStream : kAutoResident);
   if (pcm_variant_streams(variant) && !p->aligned16 && c->pcm_variant < 0) variant = kAutoResident;
+  // the pipelined kernel (frontend_pipe.cu): automatic for 16-byte aligned layouts, or forced by the
+  // tuning knob (pcm_variant == pcm_num_variants()); misaligned utterances inside it are replayed
+  const int kPipeVariant = pcm_num_variants();
+  PipePlan plan{};
+  bool pipe = fast && (c->pcm_variant == kPipeVariant || (c->pcm_variant < 0 && p->aligned16)) &&
+              pipe_kernel_plan(max_len, (int)cap_frames64, fl, kMaxSmemPerCta, &plan);
+  if (fast && !pipe && c->pcm_variant == kPipeVariant) variant = kAutoResident;
+  if (pipe) {
+    CU(c->counters.ensure(64));
+    CU(c->flag_list.ensure(sizeof(int32_t) * (size_t)B));
+    CU(cudaMemsetAsync(c->counters.p, 0, 64, c->stream));
+    PcmArgs a{};
+    a.samples = reinterpret_cast<const int16_t*>(samples);
+    a.offsets = offsets; a.lengths = lengths; a.feat_offsets = feat_offsets; a.epd_offsets = epd_offsets;
+    a.n_utts = B; a.fl = fl; a.fs = fs; a.window = p->window; a.do_epd = p->do_endpoint_detection;
+    a.hr = p->energy_high_ratio; a.lr = p->energy_low_ratio; a.zr = p->zcr_threshold_ratio;
+    a.win_f32 = c->win32.as<float>();
+    a.cap_frames = (int)cap_frames64;
+    a.tma_chunk = std::getenv("DSP_PIPE_DEBUG") ? std::atoi(std::getenv("DSP_PIPE_DEBUG")) : 0;   // debug switches, 0 in production
+    a.ring_slots = plan.ring_slots; a.n_rec = plan.n_rec; a.cap_groups = plan.cap_groups;
+    a.sm_count = c->sm_count;
+    a.work_counter = c->counters.as<unsigned int>();
+    a.flag_count = c->counters.as<int32_t>() + 1;
+    a.flag_list = c->flag_list.as<int32_t>();
+    a.out = *out;
+    const int grid = (int)std::min<int64_t>(B, (int64_t)c->sm_count);
+    static long long* d_prof = nullptr;
+    if (std::getenv("DSP_PROF")) {
+      if (!d_prof) cudaMalloc(&d_prof, 16 * sizeof(long long));
+      cudaMemsetAsync(d_prof, 0, 16 * sizeof(long long), c->stream);
+      a.prof = d_prof;
+    }
+    CU(launch_frontend_pipe(a, grid, plan.smem, c->stream));
+    if (a.prof) {
+      long long h[16]; cudaMemcpyAsync(h, d_prof, sizeof h, cudaMemcpyDeviceToHost, c->stream); cudaStreamSynchronize(c->stream);
+      const char* nm[12] = {"S.wait_full", "S.passA", "S.bar1", "S.passB", "S.bar2", "S.wait_rec", "S.passF", "-", "T.wait", "T.decide", "T.window", "T.stats+out"};
+      fprintf(stderr, "[prof pipe R=%d nrec=%d] utterances=%lld (cycles/utt, stream warp 0 / tail warp 0 x nrec)", plan.ring_slots, plan.n_rec, h[15]);
+      for (int i = 0; i < 12; ++i) fprintf(stderr, "  %s=%.0f", nm[i], (double)h[i] / (double)std::max<long long>(h[15], 1) * (i >= 8 ? plan.n_rec : 1));
+      fprintf(stderr, "\n");
+    }
+    c->launches++;
+    ExactExtras ex;
+    const int xgrid = (int)std::min<int64_t>(B, (int64_t)c->sm_count);
+    return launch_exact(c, samples, dtype, offsets, lengths, feat_offsets, epd_offsets, a.flag_list, a.flag_count, 0,
+                        max_len, p, out, ex, xgrid);
+  }
   if (fast) {
     cap_samples = (int)((std::max<int64_t>(max_len, 1) + 63) / 64 * 64);
     smem = pcm_kernel_smem_bytes(cap_samples, (int)cap_frames64, fl, !pcm_variant_streams(variant));
@@ -321,7 +367,7 @@ int dsp_create(int device, dsp_context** out) {
   CU(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
   c->stream = c->own;
-  if (const char* e = std::getenv("DSP_PCM_VARIANT")) { int v = std::atoi(e); if (v >= -1 && v < pcm_num_variants()) c->pcm_variant = v; }
+  if (const char* e = std::getenv("DSP_PCM_VARIANT")) { int v = std::atoi(e); if (v >= -1 && v <= pcm_num_variants()) c->pcm_variant = v; }
   if (const char* e = std::getenv("DSP_STAGGER_NS")) c->stagger_ns = std::atoi(e);
   if (const char* e = std::getenv("DSP_TMA_CHUNK")) { int v = std::atoi(e); if (v >= 16 && v % 16 == 0) c->tma_chunk = v; }
   for (auto& s : c->slot) {
@@ -369,7 +415,7 @@ int dsp_use_own_stream(dsp_context* c) {
 int dsp_set_tuning(dsp_context* c, const char* key, int value) {
   if (!c || !key) return fail(DSP_ERR_INVALID, "bad argument");
   if (!std::strcmp(key, "pcm_variant")) {
-    if (value < -1 || value >= pcm_num_variants()) return fail(DSP_ERR_INVALID, "pcm_variant out of range (%d builds)", pcm_num_variants());
+    if (value < -1 || value > pcm_num_variants()) return fail(DSP_ERR_INVALID, "pcm_variant out of range (%d builds + the pipelined kernel)", pcm_num_variants());
     c->pcm_variant = value;
   } else if (!std::strcmp(key, "tma_chunk")) {
     if (value < 16 || value % 16) return fail(DSP_ERR_INVALID, "tma_chunk must be a positive multiple of 16");

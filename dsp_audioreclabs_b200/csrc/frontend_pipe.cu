@@ -1,0 +1,1087 @@
+// Pipelined fused front-end kernel for 16-bit mono PCM (the throughput path, round-1 redesign).
+//
+// One persistent CTA per SM, three warp roles that never meet at a CTA-wide barrier:
+//
+//   control warp (1)   dynamic utterance scheduler + TMA producer.  Utterances are cut into 4 KB
+//                      chunks that travel through a ring of shared-memory slots (full/empty
+//                      mbarrier pair per slot, cp.async.bulk), so the next utterances are in
+//                      flight while the current one is being reduced.
+//   stream warps (8)   the two passes that touch EVERY sample, straight from the ring:
+//                        A  per 64-sample group: sum k, sum k^2 (exact integers via dp4a on the
+//                           byte planes), min, max                  -> DC (rational S/N), peak
+//                        B  one sign bit per sample (k >= thr, thr = floor(S/N)+1)
+//                        F  every endpoint-detection frame from the group sums / sign bits:
+//                           float64 energy, zero-crossing count  -> a small per-utterance record
+//                      The ring slots are released right after pass B: samples stay on chip for
+//                      exactly two reads and HBM is read once.
+//   tail warps (<= 7)  one WARP per utterance, several utterances in flight: 90th percentile by
+//                      bisection on float keys + float64 ranking of <= 32 survivors, thresholds
+//                      in NumPy's order, the six endpoint searches (certified margins, else
+//                      float64 replay), windowed energy / magnitude of the trimmed segment (re-read
+//                      from L2, fp32), the 15 statistics, all outputs.  Purely warp-synchronous:
+//                      its latency is hidden by the other tail warps and the stream warps.
+//
+// Exactness argument: identical to frontend_pcm.cu (DESIGN.md "numerics"); only the schedule differs.
+// Reference: src/audio_processing.py:49-90,135-275,299-333; src/feature_extraction.py:12-88.
+#include <algorithm>
+#include "kernels.cuh"
+
+namespace dsp {
+
+namespace {
+
+constexpr int kGroup = 64;                 // samples per group-sum record
+constexpr int kChunkSamples = 2048;        // samples per ring slot
+constexpr int kChunkBytes = 2 * kChunkSamples;
+constexpr int kGroupsPerChunk = kChunkSamples / kGroup;   // 32: one group per stream lane
+constexpr int kStreamWarps = 8;
+constexpr int kMaxTailWarps = 7;
+constexpr int kPipeWarps = kStreamWarps + kMaxTailWarps + 1;
+constexpr int kPipeThreads = 32 * kPipeWarps;             // 512
+constexpr int kStreamThreads = 32 * kStreamWarps;
+constexpr int kDescRing = 64;              // > max ring slots: the producer can never lap a reader
+constexpr int kMaxRingSlots = 56;
+constexpr int kRecHdr = 128;
+constexpr int kKeyRegs = 11;               // EPD frames per lane whose float keys stay in registers
+constexpr int kLanesPerFrame = 8;          // generic windowed pass: lanes cooperating on one frame
+
+constexpr int kBarStream = 1;              // named barrier of the stream warps
+
+struct PipeLayout {
+  int ring, gsum, bits, meta, rec, scratch, win, desc, part, consts, bars, total;
+  int rec_bytes, rec_e, rec_z, rec_zf;
+};
+
+__host__ __device__ inline int al16(int x) { return (x + 15) & ~15; }
+
+// R ring slots, capG groups / capF frames per utterance, nrec records (= active tail warps)
+__host__ __device__ inline PipeLayout make_pipe_layout(int R, int capG, int capF, int fl, int nrec) {
+  PipeLayout L;
+  int o = 0;
+  L.ring = o;    o += R * kChunkBytes;
+  L.gsum = o;    o += 2 * 8 * capG;
+  L.bits = o;    o += al16(8 * capG + 16);
+  L.meta = o;    o += al16(4 * capG);
+  L.rec_e = kRecHdr;
+  L.rec_z = L.rec_e + al16(8 * capF);
+  L.rec_zf = L.rec_z + al16(2 * capF);
+  L.rec_bytes = L.rec_zf + al16(2 * capF);
+  L.rec = o;     o += nrec * L.rec_bytes;
+  L.scratch = o; o += nrec * 256;
+  L.win = o;     o += al16(4 * fl);
+  L.desc = o;    o += kDescRing * 8;
+  L.part = o;    o += 2 * kStreamWarps * 16;
+  L.consts = o;  o += 2 * 64;
+  L.bars = o;    o += 8 * (2 * R + 2 * nrec);
+  L.total = o;
+  return L;
+}
+
+// ---- mbarrier / bulk-copy PTX ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)     // suspend-time hint: sleep, do not spin
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// ---- integer dot products on byte planes ------------------------------------------------
+__device__ __forceinline__ int dp4a_ss(int a, int b, int c) { int d; asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int dp4a_su(int a, uint32_t b, int c) { int d; asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ uint32_t dp4a_uu(uint32_t a, uint32_t b, uint32_t c) { uint32_t d; asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2) ---------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float hsum2(f32x2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a + b; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// frame_signal's frame count (kernels.cuh frame_count_host_device) in 32-bit arithmetic
+__device__ __forceinline__ int frame_count32(int n, int fl, int fs) {
+  if (n <= 0) return 0;
+  const int a = (n + fs - 1) / fs;
+  const int rem = n > fl ? n - fl : 0;
+  const int b = (rem + fs - 1) / fs + 1;
+  return a < b ? a : b;
+}
+
+__device__ __forceinline__ int sext16(uint32_t w) { return (int)(short)(w & 0xffffu); }
+
+// ---- sign-bit string helpers (linear order, bit i = "sample i is above the mean") ------------
+__device__ __forceinline__ int bit_at(const uint32_t* bits, int i) { return (bits[i >> 5] >> (i & 31)) & 1; }
+
+__device__ __forceinline__ int count_changes(const uint32_t* bits, int p, int q) {
+  if (q - p < 2) return 0;
+  int c = 0;
+  if (((p | q) & 31) == 0) {
+    const int w0 = p >> 5, w1 = (q >> 5) - 1;
+    uint32_t cur = bits[w0];
+    for (int w = w0; w < w1; ++w) {
+      const uint32_t nxt = bits[w + 1];
+      c += __popc(cur ^ __funnelshift_r(cur, nxt, 1));
+      cur = nxt;
+    }
+    c += __popc((cur ^ (cur >> 1)) & 0x7fffffffu);
+    return c;
+  }
+  const int last = q - 2;
+  const int w0 = p >> 5, w1 = last >> 5;
+#pragma unroll 1
+  for (int w = w0; w <= w1; ++w) {
+    const uint32_t cur = bits[w], nxt = bits[w + 1];
+    uint32_t x = cur ^ __funnelshift_r(cur, nxt, 1);
+    if (w == w0) x &= 0xffffffffu << (p & 31);
+    if (w == w1) x &= 0xffffffffu >> (31 - (last & 31));
+    c += __popc(x);
+  }
+  return c;
+}
+
+// zero crossings of one windowed frame (compute_zero_crossing_rate on frame*window,
+// audio_processing.py:119-132): zero padding and Hanning's exact-zero end points count as negative
+__device__ __noinline__ int frame_zcr(const uint32_t* bits, int p, int valid, int fl, bool hann) {
+  if (hann && fl <= 2) return 0;
+  int zc = count_changes(bits, p, p + valid);
+  if (valid < fl) zc += bit_at(bits, p + valid - 1);
+  if (hann) {
+    const int s0 = bit_at(bits, p), s1 = valid > 1 ? bit_at(bits, p + 1) : 0;
+    zc += s1 - (s0 ^ s1);
+    if (fl - 1 < valid) {
+      const int sl = bit_at(bits, p + fl - 1), sp = bit_at(bits, p + fl - 2);
+      zc += sp - (sp ^ sl);
+    }
+  }
+  return zc;
+}
+
+// np.mean of the <= 10 noise frames in NumPy's association (audio_processing.py:188-195)
+__device__ __noinline__ double noise_mean(const double* v, int n) {
+  double r;
+  if (n < 8) { r = 0.0; for (int i = 0; i < n; ++i) r += v[i]; }
+  else { r = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7])); for (int i = 8; i < n; ++i) r += v[i]; }
+  return r / (double)n;
+}
+
+__device__ __forceinline__ double warp_min_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// Statistics of one non-negative float sequence by ONE warp (compute_statistics,
+// feature_extraction.py:46-62): mean, population std, max, min, and the median by bisection on
+// the float bit patterns (no shared-memory histogram: a tail warp owns nothing but its record).
+// get(i) yields element i.
+// ---------------------------------------------------------------------------------------
+template <class Get>
+__device__ __forceinline__ void warp_stats(Get get, int n, float* out5) {
+  const int lane = threadIdx.x & 31;
+  double sum = 0.0;
+  uint32_t kmx = 0u, kmn = 0xffffffffu;
+#pragma unroll 1
+  for (int i = lane; i < n; i += 32) { const float x = get(i); sum += (double)x; const uint32_t k = __float_as_uint(x); kmx = max(kmx, k); kmn = min(kmn, k); }
+  sum = warp_reduce(sum, OpAddD());
+  kmx = __reduce_max_sync(0xffffffffu, kmx);
+  kmn = __reduce_min_sync(0xffffffffu, kmn);
+  const double mean = sum / (double)n;
+  double ss = 0.0;
+#pragma unroll 1
+  for (int i = lane; i < n; i += 32) { const double d = (double)get(i) - mean; ss += d * d; }
+  ss = warp_reduce(ss, OpAddD());
+  // median: key of rank r = (n-1)/2 by bisection; rank r+1 is the same key or the next larger one
+  const int rank = (n - 1) >> 1;
+  uint32_t prefix = kmn;
+  const uint32_t diff = kmn ^ kmx;
+  if (diff) {
+    int b = 31 - __clz(diff);
+    prefix = kmn & ~((2u << b) - 1u);
+    int cnt_lo = 0, cnt_bin = n;
+    while (b >= 0 && cnt_bin > 1) {
+      const uint32_t trial = prefix | (1u << b);
+      int c = 0;
+#pragma unroll 1
+      for (int i = lane; i < n; i += 32) c += (__float_as_uint(get(i)) < trial);
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (rank < c) cnt_bin = c - cnt_lo;
+      else { prefix = trial; cnt_bin = cnt_lo + cnt_bin - c; cnt_lo = c; }
+      --b;
+    }
+    if (b >= 0) {      // a single key is left in [prefix, prefix + 2^(b+1)): fetch it
+      const uint32_t hi = prefix + ((2u << b) - 1u);
+      uint32_t k = 0xffffffffu;
+#pragma unroll 1
+      for (int i = lane; i < n; i += 32) { const uint32_t kk = __float_as_uint(get(i)); if (kk >= prefix && kk <= hi) k = min(k, kk); }
+      prefix = __reduce_min_sync(0xffffffffu, k);
+    }
+  }
+  const float sel = __uint_as_float(prefix);
+  float sel2 = sel;
+  if (!(n & 1)) {
+    int le = 0;
+    uint32_t nxt = 0xffffffffu;
+#pragma unroll 1
+    for (int i = lane; i < n; i += 32) { const uint32_t kk = __float_as_uint(get(i)); if (kk <= prefix) ++le; else nxt = min(nxt, kk); }
+    le = __reduce_add_sync(0xffffffffu, le);
+    nxt = __reduce_min_sync(0xffffffffu, nxt);
+    if (le < rank + 2 && nxt != 0xffffffffu) sel2 = __uint_as_float(nxt);
+  }
+  if (lane == 0) {
+    out5[0] = (float)mean;
+    out5[1] = (float)sqrt(ss / (double)n);
+    out5[2] = __uint_as_float(kmx); out5[3] = __uint_as_float(kmn);
+    out5[4] = (n & 1) ? sel : (float)(((double)sel + (double)sel2) * 0.5);
+  }
+}
+
+// The same statistics for the three feature sequences of one utterance with the values held in
+// registers (NJ per lane): one copy of the code, no shared-memory re-reads in the bisection.
+template <int NJ>
+__device__ __noinline__ void tail_stats_regs(const float* fe, const float* fm, const unsigned short* zf, int n, float* out15) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (int q = 0; q < 3; ++q) {
+    const float* src = q == 0 ? fe : fm;
+    uint32_t key[NJ];
+    float ps = 0.f;
+    uint32_t kmn = 0xffffffffu, kmx = 0u;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int i = lane + 32 * j;
+      float x = 0.f;
+      if (i < n) x = q == 2 ? (float)zf[i] : src[i];
+      key[j] = i < n ? __float_as_uint(x) : 0xffffffffu;
+      if (i < n) { ps += x; kmn = min(kmn, key[j]); kmx = max(kmx, key[j]); }
+    }
+    const double mean = warp_reduce((double)ps, OpAddD()) / (double)n;
+    kmx = __reduce_max_sync(0xffffffffu, kmx);
+    kmn = __reduce_min_sync(0xffffffffu, kmn);
+    const float meanf = (float)mean;
+    float pss = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) if (lane + 32 * j < n) { const float d = __uint_as_float(key[j]) - meanf; pss += d * d; }
+    const double ss = warp_reduce((double)pss, OpAddD());
+    const int rank = (n - 1) >> 1;
+    uint32_t prefix = kmn;
+    const uint32_t diff = kmn ^ kmx;
+    if (diff) {
+      int b = 31 - __clz(diff);
+      prefix = kmn & ~((2u << b) - 1u);
+      int cnt_lo = 0, cnt_bin = n;
+      while (b >= 0 && cnt_bin > 1) {
+        const uint32_t trial = prefix | (1u << b);
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) c += (key[j] < trial);
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (rank < c) cnt_bin = c - cnt_lo;
+        else { prefix = trial; cnt_bin = cnt_lo + cnt_bin - c; cnt_lo = c; }
+        --b;
+      }
+      if (b >= 0) {      // a single key is left in [prefix, prefix + 2^(b+1)): fetch it
+        const uint32_t hi = prefix + ((2u << b) - 1u);
+        uint32_t k = 0xffffffffu;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) if (key[j] >= prefix && key[j] <= hi) k = min(k, key[j]);
+        prefix = __reduce_min_sync(0xffffffffu, k);
+      }
+    }
+    const float sel = __uint_as_float(prefix);
+    float sel2 = sel;
+    if (!(n & 1)) {
+      int le = 0;
+      uint32_t nxt = 0xffffffffu;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { if (key[j] <= prefix) ++le; else nxt = min(nxt, key[j]); }
+      le = __reduce_add_sync(0xffffffffu, le);
+      nxt = __reduce_min_sync(0xffffffffu, nxt);
+      if (le < rank + 2 && nxt != 0xffffffffu) sel2 = __uint_as_float(nxt);
+    }
+    if (lane == 0) {
+      float* o = out15 + 5 * q;
+      o[0] = (float)mean;
+      o[1] = (float)sqrt(ss / (double)n);
+      o[2] = __uint_as_float(kmx); o[3] = __uint_as_float(kmn);
+      o[4] = (n & 1) ? sel : (float)(((double)sel + (double)sel2) * 0.5);
+    }
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const PcmArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int R = a.ring_slots, nrec = a.n_rec;
+  const PipeLayout L = make_pipe_layout(R, a.cap_groups, a.cap_frames, a.fl, nrec);
+  unsigned char* s_ring = smem + L.ring;
+  unsigned long long* s_gsum = reinterpret_cast<unsigned long long*>(smem + L.gsum);   // [2][capG]
+  uint32_t* s_bits = reinterpret_cast<uint32_t*>(smem + L.bits);
+  uint32_t* s_meta = reinterpret_cast<uint32_t*>(smem + L.meta);   // per group: crossings inside it, its first / last two bits
+  float* s_win = reinterpret_cast<float*>(smem + L.win);
+  int2* s_desc = reinterpret_cast<int2*>(smem + L.desc);
+  int4* s_part = reinterpret_cast<int4*>(smem + L.part);                                // [2][kStreamWarps]
+  double* s_consts = reinterpret_cast<double*>(smem + L.consts);                        // [2][8]
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* bar_empty = bar_full + R;
+  uint64_t* bar_rfull = bar_empty + R;
+  uint64_t* bar_rempty = bar_rfull + nrec;
+
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int fl = a.fl, fs = a.fs;
+  const bool hann = (a.window == DSP_WIN_HANNING);
+  // frames are sums of whole groups: the stream warps are done with the samples after pass B
+  const bool edges = ((fl % kGroup) | (fs % kGroup)) != 0 || fl > 16384;
+
+#pragma unroll 1
+  for (int j = tid; j < fl; j += kPipeThreads) s_win[j] = a.win_f32[j];
+  if (tid == 0) {
+    for (int i = 0; i < R; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], kStreamWarps); }
+    for (int i = 0; i < nrec; ++i) { mbar_init(&bar_rfull[i], kStreamWarps); mbar_init(&bar_rempty[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // =========================================================================================
+  // CONTROL WARP: work distribution + TMA producer
+  // =========================================================================================
+  if (wid == kPipeWarps - 1) {
+    if (lane != 0) return;
+    int slot = 0, lap = 0, useq = 0;
+    unsigned int u_next = atomicAdd(a.work_counter, 1u);
+    for (;;) {
+      const long long u = (long long)u_next;
+      const bool done = u >= a.n_utts;
+      int n = 0;
+      const int16_t* src = nullptr;
+      if (!done) {
+        u_next = atomicAdd(a.work_counter, 1u);       // one index ahead: its latency hides behind the copies
+        const int64_t off = a.offsets[u];
+        n = a.lengths ? a.lengths[u] : (int)(a.offsets[u + 1] - off);
+        src = a.samples + off;
+        if (reinterpret_cast<uintptr_t>(src) & 15) n = -1 - n;        // misaligned: not this kernel's layout
+      }
+      s_desc[useq & (kDescRing - 1)] = make_int2(done ? -1 : (int)u, n);
+      const int nchunks = n > 0 ? (n + kChunkSamples - 1) / kChunkSamples : 1;
+      for (int c = 0; c < nchunks; ++c) {
+        if (lap > 0) mbar_wait(&bar_empty[slot], (uint32_t)((lap - 1) & 1));
+        unsigned char* dst = s_ring + (size_t)slot * kChunkBytes;
+        const int s0 = c * kChunkSamples;
+        const int cnt = n > 0 ? min(kChunkSamples, n - s0) : 0;
+        const uint32_t bytes = ((uint32_t)cnt * 2u) & ~15u;
+        // tail of < 8 samples by plain loads; the release of the arrive below publishes them
+        for (int i = (int)(bytes >> 1); i < cnt; ++i) reinterpret_cast<int16_t*>(dst)[i] = src[s0 + i];
+        if (bytes) {
+          mbar_expect_tx(&bar_full[slot], bytes);
+          bulk_g2s(dst, reinterpret_cast<const unsigned char*>(src + s0), bytes, &bar_full[slot]);
+        } else {
+          mbar_arrive(&bar_full[slot]);
+        }
+        if (++slot == R) { slot = 0; ++lap; }
+      }
+      ++useq;
+      if (done) break;
+    }
+    return;
+  }
+
+  // =========================================================================================
+  // TAIL WARPS: one warp per utterance record
+  // =========================================================================================
+  // warp ids: stream 0..7, tail 8..14, control 15 (the scheduler favours high ids: the latency-bound
+  // tail warps get the issue slots they can use, the throughput-bound stream warps fill the rest)
+#ifndef DSP_PIPE_TAIL_LOW
+  const int twid = wid - kStreamWarps;
+#else
+  const int twid = wid;
+#endif
+  if (twid >= 0 && twid < kMaxTailWarps) {
+    if (twid >= nrec) return;
+    unsigned char* rec = smem + L.rec + (size_t)twid * L.rec_bytes;
+    int* r_int = reinterpret_cast<int*>(rec);
+    double* r_dbl = reinterpret_cast<double*>(rec + 64);
+    double* r_e = reinterpret_cast<double*>(rec + L.rec_e);
+    const unsigned short* r_z = reinterpret_cast<const unsigned short*>(rec + L.rec_z);
+    const unsigned short* r_zf = reinterpret_cast<const unsigned short*>(rec + L.rec_zf);
+    float* s_fe = reinterpret_cast<float*>(r_e);            // feature sequences reuse the energy array
+    float* s_fm = s_fe + a.cap_frames;
+    double* cand = reinterpret_cast<double*>(smem + L.scratch + (size_t)twid * 256);
+
+    // window coefficients of the hop-128 / length-256 chain: a lane owns samples 8*(lane&15) .. +8 of
+    // every hop block; c = 0 is the first half of a frame, c = 1 the second
+    const bool chain_cfg = (fs == 128 && fl == 256);
+    f32x2 cw[2][4], cw2[2][4];         // (w, w) and (w^2, w^2) pairs of the lane's 8 samples
+    if (chain_cfg) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float w0 = s_win[c * 128 + 8 * (lane & 15) + 2 * k], w1 = s_win[c * 128 + 8 * (lane & 15) + 2 * k + 1];
+          cw[c][k] = pk2(w0, w1); cw2[c][k] = pk2(w0 * w0, w1 * w1);
+        }
+    }
+
+    long long tp[5] = {0, 0, 0, 0, 0}, tprev = clock64();
+    auto tick = [&](int i) { if (a.prof) { const long long t = clock64(); tp[i] += t - tprev; tprev = t; } };
+    for (int it = 0;; ++it) {
+      mbar_wait(&bar_rfull[twid], (uint32_t)(it & 1));
+      const int u = r_int[0];
+      if (u < 0) break;
+      tick(0);
+      const int n = r_int[1], f1 = r_int[2], thr = r_int[4], kmn_s = r_int[5], kmx_s = r_int[6];
+      const double phi_d = r_dbl[0], inv_m = r_dbl[1], mu = r_dbl[2];
+      const float phi = (float)phi_d;
+      const int16_t* x = a.samples + a.offsets[u];
+
+      // =========================== endpoint decision ===================================
+      int start = 0, end = n, flagged = 0;
+      if (f1 > 0) {
+        const double v = (double)(f1 - 1) * (90.0 / 100.0);
+        const bool top = v >= (double)(f1 - 1);
+        int rank = top ? f1 - 1 : (int)floor(v);
+        // float projections of the energies (monotone); kept in registers for the usual sizes
+        const bool in_regs = f1 <= 32 * kKeyRegs;
+        uint32_t key[kKeyRegs];
+        uint32_t kmin = 0xffffffffu, kmax = 0u;
+        if (in_regs) {
+#pragma unroll
+          for (int j = 0; j < kKeyRegs; ++j) {
+            const int f = lane + 32 * j;
+            key[j] = f < f1 ? __float_as_uint((float)r_e[f]) : 0xffffffffu;
+            if (f < f1) { kmin = min(kmin, key[j]); kmax = max(kmax, key[j]); }
+          }
+        } else {
+#pragma unroll 1
+          for (int f = lane; f < f1; f += 32) { const uint32_t k = __float_as_uint((float)r_e[f]); kmin = min(kmin, k); kmax = max(kmax, k); }
+        }
+        kmin = __reduce_min_sync(0xffffffffu, kmin);
+        kmax = __reduce_max_sync(0xffffffffu, kmax);
+        auto count_below = [&](uint32_t trial) {
+          int c = 0;
+          if (in_regs) {
+#pragma unroll
+            for (int j = 0; j < kKeyRegs; ++j) c += (key[j] < trial);
+          } else {
+#pragma unroll 1
+            for (int f = lane; f < f1; f += 32) c += (__float_as_uint((float)r_e[f]) < trial);
+          }
+          return (int)__reduce_add_sync(0xffffffffu, c);
+        };
+        // ---- 90th percentile: bisection until <= 32 frames share the bin, then float64 ranking
+        uint32_t prefix = kmin;
+        unsigned long long span = 1ull;
+        int cnt_lo = 0, cnt_bin = f1;
+        {
+          const uint32_t diff = kmin ^ kmax;
+          if (diff) {
+            int b = 31 - __clz(diff);
+            prefix = kmin & ~((2u << b) - 1u);
+            while (b >= 0 && cnt_bin > 8) {
+              const uint32_t trial = prefix | (1u << b);
+              const int c = count_below(trial);
+              if (rank < c) cnt_bin = c - cnt_lo;
+              else { prefix = trial; cnt_bin = cnt_lo + cnt_bin - c; cnt_lo = c; }
+              --b;
+            }
+            span = 1ull << (b + 1);
+          }
+        }
+        bool unresolved = false;
+        if (cnt_bin > 32) { unresolved = true; cnt_bin = 32; }    // > 32 frames share one float: replay in float64
+        const int r1 = unresolved ? 0 : rank - cnt_lo;
+        // gather the candidates of the bin (ballot compaction into the warp's scratch)
+        {
+          int base = 0;
+#pragma unroll 1
+          for (int f0 = 0; f0 < f1; f0 += 32) {
+            const int f = f0 + lane;
+            bool in = false;
+            double e = 0.0;
+            if (f < f1) {
+              e = r_e[f];
+              const uint32_t k = __float_as_uint((float)e);
+              in = k >= prefix && (unsigned long long)(k - prefix) < span;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, in);
+            if (in) { const int s = base + __popc(m & ((1u << lane) - 1u)); if (s < 32) cand[s] = e; }
+            base += __popc(m);
+          }
+        }
+        __syncwarp();
+        const double mine = lane < cnt_bin ? cand[lane] : INFINITY;
+        int below = 0;
+#pragma unroll 1
+        for (int j = 0; j < cnt_bin; ++j) {
+          const double o = __shfl_sync(0xffffffffu, mine, j);
+          below += (o < mine) || (o == mine && j < lane);
+        }
+        const unsigned m1 = __ballot_sync(0xffffffffu, lane < cnt_bin && below == r1);
+        const unsigned m2 = __ballot_sync(0xffffffffu, lane < cnt_bin && below == r1 + 1);
+        const double ka = __shfl_sync(0xffffffffu, mine, __ffs(m1) - 1);
+        double kb = m2 ? __shfl_sync(0xffffffffu, mine, __ffs(m2) - 1) : ka;
+        if (!m2 && !top) {               // rank + 1 lies above the candidate bin
+          double nxt = INFINITY;
+#pragma unroll 1
+          for (int f = lane; f < f1; f += 32) {
+            const double e = r_e[f];
+            const uint32_t k = __float_as_uint((float)e);
+            if (k >= prefix && (unsigned long long)(k - prefix) >= span) nxt = fmin(nxt, e);
+          }
+          nxt = warp_min_d(nxt);
+          kb = nxt == INFINITY ? ka : nxt;
+        }
+        if (top) kb = ka;
+        __syncwarp();
+
+        // ---- noise floors and thresholds (audio_processing.py:188-217,239-247), every lane alike
+        const int nf = min(5, f1 / 10);
+        double noise_e, noise_z;
+        if (nf > 0) {
+          double ve[10], vz[10];
+#pragma unroll 1
+          for (int i = 0; i < 2 * nf; ++i) { const int f = i < nf ? i : f1 - 2 * nf + i; ve[i] = r_e[f]; vz[i] = (double)r_z[f]; }
+          noise_e = noise_mean(ve, 2 * nf);
+          noise_z = noise_mean(vz, 2 * nf);
+        } else {
+          noise_e = INFINITY; noise_z = INFINITY;
+#pragma unroll 1
+          for (int f = lane; f < f1; f += 32) { noise_e = fmin(noise_e, r_e[f]); noise_z = fmin(noise_z, (double)r_z[f]); }
+          noise_e = warp_min_d(noise_e); noise_z = warp_min_d(noise_z);
+        }
+        const double speech = np_lerp(ka, kb, v - floor(v));
+        const double t1 = speech * a.hr;
+        const double t2 = noise_e + (speech - noise_e) * a.lr;
+        const double t3 = noise_z * a.zr;
+        // Slack on the thresholds (DESIGN.md "numerics"): 2^-40 relative, the rounding of the three-term
+        // energy formula at its largest possible magnitude, and the reference's mean-rounding term
+        // |mu| * sqrt(fl * E) / m at E_max (sqrt(y) <= (y + 1) / 2), each with a >= 4x margin.
+        const double emx = (double)__uint_as_float(kmax) * 1.0000002;
+        const double dmax = (double)max(kmx_s - thr, thr - kmn_s) + 1.0;
+        const double amx = (double)fl * dmax * dmax;
+        const double eps = 1.0 / 1099511627776.0;  // 2^-40
+        const double smax = 8.881784197001252e-16 /* 2^-50 */ *
+                            (fabs(mu) * 0.5 * ((double)fl * emx + 1.0) * inv_m + amx * inv_m * inv_m);
+        const double tol1 = eps * fabs(t1) + fabs(a.hr) * smax + smax + eps * emx;
+        const double tol2 = eps * (fabs(noise_e) + fabs(a.lr) * (fabs(speech) + fabs(noise_e))) +
+                            (fabs(1.0 - a.lr) + fabs(a.lr)) * smax + smax + eps * emx;
+        int n3 = f1, n4 = -1, flag = unresolved ? 1 : 0;
+#pragma unroll 1
+        for (int f = lane; f < f1; f += 32) {
+          const double e = r_e[f];
+          if (e > t1) { n3 = min(n3, f); n4 = max(n4, f); }
+          if (fabs(e - t1) <= tol1 && !(e == 0.0 && t1 == 0.0)) flag = 1;
+          if (fabs(e - t2) <= tol2 && !(e == 0.0 && t2 == 0.0)) flag = 1;
+        }
+        n3 = __reduce_min_sync(0xffffffffu, n3);
+        n4 = __reduce_max_sync(0xffffffffu, n4);
+        flagged = __any_sync(0xffffffffu, flag);
+        if (n4 >= 0) {
+          int n2 = 0, n5 = f1 - 1;
+#pragma unroll 1
+          for (int f = lane; f < f1; f += 32)
+            if (r_e[f] <= t2) { if (f < n3) n2 = max(n2, f + 1); if (f > n4) n5 = min(n5, f - 1); }
+          n2 = __reduce_max_sync(0xffffffffu, n2);
+          n5 = __reduce_min_sync(0xffffffffu, n5);
+          int n1 = 0, n6 = f1 - 1;
+#pragma unroll 1
+          for (int f = lane; f < f1; f += 32)
+            if ((double)r_z[f] <= t3) { if (f < n2) n1 = max(n1, f + 1); if (f > n5) n6 = min(n6, f - 1); }
+          n1 = __reduce_max_sync(0xffffffffu, n1);
+          n6 = __reduce_min_sync(0xffffffffu, n6);
+          start = n1 * fs;
+          end = min(n6 * fs + fl, n);
+        }
+      }
+      __syncwarp();     // the energy array is dead from here on: it becomes the feature buffers
+      tick(1);
+
+      // =========================== windowed frame features =============================
+      const int seg = end - start;
+      const int f2 = frame_count32(seg, fl, fs);
+      const double sc_e = inv_m * inv_m, sc_m = inv_m;
+      int f2_chain = 0;      // frames [0, f2_chain) by the chain path, the rest generically
+      if (chain_cfg && (start & 127) == 0 && seg >= 256) f2_chain = (seg - 256) / 128 + 1;
+      if (f2_chain > f2) f2_chain = f2;
+      if (f2_chain > 0 && !(a.tma_chunk & 2)) {
+        // 16 lanes per chain, 2 chains; a chain covers `per` consecutive frames = per + 1 hop blocks.
+        // A sample becomes a float once: 0x4B000000 | (k ^ 0x8000) is 2^23 + 32768 + k, minus the
+        // integer 2^23 + 32768 + thr (exact), minus phi (one rounding); squares, magnitudes and the
+        // four multiply-adds per sample run as packed pairs (FADD2 / FMUL2 / FFMA2).
+        constexpr int kDepth = 4;                          // hop blocks in flight per lane
+        const int chain = lane >> 4, sub = lane & 15;
+        const int per = (f2_chain + 1) >> 1;
+        const int fa = chain * per, fb = min(fa + per, f2_chain);
+        const bool hi8 = (sub & 8) != 0;
+        const int nfr = fb - fa;                           // frames of this chain; block i feeds frames i-1 and i
+        const int4* ptr = reinterpret_cast<const int4*>(x + start + 8 * sub + fa * 128);   // block i at ptr[16 * i]
+        const float c1f = -(8388608.f + 32768.f) - (float)thr;
+        const f32x2 c1 = pk2(c1f, c1f), c2 = pk2(-phi, -phi);
+        const float scale = hi8 ? (float)sc_m : (float)sc_e;
+        float* dst = (hi8 ? s_fm : s_fe) + fa - 1;        // frame fa + i - 1 at dst[i]
+        const bool writer = (sub & 7) == 0;
+        f32x2 ce = pk2(0.f, 0.f), cm = ce;                 // first-half partials of the previous block
+        int4 q[kDepth];
+#pragma unroll
+        for (int d = 0; d < kDepth; ++d) q[d] = (d <= nfr && nfr > 0 && !(a.tma_chunk & 1)) ? __ldg(ptr + 16 * d) : make_int4(0, 0, 0, 0);
+#pragma unroll 1
+        for (int i0 = 0; i0 <= per; i0 += kDepth) {       // uniform trip count: the shuffles are warp-wide
+#pragma unroll
+          for (int d = 0; d < kDepth; ++d) {
+            const int i = i0 + d;
+            if (i <= per) {
+              const uint32_t w[4] = {(uint32_t)q[d].x, (uint32_t)q[d].y, (uint32_t)q[d].z, (uint32_t)q[d].w};
+              if (i + kDepth <= nfr && !(a.tma_chunk & 1)) q[d] = __ldg(ptr + 16 * (i + kDepth));
+              f32x2 e0 = pk2(0.f, 0.f), m0 = e0, e1 = ce, m1 = cm;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint32_t ub = w[k] ^ 0x80008000u;
+                f32x2 dd = pk2(__uint_as_float(__byte_perm(ub, 0x4b000000u, 0x7610)), __uint_as_float(__byte_perm(ub, 0x4b000000u, 0x7632)));
+                dd = add2(add2(dd, c1), c2);
+                const f32x2 sq = mul2(dd, dd);
+                const f32x2 ab = dd & 0x7fffffff7fffffffull;
+                e0 = fma2(cw2[0][k], sq, e0); m0 = fma2(cw[0][k], ab, m0);
+                e1 = fma2(cw2[1][k], sq, e1); m1 = fma2(cw[1][k], ab, m1);
+              }
+              ce = e0; cm = m0;
+              // frame fa+i-1 = first half carried from the previous block + this block as its second half:
+              // transposed reduction of (e1, m1) over the chain's 16 lanes
+              const float es = hsum2(e1), ms = hsum2(m1);
+              const float send = hi8 ? es : ms, keep = hi8 ? ms : es;
+              float vv = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              vv += __shfl_xor_sync(0xffffffffu, vv, 4);
+              vv += __shfl_xor_sync(0xffffffffu, vv, 2);
+              vv += __shfl_xor_sync(0xffffffffu, vv, 1);
+              if (writer && i >= 1 && i <= nfr) dst[i] = vv * scale;
+            }
+          }
+        }
+      }
+      if (f2_chain < f2) {
+        const int sub = lane & (kLanesPerFrame - 1);
+        const int slot = lane / kLanesPerFrame;
+        constexpr int kSlots = 32 / kLanesPerFrame;
+        const bool vec_ok = ((start & 7) == 0) && ((fs & 7) == 0);
+#pragma unroll 1
+        for (int t0 = f2_chain; t0 < f2; t0 += kSlots) {
+          const int t = t0 + slot;
+          float e = 0.f, m = 0.f;
+          if (t < f2) {
+            const int p = start + t * fs;
+            const int valid = min(fl, end - p);
+            int jdone = 0;
+            if (vec_ok) {
+              const int nv = valid >> 3;
+              const int4* xv = reinterpret_cast<const int4*>(x + p);
+              const float4* wv = reinterpret_cast<const float4*>(s_win);
+#pragma unroll 1
+              for (int vq = sub; vq < nv; vq += kLanesPerFrame) {
+                const int4 q = __ldg(xv + vq);
+                const float4 wa = wv[2 * vq], wb = wv[2 * vq + 1];
+                const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+                const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float dlo = (float)(sext16(w[k]) - thr) - phi;
+                  const float dhi = (float)(((int)w[k] >> 16) - thr) - phi;
+                  const float alo = ww[2 * k] * dlo, ahi = ww[2 * k + 1] * dhi;
+                  e = fmaf(alo, alo, e); m += fabsf(alo);
+                  e = fmaf(ahi, ahi, e); m += fabsf(ahi);
+                }
+              }
+              jdone = nv << 3;
+            }
+#pragma unroll 1
+            for (int j = jdone + sub; j < valid; j += kLanesPerFrame) {
+              const float d = (float)((int)__ldg(x + p + j) - thr) - phi;
+              const float av = s_win[j] * d;
+              e = fmaf(av, av, e); m += fabsf(av);
+            }
+          }
+#pragma unroll
+          for (int o = kLanesPerFrame / 2; o > 0; o >>= 1) {
+            e += __shfl_xor_sync(0xffffffffu, e, o);
+            m += __shfl_xor_sync(0xffffffffu, m, o);
+          }
+          if (t < f2 && sub == 0) { s_fe[t] = (float)((double)e * sc_e); s_fm[t] = (float)((double)m * sc_m); }
+        }
+      }
+      __syncwarp();
+      tick(2);
+
+      // =========================== outputs + statistics ================================
+      const int zbase = start / fs;        // start is a multiple of the hop: feature frame t is frame zbase + t
+      const int64_t fo = a.feat_offsets[u];
+#pragma unroll 1
+      for (int t = lane; t < f2; t += 32) {
+        if (a.out.energy) a.out.energy[fo + t] = s_fe[t];
+        if (a.out.magnitude) a.out.magnitude[fo + t] = s_fm[t];
+        if (a.out.zcr) a.out.zcr[fo + t] = (float)r_zf[zbase + t];
+      }
+      if (a.out.stats && f2 > 0) {
+        float* stats = a.out.stats + (int64_t)u * kStats;
+        if (f2 <= 32 * 6) tail_stats_regs<6>(s_fe, s_fm, r_zf + zbase, f2, stats);
+        else if (f2 <= 32 * 11) tail_stats_regs<11>(s_fe, s_fm, r_zf + zbase, f2, stats);
+        else {
+          float st[5];
+          warp_stats([&](int i) { return s_fe[i]; }, f2, st);
+          if (lane == 0) for (int k = 0; k < 5; ++k) stats[k] = st[k];
+          warp_stats([&](int i) { return s_fm[i]; }, f2, st);
+          if (lane == 0) for (int k = 0; k < 5; ++k) stats[5 + k] = st[k];
+          warp_stats([&](int i) { return (float)r_zf[zbase + i]; }, f2, st);
+          if (lane == 0) for (int k = 0; k < 5; ++k) stats[10 + k] = st[k];
+        }
+      }
+      if (lane == 0) {
+        int status = DSP_UTT_OK;
+        if (seg <= 0) status = DSP_UTT_EMPTY; else if (f2 == 0) status = DSP_UTT_NO_FRAMES;
+        if (a.out.start) a.out.start[u] = start;
+        if (a.out.end) a.out.end[u] = end;
+        if (a.out.n_epd_frames) a.out.n_epd_frames[u] = f1;
+        if (a.out.n_frames) a.out.n_frames[u] = f2;
+        if (a.out.status) a.out.status[u] = status;
+        if (flagged) { const int s = atomicAdd(a.flag_count, 1); a.flag_list[s] = u; }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_rempty[twid]);
+      tick(3);
+    }
+    if (a.prof && twid == 0 && lane == 0) for (int i = 0; i < 4; ++i) atomicAdd((unsigned long long*)&a.prof[8 + i], (unsigned long long)tp[i]);
+    return;
+  }
+
+  // =========================================================================================
+  // STREAM WARPS
+  // =========================================================================================
+#ifndef DSP_PIPE_TAIL_LOW
+  const int swid = wid, stid = tid;
+#else
+  const int swid = wid - kMaxTailWarps, stid = tid - 32 * kMaxTailWarps;
+#endif
+  int useq = 0, cslot = 0, clap = 0;
+  long long sp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sprev = clock64();
+  auto stick = [&](int i) { if (a.prof) { const long long t = clock64(); sp[i] += t - sprev; sprev = t; } };
+  for (;;) {
+    mbar_wait(&bar_full[cslot], (uint32_t)(clap & 1));
+    stick(0);
+    const int2 dsc = s_desc[useq & (kDescRing - 1)];
+    const int u = dsc.x;
+    if (u < 0) break;
+    const int par = useq & 1;
+    const int rec_id = useq % nrec, rec_lap = useq / nrec;
+    unsigned char* rec = smem + L.rec + (size_t)rec_id * L.rec_bytes;
+    int* r_int = reinterpret_cast<int*>(rec);
+    if (dsc.y < 0) {
+      // misaligned start: hand the utterance to the float64 replay, keep the pipeline's sequence numbers
+      if (rec_lap > 0) mbar_wait(&bar_rempty[rec_id], (uint32_t)((rec_lap - 1) & 1));
+      if (stid == 0) { const int s = atomicAdd(a.flag_count, 1); a.flag_list[s] = u; r_int[0] = u; r_int[1] = 0; r_int[2] = 0; r_int[3] = 0;
+        r_int[4] = 0; r_int[5] = 0; r_int[6] = 0; double* rd = reinterpret_cast<double*>(rec + 64); rd[0] = 0.0; rd[1] = 1.0; rd[2] = 0.0; }
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&bar_empty[cslot]); mbar_arrive(&bar_rfull[rec_id]); }
+      if (++cslot == R) { cslot = 0; ++clap; }
+      ++useq;
+      continue;
+    }
+    const int n = dsc.y;
+    const int nchunks = n > 0 ? (n + kChunkSamples - 1) / kChunkSamples : 1;
+    const int ng = (n + kGroup - 1) / kGroup;
+    unsigned long long* gsum = s_gsum + (size_t)par * a.cap_groups;
+    auto chunk_ptr = [&](int c) -> const unsigned char* {
+      int s = cslot + c; if (s >= R) s -= R;
+      return s_ring + (size_t)s * kChunkBytes;
+    };
+    auto sample_at = [&](int i) -> int {
+      return (int)reinterpret_cast<const int16_t*>(chunk_ptr(i >> 11))[i & (kChunkSamples - 1)];
+    };
+
+    // =========================== pass A: group sums, min, max =========================
+    int S = 0;
+    uint32_t mn2 = 0x7fff7fffu, mx2 = 0x80008000u;
+    int mn = 32767, mx = -32768;
+#pragma unroll 1
+    for (int c = swid; c < nchunks; c += kStreamWarps) {
+      int s = cslot + c, lp = clap; if (s >= R) { s -= R; ++lp; }
+      if (c) mbar_wait(&bar_full[s], (uint32_t)(lp & 1));
+      const int g = kGroupsPerChunk * c + lane;
+      const int base = g * kGroup;
+      if (base + kGroup <= n) {
+        const unsigned char* gp = s_ring + (size_t)s * kChunkBytes + lane * (2 * kGroup);
+        int hh = 0, hl = 0, sh = 0;
+        uint32_t ll = 0, sl = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int4 q = *reinterpret_cast<const int4*>(gp + 16 * ((j + lane) & 7));   // rotated: conflict-free
+          const uint32_t h0 = __byte_perm((uint32_t)q.x, (uint32_t)q.y, 0x7531), l0 = __byte_perm((uint32_t)q.x, (uint32_t)q.y, 0x6420);
+          const uint32_t h1 = __byte_perm((uint32_t)q.z, (uint32_t)q.w, 0x7531), l1 = __byte_perm((uint32_t)q.z, (uint32_t)q.w, 0x6420);
+          hh = dp4a_ss((int)h0, (int)h0, hh); hh = dp4a_ss((int)h1, (int)h1, hh);
+          hl = dp4a_su((int)h0, l0, hl);      hl = dp4a_su((int)h1, l1, hl);
+          ll = dp4a_uu(l0, l0, ll);           ll = dp4a_uu(l1, l1, ll);
+          sh = dp4a_ss((int)h0, 0x01010101, sh); sh = dp4a_ss((int)h1, 0x01010101, sh);
+          sl = dp4a_uu(l0, 0x01010101u, sl);  sl = dp4a_uu(l1, 0x01010101u, sl);
+          mn2 = __vimin3_s16x2(mn2, (uint32_t)q.x, (uint32_t)q.y); mn2 = __vimin3_s16x2(mn2, (uint32_t)q.z, (uint32_t)q.w);
+          mx2 = __vimax3_s16x2(mx2, (uint32_t)q.x, (uint32_t)q.y); mx2 = __vimax3_s16x2(mx2, (uint32_t)q.z, (uint32_t)q.w);
+        }
+        const int s1 = 256 * sh + (int)sl;
+        const long long s2 = (long long)hh * 65536 + (long long)hl * 512 + (long long)ll;
+        S += s1;
+        gsum[g] = ((unsigned long long)s2 << 24) | (unsigned long long)((uint32_t)s1 & 0xffffffu);
+      } else if (base < n) {
+        int s1 = 0; long long s2 = 0;
+#pragma unroll 1
+        for (int i = base; i < n; ++i) { const int k = sample_at(i); s1 += k; s2 += (long long)k * k; mn = min(mn, k); mx = max(mx, k); }
+        S += s1;
+        gsum[g] = ((unsigned long long)s2 << 24) | (unsigned long long)((uint32_t)s1 & 0xffffffu);
+      }
+    }
+    mn = min(mn, min(sext16(mn2), (int)mn2 >> 16));
+    mx = max(mx, max(sext16(mx2), (int)mx2 >> 16));
+    S = __reduce_add_sync(0xffffffffu, S);
+    mn = __reduce_min_sync(0xffffffffu, mn);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0) s_part[par * kStreamWarps + swid] = make_int4(S, mn, mx, 0);
+    stick(1);
+    bar_sync(kBarStream, kStreamThreads);
+    stick(2);
+    {
+      const int4 pp = lane < kStreamWarps ? s_part[par * kStreamWarps + lane] : make_int4(0, 32767, -32768, 0);
+      S = __reduce_add_sync(0xffffffffu, pp.x);
+      mn = __reduce_min_sync(0xffffffffu, pp.y);
+      mx = __reduce_max_sync(0xffffffffu, pp.z);
+    }
+    const int N = n > 0 ? n : 1;
+    int thr;
+    { int q = S / N; if ((S % N) != 0 && S < 0) --q; thr = q + 1; }                    // floor(S/N) + 1
+    if (stid == kStreamThreads - 1) {
+      // float64 constants of the utterance (needed from pass F on; published by the next barrier)
+      const long long Rm = (long long)S - (long long)N * thr;                          // in [-N, 0)
+      const long long M = max((long long)N * mx - S, (long long)S - (long long)N * mn);
+      double* cst = s_consts + par * 8;
+      cst[0] = (double)Rm / (double)N;
+      cst[1] = (M > 0) ? (double)N / (double)M : 1.0;
+      cst[2] = (double)S / (double)N;
+    }
+
+    // =========================== pass B: sign bits ====================================
+#pragma unroll 1
+    for (int c = swid; c < nchunks; c += kStreamWarps) {
+      int s = cslot + c; if (s >= R) s -= R;
+      const int g = kGroupsPerChunk * c + lane;
+      const int base = g * kGroup;
+      uint32_t b0 = 0, b1 = 0;
+      if (base + kGroup <= n) {
+        const unsigned char* gp = s_ring + (size_t)s * kChunkBytes + lane * (2 * kGroup);
+        const int rot = lane & 7;
+        uint32_t nlo = 0, nhi = 0;         // "below the mean" bits, MSB-first, in processing order
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int4 qa = *reinterpret_cast<const int4*>(gp + 16 * ((j + rot) & 7));
+          const int4 qb = *reinterpret_cast<const int4*>(gp + 16 * ((j + 4 + rot) & 7));
+          const uint32_t wa[4] = {(uint32_t)qa.x, (uint32_t)qa.y, (uint32_t)qa.z, (uint32_t)qa.w};
+          const uint32_t wb[4] = {(uint32_t)qb.x, (uint32_t)qb.y, (uint32_t)qb.z, (uint32_t)qb.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int alo = sext16(wa[k]) - thr, ahi = ((int)wa[k] >> 16) - thr;
+            const int blo = sext16(wb[k]) - thr, bhi = ((int)wb[k] >> 16) - thr;
+            nhi = __funnelshift_l((uint32_t)alo, nhi, 1); nhi = __funnelshift_l((uint32_t)ahi, nhi, 1);
+            nlo = __funnelshift_l((uint32_t)blo, nlo, 1); nlo = __funnelshift_l((uint32_t)bhi, nlo, 1);
+          }
+        }
+        // stream (nhi:nlo) holds vector `rot` first (at the top); reverse to LSB-first, undo the rotation
+        const unsigned long long y = ((unsigned long long)__brev(nlo) << 32) | (unsigned long long)__brev(nhi);
+        const int sh = 8 * rot;
+        const unsigned long long z = sh ? ((y << sh) | (y >> (64 - sh))) : y;
+        b0 = ~(uint32_t)z; b1 = ~(uint32_t)(z >> 32);
+      } else if (base < n) {
+#pragma unroll 1
+        for (int i = 0; i < kGroup && base + i < n; ++i) {
+          const uint32_t bit = (sample_at(base + i) - thr >= 0);
+          if (i < 32) b0 |= bit << i; else b1 |= bit << (i - 32);
+        }
+      }
+      if (base < n) {
+        s_bits[2 * g] = b0; s_bits[2 * g + 1] = b1;
+        const uint32_t x0 = b0 ^ __funnelshift_r(b0, b1, 1), x1 = (b1 ^ (b1 >> 1)) & 0x7fffffffu;
+        s_meta[g] = (uint32_t)(__popc(x0) + __popc(x1)) | ((b0 & 3u) << 8) | ((b1 >> 30) << 10);
+      }
+    }
+    if (stid < 4) s_bits[2 * ng + stid] = 0;
+    auto release_slots = [&]() {
+      __syncwarp();
+      for (int c = lane; c < nchunks; c += 32) { int s = cslot + c; if (s >= R) s -= R; mbar_arrive(&bar_empty[s]); }
+    };
+    if (!edges) release_slots();
+    stick(3);
+    bar_sync(kBarStream, kStreamThreads);
+    stick(4);
+
+    // =========================== pass F: EPD frames -> record =========================
+    if (rec_lap > 0) mbar_wait(&bar_rempty[rec_id], (uint32_t)((rec_lap - 1) & 1));
+    stick(5);
+    {
+      const double phi_d = s_consts[par * 8 + 0], inv_m = s_consts[par * 8 + 1];
+      double* r_e = reinterpret_cast<double*>(rec + L.rec_e);
+      unsigned short* r_z = reinterpret_cast<unsigned short*>(rec + L.rec_z);
+      unsigned short* r_zf = reinterpret_cast<unsigned short*>(rec + L.rec_zf);
+      int f1 = 0;
+      if (a.do_epd && n >= fl) f1 = (n - fl) / fs + 1;
+      const int f2full = frame_count32(n, fl, fs);
+      const int64_t eo = (a.out.epd_energy || a.out.epd_zcr) ? a.epd_offsets[u] : 0;
+      const long long thr2 = (long long)thr * thr;
+      const int fmax = max(f1, f2full);
+#pragma unroll 1
+      for (int f = stid; f < fmax; f += kStreamThreads) {
+        const int p = f * fs;
+        int zc = 0;
+        uint32_t m_first = 0, m_last = 0;
+        if (f < f1) {
+          const int q = p + fl;
+          long long s1, s2;
+          if (!edges) {
+            // whole groups only: sum k, sum k^2, crossings from the per-group records
+            const int g0 = p / kGroup, gpf = fl / kGroup;
+            int k1 = 0; long long k2 = 0;
+            uint32_t prev = 0;
+#pragma unroll 2
+            for (int j = 0; j < gpf; ++j) {
+              const unsigned long long pk = gsum[g0 + j];
+              const uint32_t m = s_meta[g0 + j];
+              k2 += (long long)(pk >> 24);
+              k1 += ((int)((uint32_t)pk << 8)) >> 8;
+              zc += (int)(m & 0x7fu) + (int)(((m >> 8) ^ prev) & (j ? 1u : 0u));
+              prev = m >> 11;
+              if (j == 0) m_first = m;
+              m_last = m;
+            }
+            s1 = (long long)(k1 - fl * thr);
+            s2 = k2 - 2ll * thr * (long long)k1 + (long long)fl * thr2;
+          } else {
+            long long k1 = 0, k2 = 0;           // sum k, sum k^2 over the frame
+            const int ga = (p + kGroup - 1) / kGroup, gb = q / kGroup;
+            auto direct = [&](int i0, int i1) {
+#pragma unroll 1
+              for (int i = i0; i < i1; ++i) { const int k = sample_at(i); k1 += k; k2 += (long long)k * k; }
+            };
+            if (ga > gb) direct(p, q);
+            else {
+              for (int g = ga; g < gb; ++g) {
+                const unsigned long long pk = gsum[g];
+                k2 += (long long)(pk >> 24);
+                k1 += (long long)(((int)((uint32_t)pk << 8)) >> 8);
+              }
+              direct(p, ga * kGroup);
+              direct(gb * kGroup, q);
+            }
+            s1 = k1 - (long long)fl * thr;
+            s2 = k2 - 2ll * thr * k1 + (long long)fl * thr2;
+            zc = count_changes(s_bits, p, q);
+          }
+          // exact integer sums of d = k - thr, then sum (d - phi)^2 in three roundings
+          const double t1 = 2.0 * phi_d * (double)s1, t2 = (double)fl * phi_d * phi_d;
+          const double ep = ((double)s2 - t1) + t2;
+          const double e = ep * inv_m * inv_m;
+          r_e[f] = e;
+          r_z[f] = (unsigned short)zc;
+          if (a.out.epd_energy) a.out.epd_energy[eo + f] = e;
+          if (a.out.epd_zcr) a.out.epd_zcr[eo + f] = (float)zc;
+        }
+        if (f < f2full) {
+          const int valid = min(fl, n - p);
+          int zf;
+          if (f < f1 && !(hann && fl <= 2)) {
+            zf = zc;
+            if (hann) {
+              int s0, s1b, sp, sl;
+              if (!edges) { s0 = (m_first >> 8) & 1; s1b = (m_first >> 9) & 1; sp = (m_last >> 10) & 1; sl = (m_last >> 11) & 1; }
+              else { s0 = bit_at(s_bits, p); s1b = bit_at(s_bits, p + 1); sl = bit_at(s_bits, p + fl - 1); sp = bit_at(s_bits, p + fl - 2); }
+              zf += (s1b - (s0 ^ s1b)) + (sp - (sp ^ sl));
+            }
+          } else {
+            zf = frame_zcr(s_bits, p, valid, fl, hann);
+          }
+          r_zf[f] = (unsigned short)zf;
+        }
+      }
+      if (stid == kStreamThreads - 1) {
+        r_int[0] = u; r_int[1] = n; r_int[2] = f1; r_int[3] = f2full; r_int[4] = thr; r_int[5] = mn; r_int[6] = mx;
+        double* rd = reinterpret_cast<double*>(rec + 64);
+        rd[0] = phi_d; rd[1] = inv_m; rd[2] = s_consts[par * 8 + 2];
+      }
+    }
+    if (edges) release_slots();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar_rfull[rec_id]);
+    cslot += nchunks; if (cslot >= R) { cslot -= R; ++clap; }
+    ++useq;
+    stick(6);
+  }
+  if (a.prof && stid == 0) { for (int i = 0; i < 7; ++i) atomicAdd((unsigned long long*)&a.prof[i], (unsigned long long)sp[i]); atomicAdd((unsigned long long*)&a.prof[15], (unsigned long long)useq); }
+  // tell the tail warps to stop: one terminator record each
+#pragma unroll 1
+  for (int k = 0; k < nrec; ++k, ++useq) {
+    const int rec_id = useq % nrec, rec_lap = useq / nrec;
+    if (rec_lap > 0) mbar_wait(&bar_rempty[rec_id], (uint32_t)((rec_lap - 1) & 1));
+    if (stid == 0) *reinterpret_cast<int*>(smem + L.rec + (size_t)rec_id * L.rec_bytes) = -1;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar_rfull[rec_id]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Host side: capacity planning.  Returns false when the configuration does not fit this kernel
+// (the caller falls back to frontend_pcm_kernel).
+// ---------------------------------------------------------------------------------------
+bool pipe_kernel_plan(int64_t max_len, int cap_frames, int fl, size_t smem_limit, PipePlan* plan) {
+  if (max_len > 65535 || cap_frames > 65535 || fl > 65535) return false;      // 16-bit crossing counts, int32 sums
+  const int chunks = (int)std::max<int64_t>((max_len + kChunkSamples - 1) / kChunkSamples, 1);
+  const int capG = chunks * kGroupsPerChunk;
+  for (int nrec = kMaxTailWarps; nrec >= 2; --nrec) {
+    const PipeLayout fixed = make_pipe_layout(0, capG, cap_frames, fl, nrec);
+    const long long room = (long long)smem_limit - fixed.total - 1024;        // static shared memory + slack
+    int R = (int)(room / (kChunkBytes + 16));
+    if (R > kMaxRingSlots) R = kMaxRingSlots;
+    // two utterances in flight if possible; give up tail warps for ring slots otherwise
+    const bool roomy = R >= 2 * chunks;
+    if (R >= chunks + 1 && (roomy || nrec == 2)) {
+      plan->ring_slots = R; plan->n_rec = nrec; plan->cap_groups = capG;
+      plan->smem = (size_t)make_pipe_layout(R, capG, cap_frames, fl, nrec).total;
+      return true;
+    }
+  }
+  return false;
+}
+
+cudaError_t launch_frontend_pipe(const PcmArgs& a, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(frontend_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  frontend_pipe_kernel<<<grid, kPipeThreads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace dsp

@@ -57,6 +57,7 @@ struct PcmArgs {
   int tma_chunk;                // bytes per bulk copy (multiple of 16)
   int stagger_ns;               // start-up delay per co-resident CTA index (0 = none)
   int sm_count;
+  int ring_slots, n_rec, cap_groups;   // frontend_pipe_kernel: shared-memory plan (pipe_kernel_plan)
   long long* prof;              // debug: per-phase cycle counters (NULL normally)
   unsigned int* work_counter;   // dynamic utterance scheduler
   int32_t* flag_list;           // utterances that need the float64 replay
@@ -75,6 +76,10 @@ size_t pcm_kernel_smem_bytes(int cap_samples, int cap_frames, int fl, bool resid
 cudaError_t launch_frontend_pcm(int variant, const PcmArgs& a, int grid, size_t smem, cudaStream_t st);
 int pcm_kernel_max_ctas_per_sm(int variant, size_t smem);
 int pcm_num_variants();
+// frontend_pipe.cu
+struct PipePlan { int ring_slots, n_rec, cap_groups; size_t smem; };
+bool pipe_kernel_plan(int64_t max_len, int cap_frames, int fl, size_t smem_limit, PipePlan* plan);
+cudaError_t launch_frontend_pipe(const PcmArgs& a, int grid, size_t smem, cudaStream_t st);
 bool pcm_variant_streams(int variant);
 const char* pcm_variant_name(int variant);
 #ifndef DSP_PCM_THREADS

@@ -58,10 +58,10 @@ def check_against_golden(g, res, names, ci, win, rtol_feat):
                            {"energy": g[base + "/energy"], "magnitude": g[base + "/magnitude"], "zcr": g[base + "/zcr"]})
 
 
-RESIDENT, STREAM = 0, 2      # builds of the fused kernel (frontend_pcm.cu kVariants)
+RESIDENT, STREAM, PIPE = 0, 2, 10      # builds of the fused kernel (frontend_pcm.cu kVariants); 10 = frontend_pipe.cu
 
 
-@pytest.mark.parametrize("variant", [RESIDENT, STREAM])
+@pytest.mark.parametrize("variant", [RESIDENT, STREAM, PIPE])
 @pytest.mark.parametrize("ci", range(7))
 @pytest.mark.parametrize("win", ["rectangular", "hamming", "hanning"])
 def test_fast_kernel_matches_reference_fixtures(ctx, golden_fe, ci, win, variant):
@@ -74,7 +74,7 @@ def test_fast_kernel_matches_reference_fixtures(ctx, golden_fe, ci, win, variant
     utts = [golden_pcm(g, n) for n in names]
     ctx.set_tuning("pcm_variant", variant)
     try:
-        if variant == STREAM:
+        if variant in (STREAM, PIPE):
             samples, off, lengths = batch.pack_aligned(utts)          # 16-byte aligned starts + explicit lengths
             res = batch.frontend_batch(samples, off, fl, fs, win, emit_epd_lists=True, lengths=lengths, ctx=ctx)
             # the streaming kernel really ran: nothing except certified-margin flags was replayed
@@ -191,11 +191,13 @@ def test_padded_layout_with_explicit_lengths_equals_packed(ctx):
         for name in ("start", "end", "n_frames", "n_epd_frames"):
             assert np.array_equal(getattr(ra, name), getattr(rb, name)), name
         assert np.array_equal(ra.status & 0xff, rb.status & 0xff)
+        # the packed layout runs the shared-memory-resident build, the aligned one the pipelined kernel:
+        # integer outputs and float64 replay results are identical, fp32 sums may differ in the last bits
         for i in range(len(utts)):
-            for x, y in zip(ra.frames(i), rb.frames(i)):
-                assert np.array_equal(x, y)
-            for x, y in zip(ra.epd_lists(i), rb.epd_lists(i)):
-                assert np.array_equal(x, y)
+            for k, (x, y) in enumerate(zip(ra.frames(i), rb.frames(i))):
+                assert np.array_equal(x, y) if (exact or k == 2) else np.allclose(x, y, rtol=2e-6, atol=0)
+            for k, (x, y) in enumerate(zip(ra.epd_lists(i), rb.epd_lists(i))):
+                assert np.array_equal(x, y) if (exact or k == 1) else np.allclose(x, y, rtol=1e-13, atol=0)
     with pytest.raises(ValueError):
         batch.frontend_batch(b_s, b_o, 256, 128, lengths=b_l + 9, ctx=ctx)     # length exceeds its slot
 
