@@ -49,7 +49,7 @@ constexpr int kBarStream = 1;              // named barrier of the stream warps
 
 struct PipeLayout {
   int ring, gsum, bits, meta, rec, scratch, win, desc, part, consts, bars, total;
-  int rec_bytes, rec_e, rec_z, rec_zf;
+  int rec_bytes, rec_e, rec_fe, rec_fm, rec_z, rec_zf;
 };
 
 __host__ __device__ inline int al16(int x) { return (x + 15) & ~15; }
@@ -63,7 +63,9 @@ __host__ __device__ inline PipeLayout make_pipe_layout(int R, int capG, int capF
   L.bits = o;    o += al16(8 * capG + 16);
   L.meta = o;    o += al16(4 * capG);
   L.rec_e = kRecHdr;
-  L.rec_z = L.rec_e + al16(8 * capF);
+  L.rec_fe = L.rec_e + al16(8 * capF);
+  L.rec_fm = L.rec_fe + al16(4 * capF);
+  L.rec_z = L.rec_fm + al16(4 * capF);
   L.rec_zf = L.rec_z + al16(2 * capF);
   L.rec_bytes = L.rec_zf + al16(2 * capF);
   L.rec = o;     o += nrec * L.rec_bytes;
@@ -338,6 +340,9 @@ __device__ __noinline__ void tail_stats_regs(const float* fe, const float* fm, c
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
+// kChain: frame 256 / shift 128 -- the stream warps also produce the windowed energy / magnitude of
+// EVERY full frame while the samples are in shared memory (pass BW), the tail only selects.
+template <bool kChain>
 __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const PcmArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int R = a.ring_slots, nrec = a.n_rec;
@@ -430,24 +435,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
     double* r_dbl = reinterpret_cast<double*>(rec + 64);
     double* r_e = reinterpret_cast<double*>(rec + L.rec_e);
     const unsigned short* r_z = reinterpret_cast<const unsigned short*>(rec + L.rec_z);
-    const unsigned short* r_zf = reinterpret_cast<const unsigned short*>(rec + L.rec_zf);
-    float* s_fe = reinterpret_cast<float*>(r_e);            // feature sequences reuse the energy array
-    float* s_fm = s_fe + a.cap_frames;
+    unsigned short* r_zf = reinterpret_cast<unsigned short*>(rec + L.rec_zf);
+    float* s_fe = reinterpret_cast<float*>(rec + L.rec_fe);   // indexed by full-utterance frame number
+    float* s_fm = reinterpret_cast<float*>(rec + L.rec_fm);
     double* cand = reinterpret_cast<double*>(smem + L.scratch + (size_t)twid * 256);
-
-    // window coefficients of the hop-128 / length-256 chain: a lane owns samples 8*(lane&15) .. +8 of
-    // every hop block; c = 0 is the first half of a frame, c = 1 the second
-    const bool chain_cfg = (fs == 128 && fl == 256);
-    f32x2 cw[2][4], cw2[2][4];         // (w, w) and (w^2, w^2) pairs of the lane's 8 samples
-    if (chain_cfg) {
-#pragma unroll
-      for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float w0 = s_win[c * 128 + 8 * (lane & 15) + 2 * k], w1 = s_win[c * 128 + 8 * (lane & 15) + 2 * k + 1];
-          cw[c][k] = pk2(w0, w1); cw2[c][k] = pk2(w0 * w0, w1 * w1);
-        }
-    }
 
     long long tp[5] = {0, 0, 0, 0, 0}, tprev = clock64();
     auto tick = [&](int i) { if (a.prof) { const long long t = clock64(); tp[i] += t - tprev; tprev = t; } };
@@ -627,63 +618,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       const int seg = end - start;
       const int f2 = frame_count32(seg, fl, fs);
       const double sc_e = inv_m * inv_m, sc_m = inv_m;
-      int f2_chain = 0;      // frames [0, f2_chain) by the chain path, the rest generically
-      if (chain_cfg && (start & 127) == 0 && seg >= 256) f2_chain = (seg - 256) / 128 + 1;
-      if (f2_chain > f2) f2_chain = f2;
-      if (f2_chain > 0 && !(a.tma_chunk & 2)) {
-        // 16 lanes per chain, 2 chains; a chain covers `per` consecutive frames = per + 1 hop blocks.
-        // A sample becomes a float once: 0x4B000000 | (k ^ 0x8000) is 2^23 + 32768 + k, minus the
-        // integer 2^23 + 32768 + thr (exact), minus phi (one rounding); squares, magnitudes and the
-        // four multiply-adds per sample run as packed pairs (FADD2 / FMUL2 / FFMA2).
-        constexpr int kDepth = 4;                          // hop blocks in flight per lane
-        const int chain = lane >> 4, sub = lane & 15;
-        const int per = (f2_chain + 1) >> 1;
-        const int fa = chain * per, fb = min(fa + per, f2_chain);
-        const bool hi8 = (sub & 8) != 0;
-        const int nfr = fb - fa;                           // frames of this chain; block i feeds frames i-1 and i
-        const int4* ptr = reinterpret_cast<const int4*>(x + start + 8 * sub + fa * 128);   // block i at ptr[16 * i]
-        const float c1f = -(8388608.f + 32768.f) - (float)thr;
-        const f32x2 c1 = pk2(c1f, c1f), c2 = pk2(-phi, -phi);
-        const float scale = hi8 ? (float)sc_m : (float)sc_e;
-        float* dst = (hi8 ? s_fm : s_fe) + fa - 1;        // frame fa + i - 1 at dst[i]
-        const bool writer = (sub & 7) == 0;
-        f32x2 ce = pk2(0.f, 0.f), cm = ce;                 // first-half partials of the previous block
-        int4 q[kDepth];
-#pragma unroll
-        for (int d = 0; d < kDepth; ++d) q[d] = (d <= nfr && nfr > 0 && !(a.tma_chunk & 1)) ? __ldg(ptr + 16 * d) : make_int4(0, 0, 0, 0);
-#pragma unroll 1
-        for (int i0 = 0; i0 <= per; i0 += kDepth) {       // uniform trip count: the shuffles are warp-wide
-#pragma unroll
-          for (int d = 0; d < kDepth; ++d) {
-            const int i = i0 + d;
-            if (i <= per) {
-              const uint32_t w[4] = {(uint32_t)q[d].x, (uint32_t)q[d].y, (uint32_t)q[d].z, (uint32_t)q[d].w};
-              if (i + kDepth <= nfr && !(a.tma_chunk & 1)) q[d] = __ldg(ptr + 16 * (i + kDepth));
-              f32x2 e0 = pk2(0.f, 0.f), m0 = e0, e1 = ce, m1 = cm;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint32_t ub = w[k] ^ 0x80008000u;
-                f32x2 dd = pk2(__uint_as_float(__byte_perm(ub, 0x4b000000u, 0x7610)), __uint_as_float(__byte_perm(ub, 0x4b000000u, 0x7632)));
-                dd = add2(add2(dd, c1), c2);
-                const f32x2 sq = mul2(dd, dd);
-                const f32x2 ab = dd & 0x7fffffff7fffffffull;
-                e0 = fma2(cw2[0][k], sq, e0); m0 = fma2(cw[0][k], ab, m0);
-                e1 = fma2(cw2[1][k], sq, e1); m1 = fma2(cw[1][k], ab, m1);
-              }
-              ce = e0; cm = m0;
-              // frame fa+i-1 = first half carried from the previous block + this block as its second half:
-              // transposed reduction of (e1, m1) over the chain's 16 lanes
-              const float es = hsum2(e1), ms = hsum2(m1);
-              const float send = hi8 ? es : ms, keep = hi8 ? ms : es;
-              float vv = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-              vv += __shfl_xor_sync(0xffffffffu, vv, 4);
-              vv += __shfl_xor_sync(0xffffffffu, vv, 2);
-              vv += __shfl_xor_sync(0xffffffffu, vv, 1);
-              if (writer && i >= 1 && i <= nfr) dst[i] = vv * scale;
-            }
-          }
-        }
-      }
+      const int zbase = start / fs;        // start is a multiple of the hop: feature frame t is frame zbase + t
+      // frames [0, f2_pre) are already in the record (pass BW of the stream warps); the rest -- zero-padded
+      // frames, or every frame when the stream warps do no window pass -- are computed here from L2
+      int f2_chain = 0;
+      if (kChain) { const int nfull = n >= fl ? (n - fl) / fs + 1 : 0; f2_chain = max(0, min(f2, nfull - zbase)); }
       if (f2_chain < f2) {
         const int sub = lane & (kLanesPerFrame - 1);
         const int slot = lane / kLanesPerFrame;
@@ -730,30 +669,44 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
             e += __shfl_xor_sync(0xffffffffu, e, o);
             m += __shfl_xor_sync(0xffffffffu, m, o);
           }
-          if (t < f2 && sub == 0) { s_fe[t] = (float)((double)e * sc_e); s_fm[t] = (float)((double)m * sc_m); }
+          if (t < f2 && sub == 0) { s_fe[zbase + t] = (float)((double)e * sc_e); s_fm[zbase + t] = (float)((double)m * sc_m); }
+          if (kChain) {
+            // crossing count of the (zero-padded) frame straight from the samples: sign of window * (x - mean),
+            // zero counts as negative (audio_processing.py:119-132)
+            int zc = 0;
+            if (t < f2) {
+              const int p = start + t * fs;
+              const int valid = min(fl, end - p);
+              auto pos = [&](int j) { return j < valid && s_win[j] > 0.f && ((int)__ldg(x + p + j) - thr) >= 0; };
+#pragma unroll 1
+              for (int j = sub; j < min(valid, fl - 1); j += kLanesPerFrame) zc += (pos(j) != pos(j + 1));
+            }
+#pragma unroll
+            for (int o = kLanesPerFrame / 2; o > 0; o >>= 1) zc += __shfl_xor_sync(0xffffffffu, zc, o);
+            if (t < f2 && sub == 0) r_zf[zbase + t] = (unsigned short)zc;
+          }
         }
       }
       __syncwarp();
       tick(2);
 
       // =========================== outputs + statistics ================================
-      const int zbase = start / fs;        // start is a multiple of the hop: feature frame t is frame zbase + t
       const int64_t fo = a.feat_offsets[u];
 #pragma unroll 1
       for (int t = lane; t < f2; t += 32) {
-        if (a.out.energy) a.out.energy[fo + t] = s_fe[t];
-        if (a.out.magnitude) a.out.magnitude[fo + t] = s_fm[t];
+        if (a.out.energy) a.out.energy[fo + t] = s_fe[zbase + t];
+        if (a.out.magnitude) a.out.magnitude[fo + t] = s_fm[zbase + t];
         if (a.out.zcr) a.out.zcr[fo + t] = (float)r_zf[zbase + t];
       }
       if (a.out.stats && f2 > 0) {
         float* stats = a.out.stats + (int64_t)u * kStats;
-        if (f2 <= 32 * 6) tail_stats_regs<6>(s_fe, s_fm, r_zf + zbase, f2, stats);
-        else if (f2 <= 32 * 11) tail_stats_regs<11>(s_fe, s_fm, r_zf + zbase, f2, stats);
+        if (f2 <= 32 * 6) tail_stats_regs<6>(s_fe + zbase, s_fm + zbase, r_zf + zbase, f2, stats);
+        else if (f2 <= 32 * 11) tail_stats_regs<11>(s_fe + zbase, s_fm + zbase, r_zf + zbase, f2, stats);
         else {
           float st[5];
-          warp_stats([&](int i) { return s_fe[i]; }, f2, st);
+          warp_stats([&](int i) { return s_fe[zbase + i]; }, f2, st);
           if (lane == 0) for (int k = 0; k < 5; ++k) stats[k] = st[k];
-          warp_stats([&](int i) { return s_fm[i]; }, f2, st);
+          warp_stats([&](int i) { return s_fm[zbase + i]; }, f2, st);
           if (lane == 0) for (int k = 0; k < 5; ++k) stats[5 + k] = st[k];
           warp_stats([&](int i) { return (float)r_zf[zbase + i]; }, f2, st);
           if (lane == 0) for (int k = 0; k < 5; ++k) stats[10 + k] = st[k];
@@ -785,6 +738,18 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
 #else
   const int swid = wid - kMaxTailWarps, stid = tid - 32 * kMaxTailWarps;
 #endif
+  // pass BW (kChain): a lane owns samples 8*(lane&15) .. +8 of every hop block; c = 0 is the first half
+  // of a frame, c = 1 the second; (w, w) and (w^2, w^2) pairs stay in registers
+  f32x2 cw[2][4], cw2[2][4];
+  if constexpr (kChain) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float w0 = s_win[c * 128 + 8 * (lane & 15) + 2 * k], w1 = s_win[c * 128 + 8 * (lane & 15) + 2 * k + 1];
+        cw[c][k] = pk2(w0, w1); cw2[c][k] = pk2(w0 * w0, w1 * w1);
+      }
+  }
   int useq = 0, cslot = 0, clap = 0;
   long long sp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sprev = clock64();
   auto stick = [&](int i) { if (a.prof) { const long long t = clock64(); sp[i] += t - sprev; sprev = t; } };
@@ -888,6 +853,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       cst[2] = (double)S / (double)N;
     }
 
+    if constexpr (!kChain) {
     // =========================== pass B: sign bits ====================================
 #pragma unroll 1
     for (int c = swid; c < nchunks; c += kStreamWarps) {
@@ -932,6 +898,69 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       }
     }
     if (stid < 4) s_bits[2 * ng + stid] = 0;
+    } else {
+    // =========================== pass BW: sign bits + windowed sums of every full frame ==========
+    // 16 chains of 16 lanes walk the hop blocks; a sample becomes a float once: 0x4B000000 | (k ^ 0x8000)
+    // is 2^23 + 32768 + k, minus the integer 2^23 + 32768 + thr (exact; its sign IS the sign bit),
+    // minus phi (one rounding); squares, magnitudes and the four multiply-adds per sample run as packed
+    // pairs (FADD2 / FMUL2 / FFMA2).  Block b is the second half of frame b-1 and the first of frame b.
+    if (rec_lap > 0) mbar_wait(&bar_rempty[rec_id], (uint32_t)((rec_lap - 1) & 1));   // raw sums go to the record
+    stick(5);
+    {
+      const int nfull = n >= 256 ? (n - 256) / 128 + 1 : 0;
+      if (nfull > 0) {
+        const int chain = stid >> 4, sub = lane & 15;
+        const int per = (nfull + 15) >> 4;
+        const int fa = chain * per;
+        const int nfr = min(per, nfull - fa);              // frames of this chain (<= 0: idle)
+        const bool hi8 = (sub & 8) != 0, writer = (sub & 7) == 0;
+        const float phi = __fdiv_rn((float)((long long)S - (long long)N * thr), (float)N);
+        const float c1f = -(8388608.f + 32768.f) - (float)thr;
+        const f32x2 c1 = pk2(c1f, c1f), c2 = pk2(-phi, -phi);
+        float* dst = reinterpret_cast<float*>(rec + (hi8 ? L.rec_fm : L.rec_fe)) + fa - 1;   // frame fa + i - 1 at dst[i]
+        unsigned char* bitbytes = reinterpret_cast<unsigned char*>(s_bits);
+        auto load_blk = [&](int b, bool first) -> int4 {
+          int sl = cslot + (b >> 4), lp = clap; if (sl >= R) { sl -= R; ++lp; }
+          if (first || (b & 15) == 0) mbar_wait(&bar_full[sl], (uint32_t)(lp & 1));   // already complete: acquire only
+          return *reinterpret_cast<const int4*>(s_ring + (size_t)sl * kChunkBytes + (b & 15) * 256 + sub * 16);
+        };
+        f32x2 ce = pk2(0.f, 0.f), cm = ce;                 // first-half partials of the previous block
+        int4 qn = make_int4(0, 0, 0, 0);
+        if (nfr > 0) qn = load_blk(fa, true);
+#pragma unroll 1
+        for (int i = 0; i <= per; ++i) {                   // uniform trip count: the shuffles are warp-wide
+          const int b = fa + i;
+          const bool act = nfr > 0 && i <= nfr;
+          const uint32_t w[4] = {(uint32_t)qn.x, (uint32_t)qn.y, (uint32_t)qn.z, (uint32_t)qn.w};
+          if (nfr > 0 && i + 1 <= nfr) qn = load_blk(b + 1, false);
+          f32x2 e0 = pk2(0.f, 0.f), m0 = e0, e1 = ce, m1 = cm;
+          uint32_t sg = 0;                                 // "below the mean" bits, first sample at the top
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t ub = w[k] ^ 0x80008000u;
+            const f32x2 tt = add2(pk2(__uint_as_float(__byte_perm(ub, 0x4b000000u, 0x7610)), __uint_as_float(__byte_perm(ub, 0x4b000000u, 0x7632))), c1);
+            sg = __funnelshift_l((uint32_t)tt, sg, 1);
+            sg = __funnelshift_l((uint32_t)(tt >> 32), sg, 1);
+            const f32x2 dd = add2(tt, c2);
+            const f32x2 sq = mul2(dd, dd);
+            const f32x2 ab = dd & 0x7fffffff7fffffffull;
+            e0 = fma2(cw2[0][k], sq, e0); m0 = fma2(cw[0][k], ab, m0);
+            e1 = fma2(cw2[1][k], sq, e1); m1 = fma2(cw[1][k], ab, m1);
+          }
+          ce = e0; cm = m0;
+          if (act && (i < nfr || b == nfull)) bitbytes[16 * b + sub] = (unsigned char)(~(__brev(sg) >> 24));
+          // transposed reduction of (e1, m1) over the chain's 16 lanes
+          const float es = hsum2(e1), ms = hsum2(m1);
+          const float send = hi8 ? es : ms, keep = hi8 ? ms : es;
+          float vv = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          vv += __shfl_xor_sync(0xffffffffu, vv, 4);
+          vv += __shfl_xor_sync(0xffffffffu, vv, 2);
+          vv += __shfl_xor_sync(0xffffffffu, vv, 1);
+          if (writer && act && i >= 1) dst[i] = vv;        // raw sums: pass F applies the peak normalisation
+        }
+      }
+    }
+    }
     auto release_slots = [&]() {
       __syncwarp();
       for (int c = lane; c < nchunks; c += 32) { int s = cslot + c; if (s >= R) s -= R; mbar_arrive(&bar_empty[s]); }
@@ -942,8 +971,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
     stick(4);
 
     // =========================== pass F: EPD frames -> record =========================
-    if (rec_lap > 0) mbar_wait(&bar_rempty[rec_id], (uint32_t)((rec_lap - 1) & 1));
-    stick(5);
+    if constexpr (!kChain) {
+      if (rec_lap > 0) mbar_wait(&bar_rempty[rec_id], (uint32_t)((rec_lap - 1) & 1));
+      stick(5);
+    }
     {
       const double phi_d = s_consts[par * 8 + 0], inv_m = s_consts[par * 8 + 1];
       double* r_e = reinterpret_cast<double*>(rec + L.rec_e);
@@ -954,6 +985,45 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       const int f2full = frame_count32(n, fl, fs);
       const int64_t eo = (a.out.epd_energy || a.out.epd_zcr) ? a.epd_offsets[u] : 0;
       const long long thr2 = (long long)thr * thr;
+      if constexpr (kChain) {
+        // every full frame: 4 group records + 8 words of sign bits; the windowed sums of pass BW get their
+        // peak normalisation here
+        const int nfull = n >= 256 ? (n - 256) / 128 + 1 : 0;
+        float* r_fe = reinterpret_cast<float*>(rec + L.rec_fe);
+        float* r_fm = reinterpret_cast<float*>(rec + L.rec_fm);
+        const float sce = (float)(inv_m * inv_m), scm = (float)inv_m;
+#pragma unroll 1
+        for (int f = stid; f < nfull; f += kStreamThreads) {
+          const int p = f * 128;
+          int k1 = 0; long long k2 = 0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const unsigned long long pk = gsum[2 * f + j];
+            k2 += (long long)(pk >> 24);
+            k1 += ((int)((uint32_t)pk << 8)) >> 8;
+          }
+          const int zc = count_changes(s_bits, p, p + 256);
+          if (f < f1) {
+            const long long s1 = (long long)(k1 - 256 * thr);
+            const long long s2 = k2 - 2ll * thr * (long long)k1 + 256ll * thr2;
+            const double t1 = 2.0 * phi_d * (double)s1, t2 = 256.0 * phi_d * phi_d;
+            const double ep = ((double)s2 - t1) + t2;
+            const double e = ep * inv_m * inv_m;
+            r_e[f] = e;
+            r_z[f] = (unsigned short)zc;
+            if (a.out.epd_energy) a.out.epd_energy[eo + f] = e;
+            if (a.out.epd_zcr) a.out.epd_zcr[eo + f] = (float)zc;
+          }
+          int zf = zc;
+          if (hann) {
+            const int s0 = bit_at(s_bits, p), s1b = bit_at(s_bits, p + 1);
+            const int sl = bit_at(s_bits, p + 255), sp = bit_at(s_bits, p + 254);
+            zf += (s1b - (s0 ^ s1b)) + (sp - (sp ^ sl));
+          }
+          r_zf[f] = (unsigned short)zf;
+          r_fe[f] *= sce; r_fm[f] *= scm;
+        }
+      } else {
       const int fmax = max(f1, f2full);
 #pragma unroll 1
       for (int f = stid; f < fmax; f += kStreamThreads) {
@@ -1028,6 +1098,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
           r_zf[f] = (unsigned short)zf;
         }
       }
+      }
       if (stid == kStreamThreads - 1) {
         r_int[0] = u; r_int[1] = n; r_int[2] = f1; r_int[3] = f2full; r_int[4] = thr; r_int[5] = mn; r_int[6] = mx;
         double* rd = reinterpret_cast<double*>(rec + 64);
@@ -1067,7 +1138,7 @@ bool pipe_kernel_plan(int64_t max_len, int cap_frames, int fl, size_t smem_limit
     int R = (int)(room / (kChunkBytes + 16));
     if (R > kMaxRingSlots) R = kMaxRingSlots;
     // two utterances in flight if possible; give up tail warps for ring slots otherwise
-    const bool roomy = R >= 2 * chunks;
+    const bool roomy = R >= 2 * chunks - 2 || R == kMaxRingSlots;
     if (R >= chunks + 1 && (roomy || nrec == 2)) {
       plan->ring_slots = R; plan->n_rec = nrec; plan->cap_groups = capG;
       plan->smem = (size_t)make_pipe_layout(R, capG, cap_frames, fl, nrec).total;
@@ -1078,9 +1149,11 @@ bool pipe_kernel_plan(int64_t max_len, int cap_frames, int fl, size_t smem_limit
 }
 
 cudaError_t launch_frontend_pipe(const PcmArgs& a, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(frontend_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool chain = (a.fl == 256 && a.fs == 128);
+  auto fn = chain ? frontend_pipe_kernel<true> : frontend_pipe_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  frontend_pipe_kernel<<<grid, kPipeThreads, smem, st>>>(a);
+  fn<<<grid, kPipeThreads, smem, st>>>(a);
   return cudaGetLastError();
 }
 
