@@ -63,9 +63,9 @@ __host__ __device__ inline PipeLayout make_pipe_layout(int R, int capG, int capF
   L.bits = o;    o += al16(8 * capG + 16);
   L.meta = o;    o += al16(4 * capG);
   L.rec_e = kRecHdr;
-  L.rec_fe = L.rec_e + al16(8 * capF);
-  L.rec_fm = L.rec_fe + al16(4 * capF);
-  L.rec_z = L.rec_fm + al16(4 * capF);
+  L.rec_fe = L.rec_e;                       // the feature sequences reuse the (dead) energy array
+  L.rec_fm = L.rec_e + 4 * capF;
+  L.rec_z = L.rec_e + al16(8 * capF);
   L.rec_zf = L.rec_z + al16(2 * capF);
   L.rec_bytes = L.rec_zf + al16(2 * capF);
   L.rec = o;     o += nrec * L.rec_bytes;
@@ -340,8 +340,8 @@ __device__ __noinline__ void tail_stats_regs(const float* fe, const float* fm, c
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
-// kChain: frame 256 / shift 128 -- the stream warps also produce the windowed energy / magnitude of
-// EVERY full frame while the samples are in shared memory (pass BW), the tail only selects.
+// kChain: frame 256 / shift 128 -- the tail warps run the sample-stationary chain for the windowed pass
+// (each sample converted once, window coefficients in registers).
 template <bool kChain>
 __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const PcmArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
 #pragma unroll 1
   for (int j = tid; j < fl; j += kPipeThreads) s_win[j] = a.win_f32[j];
   if (tid == 0) {
-    for (int i = 0; i < R; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], kStreamWarps); }
+    for (int i = 0; i < R; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], edges ? kStreamWarps : 1); }
     for (int i = 0; i < nrec; ++i) { mbar_init(&bar_rfull[i], kStreamWarps); mbar_init(&bar_rempty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -439,6 +439,16 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
     float* s_fe = reinterpret_cast<float*>(rec + L.rec_fe);   // indexed by full-utterance frame number
     float* s_fm = reinterpret_cast<float*>(rec + L.rec_fm);
     double* cand = reinterpret_cast<double*>(smem + L.scratch + (size_t)twid * 256);
+
+    // window coefficients of the hop-128 / length-256 chain: a lane owns samples 8*(lane&15) .. +8 of
+    // every hop block; c = 0 is the first half of a frame, c = 1 the second
+    float cw[2][8], cw2[2][8];
+    if constexpr (kChain) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int q8 = 0; q8 < 8; ++q8) { const float w = s_win[c * 128 + 8 * (lane & 15) + q8]; cw[c][q8] = w; cw2[c][q8] = w * w; }
+    }
 
     long long tp[5] = {0, 0, 0, 0, 0}, tprev = clock64();
     auto tick = [&](int i) { if (a.prof) { const long long t = clock64(); tp[i] += t - tprev; tprev = t; } };
@@ -619,10 +629,62 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       const int f2 = frame_count32(seg, fl, fs);
       const double sc_e = inv_m * inv_m, sc_m = inv_m;
       const int zbase = start / fs;        // start is a multiple of the hop: feature frame t is frame zbase + t
-      // frames [0, f2_pre) are already in the record (pass BW of the stream warps); the rest -- zero-padded
-      // frames, or every frame when the stream warps do no window pass -- are computed here from L2
-      int f2_chain = 0;
-      if (kChain) { const int nfull = n >= fl ? (n - fl) / fs + 1 : 0; f2_chain = max(0, min(f2, nfull - zbase)); }
+      int f2_chain = 0;      // frames [0, f2_chain) by the chain path, the rest generically
+      if (kChain && (start & 127) == 0 && seg >= 256) f2_chain = min(f2, (seg - 256) / 128 + 1);
+      if constexpr (kChain) {
+        if (f2_chain > 0) {
+          // 16 lanes per chain, 2 chains; a chain covers `per` consecutive frames = per + 1 hop blocks.
+          // A sample becomes a float once: 0x4B000000 | (k ^ 0x8000) is 2^23 + 32768 + k, minus the integer
+          // 2^23 + 32768 + thr (exact), minus phi (one rounding); then four multiply-adds (two frame
+          // positions x energy / magnitude).  Block i is the second half of frame i-1 and the first of frame i.
+          constexpr int kDepth = 4;                          // hop blocks in flight per lane
+          const int chain = lane >> 4, sub = lane & 15;
+          const int per = (f2_chain + 1) >> 1;
+          const int fa = chain * per;
+          const int nfr = min(per, f2_chain - fa);           // frames of this chain (<= 0: idle)
+          const bool hi8 = (sub & 8) != 0, writer = (sub & 7) == 0;
+          const int4* ptr = reinterpret_cast<const int4*>(x + start + 8 * sub + fa * 128);   // block i at ptr[16 * i]
+          const float c1f = -(8388608.f + 32768.f) - (float)thr;
+          const float scale = hi8 ? (float)sc_m : (float)sc_e;
+          float* dst = (hi8 ? s_fm : s_fe) + zbase + fa - 1;   // frame fa + i - 1 at dst[i]
+          float ce = 0.f, cm = 0.f;                          // first-half partials of the previous block
+          int4 q[kDepth];
+#pragma unroll
+          for (int d = 0; d < kDepth; ++d) q[d] = (nfr > 0 && d <= nfr) ? __ldg(ptr + 16 * d) : make_int4(0, 0, 0, 0);
+#pragma unroll 1
+          for (int i0 = 0; i0 <= per; i0 += kDepth) {       // uniform trip count: the shuffles are warp-wide
+#pragma unroll
+            for (int d = 0; d < kDepth; ++d) {
+              const int i = i0 + d;
+              if (i <= per) {
+                const uint32_t w[4] = {(uint32_t)q[d].x, (uint32_t)q[d].y, (uint32_t)q[d].z, (uint32_t)q[d].w};
+                if (i + kDepth <= nfr) q[d] = __ldg(ptr + 16 * (i + kDepth));
+                float e0 = 0.f, m0 = 0.f, e1 = ce, m1 = cm;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t ub = w[k] ^ 0x80008000u;
+                  const float dlo = (__uint_as_float(__byte_perm(ub, 0x4b000000u, 0x7610)) + c1f) - phi;
+                  const float dhi = (__uint_as_float(__byte_perm(ub, 0x4b000000u, 0x7632)) + c1f) - phi;
+                  const float qlo = dlo * dlo, qhi = dhi * dhi;
+                  const float alo = fabsf(dlo), ahi = fabsf(dhi);
+                  e0 = fmaf(cw2[0][2 * k], qlo, e0); m0 = fmaf(cw[0][2 * k], alo, m0);
+                  e1 = fmaf(cw2[1][2 * k], qlo, e1); m1 = fmaf(cw[1][2 * k], alo, m1);
+                  e0 = fmaf(cw2[0][2 * k + 1], qhi, e0); m0 = fmaf(cw[0][2 * k + 1], ahi, m0);
+                  e1 = fmaf(cw2[1][2 * k + 1], qhi, e1); m1 = fmaf(cw[1][2 * k + 1], ahi, m1);
+                }
+                ce = e0; cm = m0;
+                // transposed reduction of (e1, m1) over the chain's 16 lanes
+                const float send = hi8 ? e1 : m1, keep = hi8 ? m1 : e1;
+                float vv = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                vv += __shfl_xor_sync(0xffffffffu, vv, 4);
+                vv += __shfl_xor_sync(0xffffffffu, vv, 2);
+                vv += __shfl_xor_sync(0xffffffffu, vv, 1);
+                if (writer && i >= 1 && i <= nfr) dst[i] = vv * scale;
+              }
+            }
+          }
+        }
+      }
       if (f2_chain < f2) {
         const int sub = lane & (kLanesPerFrame - 1);
         const int slot = lane / kLanesPerFrame;
@@ -670,11 +732,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
             m += __shfl_xor_sync(0xffffffffu, m, o);
           }
           if (t < f2 && sub == 0) { s_fe[zbase + t] = (float)((double)e * sc_e); s_fm[zbase + t] = (float)((double)m * sc_m); }
-          if (kChain) {
-            // crossing count of the (zero-padded) frame straight from the samples: sign of window * (x - mean),
-            // zero counts as negative (audio_processing.py:119-132)
+          // zero-padded frame whose crossing count the stream warps could not take from a bit string: count it
+          // from the samples (sign of window * (x - mean), zero is negative, audio_processing.py:119-132)
+          const bool need_zc = t < f2 && r_zf[zbase + t] == 0xffffu;
+          if (__any_sync(0xffffffffu, need_zc)) {
             int zc = 0;
-            if (t < f2) {
+            if (need_zc) {
               const int p = start + t * fs;
               const int valid = min(fl, end - p);
               auto pos = [&](int j) { return j < valid && s_win[j] > 0.f && ((int)__ldg(x + p + j) - thr) >= 0; };
@@ -683,7 +746,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
             }
 #pragma unroll
             for (int o = kLanesPerFrame / 2; o > 0; o >>= 1) zc += __shfl_xor_sync(0xffffffffu, zc, o);
-            if (t < f2 && sub == 0) r_zf[zbase + t] = (unsigned short)zc;
+            __syncwarp();
+            if (need_zc && sub == 0) r_zf[zbase + t] = (unsigned short)zc;
           }
         }
       }
@@ -738,18 +802,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
 #else
   const int swid = wid - kMaxTailWarps, stid = tid - 32 * kMaxTailWarps;
 #endif
-  // pass BW (kChain): a lane owns samples 8*(lane&15) .. +8 of every hop block; c = 0 is the first half
-  // of a frame, c = 1 the second; (w, w) and (w^2, w^2) pairs stay in registers
-  f32x2 cw[2][4], cw2[2][4];
-  if constexpr (kChain) {
-#pragma unroll
-    for (int c = 0; c < 2; ++c)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float w0 = s_win[c * 128 + 8 * (lane & 15) + 2 * k], w1 = s_win[c * 128 + 8 * (lane & 15) + 2 * k + 1];
-        cw[c][k] = pk2(w0, w1); cw2[c][k] = pk2(w0 * w0, w1 * w1);
-      }
-  }
   int useq = 0, cslot = 0, clap = 0;
   long long sp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sprev = clock64();
   auto stick = [&](int i) { if (a.prof) { const long long t = clock64(); sp[i] += t - sprev; sprev = t; } };
@@ -769,7 +821,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       if (stid == 0) { const int s = atomicAdd(a.flag_count, 1); a.flag_list[s] = u; r_int[0] = u; r_int[1] = 0; r_int[2] = 0; r_int[3] = 0;
         r_int[4] = 0; r_int[5] = 0; r_int[6] = 0; double* rd = reinterpret_cast<double*>(rec + 64); rd[0] = 0.0; rd[1] = 1.0; rd[2] = 0.0; }
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&bar_empty[cslot]); mbar_arrive(&bar_rfull[rec_id]); }
+      if (lane == 0) { if (edges || swid == 0) mbar_arrive(&bar_empty[cslot]); mbar_arrive(&bar_rfull[rec_id]); }
       if (++cslot == R) { cslot = 0; ++clap; }
       ++useq;
       continue;
@@ -853,8 +905,48 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       cst[2] = (double)S / (double)N;
     }
 
-    if constexpr (!kChain) {
     // =========================== pass B: sign bits ====================================
+    // When k - thr fits 16 bits for every sample (always, unless a full-scale signal sits on a large DC
+    // offset) the subtraction runs on the packed word: w - (thr << 16) has the sign of the high sample,
+    // w * 65536 - (thr << 16) that of the low one -- one instruction each, no unpacking.
+    const bool narrow = (mx - thr <= 32766) && (thr - mn <= 32768) && thr >= -32766 && thr <= 32767;
+    const uint32_t thr16 = (uint32_t)thr << 16;
+    // fastest form (whole-group frames, narrow range): max(min(k - thr + 1, 1), 0) on both halves of a word in
+    // ONE instruction (VIADDMNMX.S16x2.RELU) is the pair of "above the mean" bits; acc + acc + r appends
+    // them to an even-sample and an odd-sample bit plane.  Only the per-group record (crossings inside the
+    // group, its first / last two bits) is needed downstream, the bit string itself is never stored.
+    const bool fastb = narrow && !edges;
+    if (fastb) {
+      const uint32_t t2 = ((uint32_t)(1 - thr) & 0xffffu) * 0x00010001u;
+#pragma unroll 1
+      for (int c = swid; c < nchunks; c += kStreamWarps) {
+        int s = cslot + c; if (s >= R) s -= R;
+        const int g = kGroupsPerChunk * c + lane;
+        if (g * kGroup + kGroup <= n) {
+          const unsigned char* gp = s_ring + (size_t)s * kChunkBytes + lane * (2 * kGroup);
+          const int rot = lane & 7;
+          uint32_t acc0 = 0, acc1 = 0;
+#pragma unroll
+          for (int pp = 3; pp >= 0; --pp) {      // descending: the first sample ends up in bit 0
+            const int4 qa = *reinterpret_cast<const int4*>(gp + 16 * ((pp + rot) & 7));
+            const int4 qb = *reinterpret_cast<const int4*>(gp + 16 * ((pp + 4 + rot) & 7));
+            acc0 = acc0 + acc0 + __viaddmin_s16x2_relu((uint32_t)qa.w, t2, 0x00010001u);
+            acc1 = acc1 + acc1 + __viaddmin_s16x2_relu((uint32_t)qb.w, t2, 0x00010001u);
+            acc0 = acc0 + acc0 + __viaddmin_s16x2_relu((uint32_t)qa.z, t2, 0x00010001u);
+            acc1 = acc1 + acc1 + __viaddmin_s16x2_relu((uint32_t)qb.z, t2, 0x00010001u);
+            acc0 = acc0 + acc0 + __viaddmin_s16x2_relu((uint32_t)qa.y, t2, 0x00010001u);
+            acc1 = acc1 + acc1 + __viaddmin_s16x2_relu((uint32_t)qb.y, t2, 0x00010001u);
+            acc0 = acc0 + acc0 + __viaddmin_s16x2_relu((uint32_t)qa.x, t2, 0x00010001u);
+            acc1 = acc1 + acc1 + __viaddmin_s16x2_relu((uint32_t)qb.x, t2, 0x00010001u);
+          }
+          // planes in processing order -> undo the rotation: bit a of E / O is sample 2a / 2a+1 of the group
+          const uint32_t ep = __byte_perm(acc0, acc1, 0x5410), op = __byte_perm(acc0, acc1, 0x7632);
+          const uint32_t E = __funnelshift_l(ep, ep, 4 * rot), O = __funnelshift_l(op, op, 4 * rot);
+          const uint32_t x1 = E ^ O, x2 = (O ^ (E >> 1)) & 0x7fffffffu;
+          s_meta[g] = (uint32_t)(__popc(x1) + __popc(x2)) | ((E & 1u) << 8) | ((O & 1u) << 9) | ((E >> 31) << 10) | ((O >> 31) << 11);
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int c = swid; c < nchunks; c += kStreamWarps) {
       int s = cslot + c; if (s >= R) s -= R;
@@ -865,18 +957,33 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
         const unsigned char* gp = s_ring + (size_t)s * kChunkBytes + lane * (2 * kGroup);
         const int rot = lane & 7;
         uint32_t nlo = 0, nhi = 0;         // "below the mean" bits, MSB-first, in processing order
+        if (narrow) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int4 qa = *reinterpret_cast<const int4*>(gp + 16 * ((j + rot) & 7));
-          const int4 qb = *reinterpret_cast<const int4*>(gp + 16 * ((j + 4 + rot) & 7));
-          const uint32_t wa[4] = {(uint32_t)qa.x, (uint32_t)qa.y, (uint32_t)qa.z, (uint32_t)qa.w};
-          const uint32_t wb[4] = {(uint32_t)qb.x, (uint32_t)qb.y, (uint32_t)qb.z, (uint32_t)qb.w};
+          for (int j = 0; j < 4; ++j) {
+            const int4 qa = *reinterpret_cast<const int4*>(gp + 16 * ((j + rot) & 7));
+            const int4 qb = *reinterpret_cast<const int4*>(gp + 16 * ((j + 4 + rot) & 7));
+            const uint32_t wa[4] = {(uint32_t)qa.x, (uint32_t)qa.y, (uint32_t)qa.z, (uint32_t)qa.w};
+            const uint32_t wb[4] = {(uint32_t)qb.x, (uint32_t)qb.y, (uint32_t)qb.z, (uint32_t)qb.w};
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int alo = sext16(wa[k]) - thr, ahi = ((int)wa[k] >> 16) - thr;
-            const int blo = sext16(wb[k]) - thr, bhi = ((int)wb[k] >> 16) - thr;
-            nhi = __funnelshift_l((uint32_t)alo, nhi, 1); nhi = __funnelshift_l((uint32_t)ahi, nhi, 1);
-            nlo = __funnelshift_l((uint32_t)blo, nlo, 1); nlo = __funnelshift_l((uint32_t)bhi, nlo, 1);
+            for (int k = 0; k < 4; ++k) {
+              nhi = __funnelshift_l(wa[k] * 65536u - thr16, nhi, 1); nhi = __funnelshift_l(wa[k] - thr16, nhi, 1);
+              nlo = __funnelshift_l(wb[k] * 65536u - thr16, nlo, 1); nlo = __funnelshift_l(wb[k] - thr16, nlo, 1);
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            const int4 qa = *reinterpret_cast<const int4*>(gp + 16 * ((j + rot) & 7));
+            const int4 qb = *reinterpret_cast<const int4*>(gp + 16 * ((j + 4 + rot) & 7));
+            const uint32_t wa[4] = {(uint32_t)qa.x, (uint32_t)qa.y, (uint32_t)qa.z, (uint32_t)qa.w};
+            const uint32_t wb[4] = {(uint32_t)qb.x, (uint32_t)qb.y, (uint32_t)qb.z, (uint32_t)qb.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int alo = sext16(wa[k]) - thr, ahi = ((int)wa[k] >> 16) - thr;
+              const int blo = sext16(wb[k]) - thr, bhi = ((int)wb[k] >> 16) - thr;
+              nhi = __funnelshift_l((uint32_t)alo, nhi, 1); nhi = __funnelshift_l((uint32_t)ahi, nhi, 1);
+              nlo = __funnelshift_l((uint32_t)blo, nlo, 1); nlo = __funnelshift_l((uint32_t)bhi, nlo, 1);
+            }
           }
         }
         // stream (nhi:nlo) holds vector `rot` first (at the top); reverse to LSB-first, undo the rotation
@@ -898,72 +1005,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       }
     }
     if (stid < 4) s_bits[2 * ng + stid] = 0;
-    } else {
-    // =========================== pass BW: sign bits + windowed sums of every full frame ==========
-    // 16 chains of 16 lanes walk the hop blocks; a sample becomes a float once: 0x4B000000 | (k ^ 0x8000)
-    // is 2^23 + 32768 + k, minus the integer 2^23 + 32768 + thr (exact; its sign IS the sign bit),
-    // minus phi (one rounding); squares, magnitudes and the four multiply-adds per sample run as packed
-    // pairs (FADD2 / FMUL2 / FFMA2).  Block b is the second half of frame b-1 and the first of frame b.
-    if (rec_lap > 0) mbar_wait(&bar_rempty[rec_id], (uint32_t)((rec_lap - 1) & 1));   // raw sums go to the record
-    stick(5);
-    {
-      const int nfull = n >= 256 ? (n - 256) / 128 + 1 : 0;
-      if (nfull > 0) {
-        const int chain = stid >> 4, sub = lane & 15;
-        const int per = (nfull + 15) >> 4;
-        const int fa = chain * per;
-        const int nfr = min(per, nfull - fa);              // frames of this chain (<= 0: idle)
-        const bool hi8 = (sub & 8) != 0, writer = (sub & 7) == 0;
-        const float phi = __fdiv_rn((float)((long long)S - (long long)N * thr), (float)N);
-        const float c1f = -(8388608.f + 32768.f) - (float)thr;
-        const f32x2 c1 = pk2(c1f, c1f), c2 = pk2(-phi, -phi);
-        float* dst = reinterpret_cast<float*>(rec + (hi8 ? L.rec_fm : L.rec_fe)) + fa - 1;   // frame fa + i - 1 at dst[i]
-        unsigned char* bitbytes = reinterpret_cast<unsigned char*>(s_bits);
-        auto load_blk = [&](int b, bool first) -> int4 {
-          int sl = cslot + (b >> 4), lp = clap; if (sl >= R) { sl -= R; ++lp; }
-          if (first || (b & 15) == 0) mbar_wait(&bar_full[sl], (uint32_t)(lp & 1));   // already complete: acquire only
-          return *reinterpret_cast<const int4*>(s_ring + (size_t)sl * kChunkBytes + (b & 15) * 256 + sub * 16);
-        };
-        f32x2 ce = pk2(0.f, 0.f), cm = ce;                 // first-half partials of the previous block
-        int4 qn = make_int4(0, 0, 0, 0);
-        if (nfr > 0) qn = load_blk(fa, true);
-#pragma unroll 1
-        for (int i = 0; i <= per; ++i) {                   // uniform trip count: the shuffles are warp-wide
-          const int b = fa + i;
-          const bool act = nfr > 0 && i <= nfr;
-          const uint32_t w[4] = {(uint32_t)qn.x, (uint32_t)qn.y, (uint32_t)qn.z, (uint32_t)qn.w};
-          if (nfr > 0 && i + 1 <= nfr) qn = load_blk(b + 1, false);
-          f32x2 e0 = pk2(0.f, 0.f), m0 = e0, e1 = ce, m1 = cm;
-          uint32_t sg = 0;                                 // "below the mean" bits, first sample at the top
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t ub = w[k] ^ 0x80008000u;
-            const f32x2 tt = add2(pk2(__uint_as_float(__byte_perm(ub, 0x4b000000u, 0x7610)), __uint_as_float(__byte_perm(ub, 0x4b000000u, 0x7632))), c1);
-            sg = __funnelshift_l((uint32_t)tt, sg, 1);
-            sg = __funnelshift_l((uint32_t)(tt >> 32), sg, 1);
-            const f32x2 dd = add2(tt, c2);
-            const f32x2 sq = mul2(dd, dd);
-            const f32x2 ab = dd & 0x7fffffff7fffffffull;
-            e0 = fma2(cw2[0][k], sq, e0); m0 = fma2(cw[0][k], ab, m0);
-            e1 = fma2(cw2[1][k], sq, e1); m1 = fma2(cw[1][k], ab, m1);
-          }
-          ce = e0; cm = m0;
-          if (act && (i < nfr || b == nfull)) bitbytes[16 * b + sub] = (unsigned char)(~(__brev(sg) >> 24));
-          // transposed reduction of (e1, m1) over the chain's 16 lanes
-          const float es = hsum2(e1), ms = hsum2(m1);
-          const float send = hi8 ? es : ms, keep = hi8 ? ms : es;
-          float vv = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-          vv += __shfl_xor_sync(0xffffffffu, vv, 4);
-          vv += __shfl_xor_sync(0xffffffffu, vv, 2);
-          vv += __shfl_xor_sync(0xffffffffu, vv, 1);
-          if (writer && act && i >= 1) dst[i] = vv;        // raw sums: pass F applies the peak normalisation
-        }
-      }
     }
-    }
+    // ring slots back to the producer: every warp for every slot when pass F still reads samples (frame
+    // edges), else only the owner of a chunk, right after its own pass B
     auto release_slots = [&]() {
       __syncwarp();
-      for (int c = lane; c < nchunks; c += 32) { int s = cslot + c; if (s >= R) s -= R; mbar_arrive(&bar_empty[s]); }
+      if (edges) { for (int c = lane; c < nchunks; c += 32) { int s = cslot + c; if (s >= R) s -= R; mbar_arrive(&bar_empty[s]); } }
+      else if (lane == 0) { for (int c = swid; c < nchunks; c += kStreamWarps) { int s = cslot + c; if (s >= R) s -= R; mbar_arrive(&bar_empty[s]); } }
     };
     if (!edges) release_slots();
     stick(3);
@@ -971,10 +1019,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
     stick(4);
 
     // =========================== pass F: EPD frames -> record =========================
-    if constexpr (!kChain) {
-      if (rec_lap > 0) mbar_wait(&bar_rempty[rec_id], (uint32_t)((rec_lap - 1) & 1));
-      stick(5);
-    }
+    if (rec_lap > 0) mbar_wait(&bar_rempty[rec_id], (uint32_t)((rec_lap - 1) & 1));
+    stick(5);
     {
       const double phi_d = s_consts[par * 8 + 0], inv_m = s_consts[par * 8 + 1];
       double* r_e = reinterpret_cast<double*>(rec + L.rec_e);
@@ -985,52 +1031,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       const int f2full = frame_count32(n, fl, fs);
       const int64_t eo = (a.out.epd_energy || a.out.epd_zcr) ? a.epd_offsets[u] : 0;
       const long long thr2 = (long long)thr * thr;
-      if constexpr (kChain) {
-        // every full frame: 4 group records + 8 words of sign bits; the windowed sums of pass BW get their
-        // peak normalisation here
-        const int nfull = n >= 256 ? (n - 256) / 128 + 1 : 0;
-        float* r_fe = reinterpret_cast<float*>(rec + L.rec_fe);
-        float* r_fm = reinterpret_cast<float*>(rec + L.rec_fm);
-        const float sce = (float)(inv_m * inv_m), scm = (float)inv_m;
-#pragma unroll 1
-        for (int f = stid; f < nfull; f += kStreamThreads) {
-          const int p = f * 128;
-          int k1 = 0; long long k2 = 0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const unsigned long long pk = gsum[2 * f + j];
-            k2 += (long long)(pk >> 24);
-            k1 += ((int)((uint32_t)pk << 8)) >> 8;
-          }
-          const int zc = count_changes(s_bits, p, p + 256);
-          if (f < f1) {
-            const long long s1 = (long long)(k1 - 256 * thr);
-            const long long s2 = k2 - 2ll * thr * (long long)k1 + 256ll * thr2;
-            const double t1 = 2.0 * phi_d * (double)s1, t2 = 256.0 * phi_d * phi_d;
-            const double ep = ((double)s2 - t1) + t2;
-            const double e = ep * inv_m * inv_m;
-            r_e[f] = e;
-            r_z[f] = (unsigned short)zc;
-            if (a.out.epd_energy) a.out.epd_energy[eo + f] = e;
-            if (a.out.epd_zcr) a.out.epd_zcr[eo + f] = (float)zc;
-          }
-          int zf = zc;
-          if (hann) {
-            const int s0 = bit_at(s_bits, p), s1b = bit_at(s_bits, p + 1);
-            const int sl = bit_at(s_bits, p + 255), sp = bit_at(s_bits, p + 254);
-            zf += (s1b - (s0 ^ s1b)) + (sp - (sp ^ sl));
-          }
-          r_zf[f] = (unsigned short)zf;
-          r_fe[f] *= sce; r_fm[f] *= scm;
-        }
-      } else {
-      const int fmax = max(f1, f2full);
+      const int nfull = n >= fl ? (n - fl) / fs + 1 : 0;        // frames without zero padding
+      const int fmax = max(nfull, f2full);
 #pragma unroll 1
       for (int f = stid; f < fmax; f += kStreamThreads) {
         const int p = f * fs;
         int zc = 0;
         uint32_t m_first = 0, m_last = 0;
-        if (f < f1) {
+        if (f < nfull) {
           const int q = p + fl;
           long long s1, s2;
           if (!edges) {
@@ -1072,19 +1080,21 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
             s2 = k2 - 2ll * thr * k1 + (long long)fl * thr2;
             zc = count_changes(s_bits, p, q);
           }
-          // exact integer sums of d = k - thr, then sum (d - phi)^2 in three roundings
-          const double t1 = 2.0 * phi_d * (double)s1, t2 = (double)fl * phi_d * phi_d;
-          const double ep = ((double)s2 - t1) + t2;
-          const double e = ep * inv_m * inv_m;
-          r_e[f] = e;
-          r_z[f] = (unsigned short)zc;
-          if (a.out.epd_energy) a.out.epd_energy[eo + f] = e;
-          if (a.out.epd_zcr) a.out.epd_zcr[eo + f] = (float)zc;
+          if (f < f1) {
+            // exact integer sums of d = k - thr, then sum (d - phi)^2 in three roundings
+            const double t1 = 2.0 * phi_d * (double)s1, t2 = (double)fl * phi_d * phi_d;
+            const double ep = ((double)s2 - t1) + t2;
+            const double e = ep * inv_m * inv_m;
+            r_e[f] = e;
+            r_z[f] = (unsigned short)zc;
+            if (a.out.epd_energy) a.out.epd_energy[eo + f] = e;
+            if (a.out.epd_zcr) a.out.epd_zcr[eo + f] = (float)zc;
+          }
         }
         if (f < f2full) {
           const int valid = min(fl, n - p);
           int zf;
-          if (f < f1 && !(hann && fl <= 2)) {
+          if (f < nfull && !(hann && fl <= 2)) {
             zf = zc;
             if (hann) {
               int s0, s1b, sp, sl;
@@ -1092,12 +1102,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
               else { s0 = bit_at(s_bits, p); s1b = bit_at(s_bits, p + 1); sl = bit_at(s_bits, p + fl - 1); sp = bit_at(s_bits, p + fl - 2); }
               zf += (s1b - (s0 ^ s1b)) + (sp - (sp ^ sl));
             }
+          } else if (fastb) {
+            zf = 0xffff;                     // zero-padded frame, no bit string in this mode: the tail counts it from L2
           } else {
             zf = frame_zcr(s_bits, p, valid, fl, hann);
           }
           r_zf[f] = (unsigned short)zf;
         }
-      }
       }
       if (stid == kStreamThreads - 1) {
         r_int[0] = u; r_int[1] = n; r_int[2] = f1; r_int[3] = f2full; r_int[4] = thr; r_int[5] = mn; r_int[6] = mx;
