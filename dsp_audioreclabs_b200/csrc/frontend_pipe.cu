@@ -46,6 +46,11 @@ constexpr int kKeyRegs = 11;               // EPD frames per lane whose float ke
 constexpr int kLanesPerFrame = 8;          // generic windowed pass: lanes cooperating on one frame
 
 constexpr int kBarStream = 1;              // named barrier of the stream warps
+// record hand-offs use named barriers too (a warp parked on bar.sync costs no issue slots, a warp polling an
+// mbarrier does): kBarRecFull + r is "record r is complete" (stream warps arrive, its tail warp syncs),
+// kBarRecEmpty + r is "record r is free again" (the tail warp arrives, the stream warps sync)
+constexpr int kBarRecFull = 2, kBarRecEmpty = 9;
+constexpr int kRecBarThreads = 32 * (kStreamWarps + 1);   // the stream warps + the record's tail warp
 
 struct PipeLayout {
   int ring, gsum, bits, meta, rec, scratch, win, desc, part, consts, bars, total;
@@ -107,6 +112,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // ---- integer dot products on byte planes ------------------------------------------------
 __device__ __forceinline__ int dp4a_ss(int a, int b, int c) { int d; asm("dp4a.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
@@ -357,8 +363,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
   double* s_consts = reinterpret_cast<double*>(smem + L.consts);                        // [2][8]
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* bar_empty = bar_full + R;
-  uint64_t* bar_rfull = bar_empty + R;
-  uint64_t* bar_rempty = bar_rfull + nrec;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int fl = a.fl, fs = a.fs;
@@ -370,7 +374,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
   for (int j = tid; j < fl; j += kPipeThreads) s_win[j] = a.win_f32[j];
   if (tid == 0) {
     for (int i = 0; i < R; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], edges ? kStreamWarps : 1); }
-    for (int i = 0; i < nrec; ++i) { mbar_init(&bar_rfull[i], kStreamWarps); mbar_init(&bar_rempty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -453,7 +456,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
     long long tp[5] = {0, 0, 0, 0, 0}, tprev = clock64();
     auto tick = [&](int i) { if (a.prof) { const long long t = clock64(); tp[i] += t - tprev; tprev = t; } };
     for (int it = 0;; ++it) {
-      mbar_wait(&bar_rfull[twid], (uint32_t)(it & 1));
+      bar_sync(kBarRecFull + twid, kRecBarThreads);
       const int u = r_int[0];
       if (u < 0) break;
       tick(0);
@@ -637,51 +640,50 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
           // A sample becomes a float once: 0x4B000000 | (k ^ 0x8000) is 2^23 + 32768 + k, minus the integer
           // 2^23 + 32768 + thr (exact), minus phi (one rounding); then four multiply-adds (two frame
           // positions x energy / magnitude).  Block i is the second half of frame i-1 and the first of frame i.
-          constexpr int kDepth = 4;                          // hop blocks in flight per lane
           const int chain = lane >> 4, sub = lane & 15;
           const int per = (f2_chain + 1) >> 1;
           const int fa = chain * per;
           const int nfr = min(per, f2_chain - fa);           // frames of this chain (<= 0: idle)
+          const int last = max(nfr, 0);                      // last hop block this chain may touch
           const bool hi8 = (sub & 8) != 0, writer = (sub & 7) == 0;
-          const int4* ptr = reinterpret_cast<const int4*>(x + start + 8 * sub + fa * 128);   // block i at ptr[16 * i]
+          // block i at ptr[16 * i]; an idle chain re-reads the first block of the segment and stores nothing
+          const int4* ptr = reinterpret_cast<const int4*>(x + start + 8 * sub + (nfr > 0 ? fa : 0) * 128);
           const float c1f = -(8388608.f + 32768.f) - (float)thr;
           const float scale = hi8 ? (float)sc_m : (float)sc_e;
           float* dst = (hi8 ? s_fm : s_fe) + zbase + fa - 1;   // frame fa + i - 1 at dst[i]
           float ce = 0.f, cm = 0.f;                          // first-half partials of the previous block
-          int4 q[kDepth];
+          auto step = [&](const int4& q, int i) {
+            const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+            float e0 = 0.f, m0 = 0.f, e1 = ce, m1 = cm;
 #pragma unroll
-          for (int d = 0; d < kDepth; ++d) q[d] = (nfr > 0 && d <= nfr) ? __ldg(ptr + 16 * d) : make_int4(0, 0, 0, 0);
-#pragma unroll 1
-          for (int i0 = 0; i0 <= per; i0 += kDepth) {       // uniform trip count: the shuffles are warp-wide
-#pragma unroll
-            for (int d = 0; d < kDepth; ++d) {
-              const int i = i0 + d;
-              if (i <= per) {
-                const uint32_t w[4] = {(uint32_t)q[d].x, (uint32_t)q[d].y, (uint32_t)q[d].z, (uint32_t)q[d].w};
-                if (i + kDepth <= nfr) q[d] = __ldg(ptr + 16 * (i + kDepth));
-                float e0 = 0.f, m0 = 0.f, e1 = ce, m1 = cm;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint32_t ub = w[k] ^ 0x80008000u;
-                  const float dlo = (__uint_as_float(__byte_perm(ub, 0x4b000000u, 0x7610)) + c1f) - phi;
-                  const float dhi = (__uint_as_float(__byte_perm(ub, 0x4b000000u, 0x7632)) + c1f) - phi;
-                  const float qlo = dlo * dlo, qhi = dhi * dhi;
-                  const float alo = fabsf(dlo), ahi = fabsf(dhi);
-                  e0 = fmaf(cw2[0][2 * k], qlo, e0); m0 = fmaf(cw[0][2 * k], alo, m0);
-                  e1 = fmaf(cw2[1][2 * k], qlo, e1); m1 = fmaf(cw[1][2 * k], alo, m1);
-                  e0 = fmaf(cw2[0][2 * k + 1], qhi, e0); m0 = fmaf(cw[0][2 * k + 1], ahi, m0);
-                  e1 = fmaf(cw2[1][2 * k + 1], qhi, e1); m1 = fmaf(cw[1][2 * k + 1], ahi, m1);
-                }
-                ce = e0; cm = m0;
-                // transposed reduction of (e1, m1) over the chain's 16 lanes
-                const float send = hi8 ? e1 : m1, keep = hi8 ? m1 : e1;
-                float vv = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-                vv += __shfl_xor_sync(0xffffffffu, vv, 4);
-                vv += __shfl_xor_sync(0xffffffffu, vv, 2);
-                vv += __shfl_xor_sync(0xffffffffu, vv, 1);
-                if (writer && i >= 1 && i <= nfr) dst[i] = vv * scale;
-              }
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t ub = w[k] ^ 0x80008000u;
+              const float dlo = (__uint_as_float(__byte_perm(ub, 0x4b000000u, 0x7610)) + c1f) - phi;
+              const float dhi = (__uint_as_float(__byte_perm(ub, 0x4b000000u, 0x7632)) + c1f) - phi;
+              const float qlo = dlo * dlo, qhi = dhi * dhi;
+              const float alo = fabsf(dlo), ahi = fabsf(dhi);
+              e0 = fmaf(cw2[0][2 * k], qlo, e0); m0 = fmaf(cw[0][2 * k], alo, m0);
+              e1 = fmaf(cw2[1][2 * k], qlo, e1); m1 = fmaf(cw[1][2 * k], alo, m1);
+              e0 = fmaf(cw2[0][2 * k + 1], qhi, e0); m0 = fmaf(cw[0][2 * k + 1], ahi, m0);
+              e1 = fmaf(cw2[1][2 * k + 1], qhi, e1); m1 = fmaf(cw[1][2 * k + 1], ahi, m1);
             }
+            ce = e0; cm = m0;
+            // transposed reduction of (e1, m1) over the chain's 16 lanes
+            const float send = hi8 ? e1 : m1, keep = hi8 ? m1 : e1;
+            float vv = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            vv += __shfl_xor_sync(0xffffffffu, vv, 4);
+            vv += __shfl_xor_sync(0xffffffffu, vv, 2);
+            vv += __shfl_xor_sync(0xffffffffu, vv, 1);
+            if (writer && i >= 1 && i <= nfr) dst[i] = vv * scale;
+          };
+          // four hop blocks in flight per lane; loads past the chain's last block re-read that block
+          int4 q0 = __ldg(ptr), q1 = __ldg(ptr + 16 * min(1, last)), q2 = __ldg(ptr + 16 * min(2, last)), q3 = __ldg(ptr + 16 * min(3, last));
+#pragma unroll 1
+          for (int i = 0; i <= per; i += 4) {               // uniform trip count: the shuffles are warp-wide
+            step(q0, i);     q0 = __ldg(ptr + 16 * min(i + 4, last));
+            step(q1, i + 1); q1 = __ldg(ptr + 16 * min(i + 5, last));
+            step(q2, i + 2); q2 = __ldg(ptr + 16 * min(i + 6, last));
+            step(q3, i + 3); q3 = __ldg(ptr + 16 * min(i + 7, last));
           }
         }
       }
@@ -787,7 +789,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
         if (flagged) { const int s = atomicAdd(a.flag_count, 1); a.flag_list[s] = u; }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_rempty[twid]);
+      bar_arrive(kBarRecEmpty + twid, kRecBarThreads);
       tick(3);
     }
     if (a.prof && twid == 0 && lane == 0) for (int i = 0; i < 4; ++i) atomicAdd((unsigned long long*)&a.prof[8 + i], (unsigned long long)tp[i]);
@@ -802,7 +804,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
 #else
   const int swid = wid - kMaxTailWarps, stid = tid - 32 * kMaxTailWarps;
 #endif
-  int useq = 0, cslot = 0, clap = 0;
+  int useq = 0, cslot = 0, clap = 0, rec_id = 0, rec_lap = 0;
   long long sp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sprev = clock64();
   auto stick = [&](int i) { if (a.prof) { const long long t = clock64(); sp[i] += t - sprev; sprev = t; } };
   for (;;) {
@@ -812,18 +814,20 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
     const int u = dsc.x;
     if (u < 0) break;
     const int par = useq & 1;
-    const int rec_id = useq % nrec, rec_lap = useq / nrec;
     unsigned char* rec = smem + L.rec + (size_t)rec_id * L.rec_bytes;
     int* r_int = reinterpret_cast<int*>(rec);
     if (dsc.y < 0) {
       // misaligned start: hand the utterance to the float64 replay, keep the pipeline's sequence numbers
-      if (rec_lap > 0) mbar_wait(&bar_rempty[rec_id], (uint32_t)((rec_lap - 1) & 1));
+      if (rec_lap > 0) bar_sync(kBarRecEmpty + rec_id, kRecBarThreads);
       if (stid == 0) { const int s = atomicAdd(a.flag_count, 1); a.flag_list[s] = u; r_int[0] = u; r_int[1] = 0; r_int[2] = 0; r_int[3] = 0;
         r_int[4] = 0; r_int[5] = 0; r_int[6] = 0; double* rd = reinterpret_cast<double*>(rec + 64); rd[0] = 0.0; rd[1] = 1.0; rd[2] = 0.0; }
       __syncwarp();
-      if (lane == 0) { if (edges || swid == 0) mbar_arrive(&bar_empty[cslot]); mbar_arrive(&bar_rfull[rec_id]); }
+      if (lane == 0 && (edges || swid == 0)) mbar_arrive(&bar_empty[cslot]);
+      __syncwarp();
+      bar_arrive(kBarRecFull + rec_id, kRecBarThreads);
       if (++cslot == R) { cslot = 0; ++clap; }
       ++useq;
+      if (++rec_id == nrec) { rec_id = 0; ++rec_lap; }
       continue;
     }
     const int n = dsc.y;
@@ -1019,7 +1023,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
     stick(4);
 
     // =========================== pass F: EPD frames -> record =========================
-    if (rec_lap > 0) mbar_wait(&bar_rempty[rec_id], (uint32_t)((rec_lap - 1) & 1));
+    if (rec_lap > 0) bar_sync(kBarRecEmpty + rec_id, kRecBarThreads);
     stick(5);
     {
       const double phi_d = s_consts[par * 8 + 0], inv_m = s_consts[par * 8 + 1];
@@ -1118,20 +1122,21 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
     }
     if (edges) release_slots();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&bar_rfull[rec_id]);
+    bar_arrive(kBarRecFull + rec_id, kRecBarThreads);
     cslot += nchunks; if (cslot >= R) { cslot -= R; ++clap; }
     ++useq;
+    if (++rec_id == nrec) { rec_id = 0; ++rec_lap; }
     stick(6);
   }
   if (a.prof && stid == 0) { for (int i = 0; i < 7; ++i) atomicAdd((unsigned long long*)&a.prof[i], (unsigned long long)sp[i]); atomicAdd((unsigned long long*)&a.prof[15], (unsigned long long)useq); }
   // tell the tail warps to stop: one terminator record each
 #pragma unroll 1
-  for (int k = 0; k < nrec; ++k, ++useq) {
-    const int rec_id = useq % nrec, rec_lap = useq / nrec;
-    if (rec_lap > 0) mbar_wait(&bar_rempty[rec_id], (uint32_t)((rec_lap - 1) & 1));
+  for (int k = 0; k < nrec; ++k) {
+    if (rec_lap > 0) bar_sync(kBarRecEmpty + rec_id, kRecBarThreads);
     if (stid == 0) *reinterpret_cast<int*>(smem + L.rec + (size_t)rec_id * L.rec_bytes) = -1;
     __syncwarp();
-    if (lane == 0) mbar_arrive(&bar_rfull[rec_id]);
+    bar_arrive(kBarRecFull + rec_id, kRecBarThreads);
+    if (++rec_id == nrec) { rec_id = 0; ++rec_lap; }
   }
 }
 
