@@ -259,7 +259,7 @@ def run_ours(args):
     total_ms_max = float(tmax.item())
     value = world * audio_s_per_step * args.steps / (total_ms_max / 1000.0)
 
-    # ---- roofline of the dominant kernel (frontend_pcm_kernel) ------------------------------
+    # ---- roofline of the dominant kernel (frontend_pipe_kernel, csrc/frontend_pipe.cu) --------
     per_window = {}
     for wi, w in enumerate(WINDOWS):
         ms = [step_ms[i] for i in range(args.steps) if i % 3 == wi]
@@ -277,7 +277,7 @@ def run_ours(args):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "frontend_pcm_kernel", "peak_source": peak_src,
+                "traffic": traffic, "kernel": "frontend_pipe_kernel<true>", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": avg_ms}
 
     # ---- parity spot check against the oracle on a few of the benchmarked utterances --------

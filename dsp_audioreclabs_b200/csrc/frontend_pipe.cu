@@ -365,10 +365,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
   uint64_t* bar_empty = bar_full + R;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int fl = a.fl, fs = a.fs;
+  // kChain fixes frame 256 / shift 128 at compile time: divisions, edge handling and the generic loops fold away
+  const int fl = kChain ? 256 : a.fl, fs = kChain ? 128 : a.fs;
   const bool hann = (a.window == DSP_WIN_HANNING);
   // frames are sums of whole groups: the stream warps are done with the samples after pass B
-  const bool edges = ((fl % kGroup) | (fs % kGroup)) != 0 || fl > 16384;
+  const bool edges = kChain ? false : (((fl % kGroup) | (fs % kGroup)) != 0 || fl > 16384);
 
 #pragma unroll 1
   for (int j = tid; j < fl; j += kPipeThreads) s_win[j] = a.win_f32[j];
