@@ -289,10 +289,10 @@ __device__ __noinline__ void tail_stats_regs(const float* fe, const float* fm, c
       key[j] = i < n ? __float_as_uint(x) : 0xffffffffu;
       if (i < n) { ps += x; kmn = min(kmn, key[j]); kmx = max(kmx, key[j]); }
     }
-    const double mean = warp_reduce((double)ps, OpAddD()) / (double)n;
+    const float inv_n = 1.0f / (float)n;
+    const float meanf = (float)warp_reduce((double)ps, OpAddD()) * inv_n;     // float32 result: float divide is enough
     kmx = __reduce_max_sync(0xffffffffu, kmx);
     kmn = __reduce_min_sync(0xffffffffu, kmn);
-    const float meanf = (float)mean;
     float pss = 0.f;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) if (lane + 32 * j < n) { const float d = __uint_as_float(key[j]) - meanf; pss += d * d; }
@@ -335,10 +335,10 @@ __device__ __noinline__ void tail_stats_regs(const float* fe, const float* fm, c
     }
     if (lane == 0) {
       float* o = out15 + 5 * q;
-      o[0] = (float)mean;
-      o[1] = (float)sqrt(ss / (double)n);
+      o[0] = meanf;
+      o[1] = sqrtf((float)ss * inv_n);
       o[2] = __uint_as_float(kmx); o[3] = __uint_as_float(kmn);
-      o[4] = (n & 1) ? sel : (float)(((double)sel + (double)sel2) * 0.5);
+      o[4] = (n & 1) ? sel : 0.5f * sel + 0.5f * sel2;
     }
   }
 }
@@ -399,22 +399,45 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
         if (reinterpret_cast<uintptr_t>(src) & 15) n = -1 - n;        // misaligned: not this kernel's layout
       }
       s_desc[useq & (kDescRing - 1)] = make_int2(done ? -1 : (int)u, n);
+      // full 4 KB chunks first (running shared / global addresses, no per-chunk arithmetic), then the last,
+      // possibly partial one
       const int nchunks = n > 0 ? (n + kChunkSamples - 1) / kChunkSamples : 1;
-      for (int c = 0; c < nchunks; ++c) {
-        if (lap > 0) mbar_wait(&bar_empty[slot], (uint32_t)((lap - 1) & 1));
-        unsigned char* dst = s_ring + (size_t)slot * kChunkBytes;
-        const int s0 = c * kChunkSamples;
-        const int cnt = n > 0 ? min(kChunkSamples, n - s0) : 0;
+      const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(src);
+      uint32_t dst32 = smem_u32(s_ring) + (uint32_t)slot * kChunkBytes, full32 = smem_u32(&bar_full[slot]), empty32 = smem_u32(&bar_empty[slot]);
+      auto next_slot = [&]() {
+        dst32 += kChunkBytes; full32 += 8; empty32 += 8;
+        if (++slot == R) { slot = 0; ++lap; dst32 = smem_u32(s_ring); full32 = smem_u32(bar_full); empty32 = smem_u32(bar_empty); }
+      };
+      auto wait_empty = [&]() {
+        if (lap > 0)
+          asm volatile("{\n\t.reg .pred p;\n\tWE_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t@p bra DE_%=;\n\tbra WE_%=;\n\tDE_%=:\n\t}"
+                       ::"r"(empty32), "r"((uint32_t)((lap - 1) & 1)), "r"(0x989680u) : "memory");
+      };
+#pragma unroll 1
+      for (int c = 0; c + 1 < nchunks; ++c) {
+        wait_empty();
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full32), "r"((uint32_t)kChunkBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst32), "l"(gsrc), "r"((uint32_t)kChunkBytes), "r"(full32) : "memory");
+        gsrc += kChunkBytes;
+        next_slot();
+      }
+      {
+        wait_empty();
+        const int s0 = (nchunks - 1) * kChunkSamples;
+        const int cnt = n > 0 ? n - s0 : 0;
         const uint32_t bytes = ((uint32_t)cnt * 2u) & ~15u;
         // tail of < 8 samples by plain loads; the release of the arrive below publishes them
-        for (int i = (int)(bytes >> 1); i < cnt; ++i) reinterpret_cast<int16_t*>(dst)[i] = src[s0 + i];
+        int16_t* dst = reinterpret_cast<int16_t*>(s_ring + (size_t)slot * kChunkBytes);
+        for (int i = (int)(bytes >> 1); i < cnt; ++i) dst[i] = src[s0 + i];
         if (bytes) {
-          mbar_expect_tx(&bar_full[slot], bytes);
-          bulk_g2s(dst, reinterpret_cast<const unsigned char*>(src + s0), bytes, &bar_full[slot]);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full32), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(dst32), "l"(gsrc), "r"(bytes), "r"(full32) : "memory");
         } else {
-          mbar_arrive(&bar_full[slot]);
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full32) : "memory");
         }
-        if (++slot == R) { slot = 0; ++lap; }
+        next_slot();
       }
       ++useq;
       if (done) break;
@@ -525,19 +548,29 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
         // gather the candidates of the bin (ballot compaction into the warp's scratch)
         {
           int base = 0;
-#pragma unroll 1
-          for (int f0 = 0; f0 < f1; f0 += 32) {
-            const int f = f0 + lane;
-            bool in = false;
-            double e = 0.0;
-            if (f < f1) {
-              e = r_e[f];
-              const uint32_t k = __float_as_uint((float)e);
-              in = k >= prefix && (unsigned long long)(k - prefix) < span;
+          if (in_regs) {
+#pragma unroll
+            for (int j = 0; j < kKeyRegs; ++j) {
+              const bool in = key[j] >= prefix && (unsigned long long)(key[j] - prefix) < span && key[j] != 0xffffffffu;
+              const unsigned m = __ballot_sync(0xffffffffu, in);
+              if (in) { const int s = base + __popc(m & ((1u << lane) - 1u)); if (s < 32) cand[s] = r_e[lane + 32 * j]; }
+              base += __popc(m);
             }
-            const unsigned m = __ballot_sync(0xffffffffu, in);
-            if (in) { const int s = base + __popc(m & ((1u << lane) - 1u)); if (s < 32) cand[s] = e; }
-            base += __popc(m);
+          } else {
+#pragma unroll 1
+            for (int f0 = 0; f0 < f1; f0 += 32) {
+              const int f = f0 + lane;
+              bool in = false;
+              double e = 0.0;
+              if (f < f1) {
+                e = r_e[f];
+                const uint32_t k = __float_as_uint((float)e);
+                in = k >= prefix && (unsigned long long)(k - prefix) < span;
+              }
+              const unsigned m = __ballot_sync(0xffffffffu, in);
+              if (in) { const int s = base + __popc(m & ((1u << lane) - 1u)); if (s < 32) cand[s] = e; }
+              base += __popc(m);
+            }
           }
         }
         __syncwarp();
