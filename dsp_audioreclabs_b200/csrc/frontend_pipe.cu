@@ -34,10 +34,24 @@ constexpr int kGroup = 64;                 // samples per group-sum record
 constexpr int kChunkSamples = 2048;        // samples per ring slot
 constexpr int kChunkBytes = 2 * kChunkSamples;
 constexpr int kGroupsPerChunk = kChunkSamples / kGroup;   // 32: one group per stream lane
-constexpr int kStreamWarps = 8;
+#ifndef DSP_PIPE_STREAM_WARPS
+#define DSP_PIPE_STREAM_WARPS 12
+#endif
+constexpr int kStreamWarps = DSP_PIPE_STREAM_WARPS;       // a multiple of 4: whole warpgroups (setmaxnreg)
 constexpr int kMaxTailWarps = 7;
 constexpr int kPipeWarps = kStreamWarps + kMaxTailWarps + 1;
-constexpr int kPipeThreads = 32 * kPipeWarps;             // 512
+constexpr int kPipeThreads = 32 * kPipeWarps;             // 768
+// Register split (setmaxnreg, per warpgroup): the stream warps run short integer loops and give their
+// registers to the tail warps, which keep whole sequences in registers.  The launch allocates
+// kLaunchRegs = 65536 / kPipeThreads registers per thread (rounded down to 8) and the CTA owns only those:
+// setmaxnreg.inc can take no more than the stream warps have given back, or it waits forever.
+constexpr bool kSplitRegs = kStreamWarps > 8;
+constexpr int kLaunchRegs = (65536 / kPipeThreads) & ~7;
+constexpr int kStreamRegs = kStreamWarps == 16 ? 56 : 64;
+constexpr int kTailRegs = ((kLaunchRegs * kPipeThreads - kStreamWarps * 32 * kStreamRegs) / ((kMaxTailWarps + 1) * 32)) & ~7;
+static_assert(kStreamWarps % 4 == 0 && (kMaxTailWarps + 1) % 4 == 0, "roles must cover whole warpgroups");
+static_assert(!kSplitRegs || kStreamWarps * 32 * kStreamRegs + (kMaxTailWarps + 1) * 32 * kTailRegs <= kLaunchRegs * kPipeThreads, "register pool of the CTA");
+static_assert(!kSplitRegs || kTailRegs >= 128, "tail warps keep whole sequences in registers");
 constexpr int kStreamThreads = 32 * kStreamWarps;
 constexpr int kDescRing = 64;              // > max ring slots: the producer can never lap a reader
 constexpr int kMaxRingSlots = 56;
@@ -382,6 +396,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
   // =========================================================================================
   // CONTROL WARP: work distribution + TMA producer
   // =========================================================================================
+  // The two register regimes never meet again: everything inside this branch ends in a return.
+  if (wid >= kStreamWarps) {
+  if constexpr (kSplitRegs) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTailRegs));
   if (wid == kPipeWarps - 1) {
     if (lane != 0) return;
     int slot = 0, lap = 0, useq = 0;
@@ -448,13 +465,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
   // =========================================================================================
   // TAIL WARPS: one warp per utterance record
   // =========================================================================================
-  // warp ids: stream 0..7, tail 8..14, control 15 (the scheduler favours high ids: the latency-bound
+  // warp ids: stream first, then the tail warps, control last (the scheduler favours high ids: the latency-bound
   // tail warps get the issue slots they can use, the throughput-bound stream warps fill the rest)
-#ifndef DSP_PIPE_TAIL_LOW
   const int twid = wid - kStreamWarps;
-#else
-  const int twid = wid;
-#endif
   if (twid >= 0 && twid < kMaxTailWarps) {
     if (twid >= nrec) return;
     unsigned char* rec = smem + L.rec + (size_t)twid * L.rec_bytes;
@@ -738,9 +751,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
               const int nv = valid >> 3;
               const int4* xv = reinterpret_cast<const int4*>(x + p);
               const float4* wv = reinterpret_cast<const float4*>(s_win);
-#pragma unroll 1
-              for (int vq = sub; vq < nv; vq += kLanesPerFrame) {
-                const int4 q = __ldg(xv + vq);
+              // four 16-byte loads in flight per lane (the samples come from L2)
+              auto acc8 = [&](const int4& q, int vq) {
                 const float4 wa = wv[2 * vq], wb = wv[2 * vq + 1];
                 const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
                 const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
@@ -752,7 +764,16 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
                   e = fmaf(alo, alo, e); m += fabsf(alo);
                   e = fmaf(ahi, ahi, e); m += fabsf(ahi);
                 }
+              };
+              int vq = sub;
+#pragma unroll 1
+              for (; vq + 3 * kLanesPerFrame < nv; vq += 4 * kLanesPerFrame) {
+                const int4 q0 = __ldg(xv + vq), q1 = __ldg(xv + vq + kLanesPerFrame);
+                const int4 q2 = __ldg(xv + vq + 2 * kLanesPerFrame), q3 = __ldg(xv + vq + 3 * kLanesPerFrame);
+                acc8(q0, vq); acc8(q1, vq + kLanesPerFrame); acc8(q2, vq + 2 * kLanesPerFrame); acc8(q3, vq + 3 * kLanesPerFrame);
               }
+#pragma unroll 1
+              for (; vq < nv; vq += kLanesPerFrame) { const int4 q = __ldg(xv + vq); acc8(q, vq); }
               jdone = nv << 3;
             }
 #pragma unroll 1
@@ -829,15 +850,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
     if (a.prof && twid == 0 && lane == 0) for (int i = 0; i < 4; ++i) atomicAdd((unsigned long long*)&a.prof[8 + i], (unsigned long long)tp[i]);
     return;
   }
+  return;
+  }   // wid >= kStreamWarps
+  if constexpr (kSplitRegs) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kStreamRegs));
 
   // =========================================================================================
   // STREAM WARPS
   // =========================================================================================
-#ifndef DSP_PIPE_TAIL_LOW
   const int swid = wid, stid = tid;
-#else
-  const int swid = wid - kMaxTailWarps, stid = tid - 32 * kMaxTailWarps;
-#endif
   int useq = 0, cslot = 0, clap = 0, rec_id = 0, rec_lap = 0;
   long long sp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sprev = clock64();
   auto stick = [&](int i) { if (a.prof) { const long long t = clock64(); sp[i] += t - sprev; sprev = t; } };
@@ -890,6 +910,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
         const unsigned char* gp = s_ring + (size_t)s * kChunkBytes + lane * (2 * kGroup);
         int hh = 0, hl = 0, sh = 0;
         uint32_t ll = 0, sl = 0;
+        // fully unrolled on purpose: a compact 2-unit loop (L0-resident, measured) made pass A 8 % faster and the
+        // kernel no faster -- the phases share the SM's issue slots, see DESIGN.md
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int4 q = *reinterpret_cast<const int4*>(gp + 16 * ((j + lane) & 7));   // rotated: conflict-free

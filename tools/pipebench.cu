@@ -31,6 +31,14 @@ __global__ void bench(long long* out, int iters, float seed) {
       if (OP == 11) u[k] = u[k] * cu + u[(k + 1) % K];                       // IMAD
       if (OP == 12) u[k] = __popc(u[k]) + u[(k+1)%K];                        // POPC (+IADD)
       if (OP == 13) f[k] = (float)(int)u[k] + f[k];                          // I2F (+FADD)
+      // mixes: do instructions of different pipes overlap (1 inst/cycle) or share one half-rate dispatch port?
+      if (OP == 14) { if (k & 1) u[k] = (u[k] & cu) ^ u[(k + 1) % K]; else u[k] = u[k] * cu + u[(k + 1) % K]; }                 // LOP3 | IMAD
+      if (OP == 15) { u[k] = (u[k] & cu) ^ u[(k + 1) % K]; f[k] = fmaf(f[k], c, f[k]); }                                        // LOP3 + FFMA
+      if (OP == 16) { if (k & 1) u[k] = __byte_perm(u[k], u[(k + 1) % K], 0x7531); else u[k] = __dp4a((int)u[k], (int)u[(k + 1) % K], (int)u[k]); }  // PRMT | IDP
+      if (OP == 17) { u[k] = u[k] * cu + u[(k + 1) % K]; f[k] = fmaf(f[k], c, f[k]); }                                          // IMAD + FFMA
+      if (OP == 18) { u[k] = __dp4a((int)u[k], (int)u[(k + 1) % K], (int)u[k]); f[k] = fmaf(f[k], c, f[k]); }                   // IDP + FFMA
+      if (OP == 19) { if (k & 1) u[k] = __vimin3_s16x2(u[k], u[(k + 1) % K], cu); else u[k] = __dp4a((int)u[k], (int)u[(k + 1) % K], (int)u[k]); }   // VIMNMX3 | IDP
+      if (OP == 20) { u[k] = (u[k] & cu) ^ u[(k + 1) % K]; f[k] = f[k] + c; }                                                   // LOP3 + FADD
     }
   }
   const long long t1 = clock64();
@@ -53,5 +61,7 @@ int main() {
   run<0>("FFMA", d, 0); run<1>("FFMA2", d, 0); run<2>("FADD2", d, 0); run<3>("LOP3", d, 0); run<4>("PRMT", d, 0);
   run<5>("SHF", d, 0); run<6>("SHFL", d, 0); run<7>("IDP.4A", d, 0); run<8>("VIMNMX3", d, 0); run<9>("IADD", d, 0);
   run<10>("FADD", d, 0); run<11>("IMAD", d, 0); run<12>("POPC+IADD", d, 1); run<13>("I2F+FADD", d, 1);
+  run<14>("LOP3|IMAD", d, 0); run<15>("LOP3+FFMA", d, 1); run<16>("PRMT|IDP", d, 0); run<17>("IMAD+FFMA", d, 1); run<18>("IDP+FFMA", d, 1);
+  run<19>("VIMNMX3|IDP", d, 0); run<20>("LOP3+FADD", d, 1);
   return 0;
 }
