@@ -39,6 +39,13 @@ class FrontendOutputs(C.Structure):
     ]
 
 
+class WavInfo(C.Structure):
+    _fields_ = [
+        ("status", C.c_int32), ("channels", C.c_int32), ("sample_width", C.c_int32), ("sample_rate", C.c_int32),
+        ("n_frames", C.c_int64), ("data_offset", C.c_int64), ("data_bytes", C.c_int64),
+    ]
+
+
 # every symbol include/dspfront.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 _I64 = C.c_int64
@@ -77,6 +84,10 @@ SIGNATURES = {
     "dsp_knn_predict_host": (C.c_int, [_P, _P, _I64, _P]),
     "dsp_knn_predict_device": (C.c_int, [_P, _P, _I64, _P]),
     "dsp_knn_merge_vote_device": (C.c_int, [_P, _P, _P, _P, _I32, _I64, _I32, _P, _P, _P]),
+    "dsp_wav_scan": (C.c_int, [_P, _I64, _I32, _P]),
+    "dsp_wav_read": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _I64]),
+    "dsp_host_alloc": (C.c_int, [_I64, C.POINTER(_P)]),
+    "dsp_host_free": (C.c_int, [_P]),
 }
 
 _lib = None

@@ -1,8 +1,9 @@
 """Batched replacement for the reference's per-file dataset loops:
 `load_dataset` walks the class-per-directory tree exactly like
 experiments/run_experiments.py:64-114 / train_model.py:56-98 (sorted class folders, hidden ones
-skipped, glob('*.wav') per class), but decodes every file first and runs ONE fused front-end
-launch over the whole set instead of one Python call chain per file.  `ablation_sweep` re-runs
+skipped, glob('*.wav') per class), but reads every file first -- natively, into one pinned staging buffer (wavio.py / csrc/wavio.cpp,
+SURVEY 8 f1) -- and runs ONE fused front-end launch over the whole set instead of one Python call
+chain per file.  `ablation_sweep` re-runs
 the front end once per (frame_length, frame_shift) on the samples already decoded, which is
 BASELINE config 4's "one GPU launch per configuration" (ablation_study.py:146-163 re-reads and
 re-processes every WAV for every sweep value)."""
@@ -11,46 +12,69 @@ from glob import glob
 
 import numpy as np
 
-from . import batch
+from . import batch, wavio
 
 FEATURE_NAMES = batch.FEATURE_NAMES
 
 
-def read_wav_pcm(path):
-    """(pcm, sample_rate, channels) with the reference's rules (src/audio_processing.py:21-40)."""
-    import wave
-    with wave.open(path, "rb") as w:
-        ch, width, sr = w.getnchannels(), w.getsampwidth(), w.getframerate()
-        raw = w.readframes(w.getnframes())
-    if width == 1:
-        return np.frombuffer(raw, dtype=np.uint8), sr, ch
-    if width == 2:
-        return np.frombuffer(raw, dtype=np.int16), sr, ch
-    raise ValueError(f"unsupported sample width: {width}")
+def list_tree(data_dir):
+    """-> (paths, labels, class_names): sorted class folders, hidden ones skipped, glob('*.wav') per class
+    (run_experiments.py:64-88, train_model.py:56-72)."""
+    class_names = sorted(d for d in os.listdir(data_dir)
+                         if os.path.isdir(os.path.join(data_dir, d)) and not d.startswith("."))
+    paths, labels = [], []
+    for ci, name in enumerate(class_names):
+        for path in glob(os.path.join(data_dir, name, "*.wav")):
+            paths.append(path)
+            labels.append(ci)
+    return paths, np.array(labels, dtype=np.int64), class_names
+
+
+def decode_tree_packed(data_dir, threads=None):
+    """Native ingest of the whole tree: -> (groups, readable[n], paths, labels, class_names).
+    Headers are parsed and payloads read by the library's thread pool straight into one pinned, 16-byte
+    aligned staging buffer per encoding (wavio.read_packed); files `wave` would refuse, and sample widths
+    load_wav refuses, are dropped like the reference's try/except does (run_experiments.py:109-111)."""
+    paths, labels, class_names = list_tree(data_dir)
+    groups, _info = wavio.read_packed(paths, threads)
+    readable = np.zeros(len(paths), dtype=bool)
+    for g in groups:
+        readable[g.index] = True
+    return groups, readable, paths, labels, class_names
 
 
 def decode_tree(data_dir):
-    """-> (clips [(pcm, channels)], labels, class_names, paths); unreadable files are skipped like the
-    reference's try/except does (run_experiments.py:109-111)."""
-    class_names = sorted(d for d in os.listdir(data_dir)
-                         if os.path.isdir(os.path.join(data_dir, d)) and not d.startswith("."))
-    clips, labels, paths = [], [], []
-    for ci, name in enumerate(class_names):
-        for path in glob(os.path.join(data_dir, name, "*.wav")):
-            try:
-                pcm, _, ch = read_wav_pcm(path)
-            except Exception:
-                continue
-            clips.append((pcm, ch))
-            labels.append(ci)
-            paths.append(path)
-    return clips, np.array(labels, dtype=np.int64), class_names, paths
+    """-> (clips [(pcm, channels)], labels, class_names, paths) of the readable files, as views into the
+    packed staging buffers."""
+    groups, readable, paths, labels, class_names = decode_tree_packed(data_dir)
+    clip_of = {}
+    for g in groups:
+        for j, i in enumerate(g.index):
+            clip_of[int(i)] = (g.clip(j), g.channels)
+    keep = [i for i in range(len(paths)) if readable[i]]
+    return [clip_of[i] for i in keep], labels[keep], class_names, [paths[i] for i in keep]
+
+
+def features_for_groups(groups, n_files, frame_length, frame_shift, window_type="hamming", do_endpoint_detection=True,
+                        energy_high_ratio=0.5, energy_low_ratio=0.1, zcr_threshold_ratio=1.5, ctx=None):
+    """15-dim statistical features of every packed file: ONE launch per encoding group, straight from the
+    staging buffer (no per-file arrays, no re-packing).  Returns (X[n_files,15] float64, ok[n_files])."""
+    X = np.zeros((n_files, 15), dtype=np.float64)
+    ok = np.zeros(n_files, dtype=bool)
+    for g in groups:
+        if not len(g.index):
+            continue
+        res = batch.frontend_batch(g.samples, g.offsets, frame_length, frame_shift, window_type, do_endpoint_detection,
+                                   energy_high_ratio, energy_low_ratio, zcr_threshold_ratio, channels=g.channels,
+                                   emit_frames=False, lengths=g.lengths, ctx=ctx)
+        X[g.index] = res.stats
+        ok[g.index] = (res.status & 0xff) == 0
+    return X, ok
 
 
 def features_for_clips(clips, frame_length, frame_shift, window_type="hamming", do_endpoint_detection=True,
                        energy_high_ratio=0.5, energy_low_ratio=0.1, zcr_threshold_ratio=1.5, ctx=None):
-    """15-dim statistical features of every clip: one launch per (dtype, channels) group (16-bit mono
-    files -- the normal case -- all go through the fused int16 kernel).  Returns (X[n,15] float64, ok[n])."""
+    """The same for clips already in memory [(pcm, channels)]: packed here, one launch per (dtype, channels)."""
     n = len(clips)
     X = np.zeros((n, 15), dtype=np.float64)
     ok = np.zeros(n, dtype=bool)
@@ -62,9 +86,8 @@ def features_for_clips(clips, frame_length, frame_shift, window_type="hamming", 
         res = batch.frontend_batch(samples, offsets, frame_length, frame_shift, window_type, do_endpoint_detection,
                                    energy_high_ratio, energy_low_ratio, zcr_threshold_ratio, channels=ch,
                                    emit_frames=False, lengths=lengths, ctx=ctx)
-        good = (res.status & 0xff) == 0
         X[idx] = res.stats
-        ok[idx] = good
+        ok[idx] = (res.status & 0xff) == 0
     return X, ok
 
 
@@ -72,18 +95,18 @@ def load_dataset(data_dir, frame_length, frame_shift, window_type="hamming", do_
                  energy_high_ratio=0.5, energy_low_ratio=0.1, zcr_threshold_ratio=1.5, ctx=None):
     """-> (X, y, class_names, feature_names): what SpeechRecognitionExperiment.load_dataset /
     train_model.load_dataset build, with failed files dropped."""
-    clips, labels, class_names, _ = decode_tree(data_dir)
-    X, ok = features_for_clips(clips, frame_length, frame_shift, window_type, do_endpoint_detection,
-                               energy_high_ratio, energy_low_ratio, zcr_threshold_ratio, ctx)
+    groups, _readable, paths, labels, class_names = decode_tree_packed(data_dir)
+    X, ok = features_for_groups(groups, len(paths), frame_length, frame_shift, window_type, do_endpoint_detection,
+                                energy_high_ratio, energy_low_ratio, zcr_threshold_ratio, ctx)
     return X[ok], labels[ok], class_names, list(FEATURE_NAMES)
 
 
 def ablation_sweep(data_dir, frame_configs, window_type="hamming", sample_rate=44100, ctx=None, **kw):
     """{(frame_length, frame_shift): (X, y)} for each configuration, decoding the WAVs once.
     `frame_configs` are sample counts, e.g. int(sample_rate * ms / 1000) as train_model.py:45-46."""
-    clips, labels, class_names, _ = decode_tree(data_dir)
+    groups, _readable, paths, labels, class_names = decode_tree_packed(data_dir)
     out = {}
     for fl, fs in frame_configs:
-        X, ok = features_for_clips(clips, int(fl), int(fs), window_type, ctx=ctx, **kw)
+        X, ok = features_for_groups(groups, len(paths), int(fl), int(fs), window_type, ctx=ctx, **kw)
         out[(int(fl), int(fs))] = (X[ok], labels[ok])
     return out, class_names

@@ -5,11 +5,9 @@ Every function cites the reference lines it stands in for.  `process_audio_file`
 16-bit PCM as integers and uses the fused kernel; the per-call functions on float arrays use
 the float64 replay kernel, which restates NumPy's operation order and is bit-identical to it.
 """
-import wave
-
 import numpy as np
 
-from dsp_audioreclabs_b200 import batch as _b
+from dsp_audioreclabs_b200 import batch as _b, wavio as _wavio
 
 
 class FrameArray(np.ndarray):
@@ -26,20 +24,10 @@ class FrameArray(np.ndarray):
 
 
 def read_wav_pcm(filepath):
-    """WAV -> (pcm array as stored, sample_rate, n_channels).  Same `wave` calls and the same
-    ValueError for other sample widths as load_wav (src/audio_processing.py:21-40)."""
-    with wave.open(filepath, 'rb') as wav_file:
-        n_channels = wav_file.getnchannels()
-        sample_width = wav_file.getsampwidth()
-        sample_rate = wav_file.getframerate()
-        audio_bytes = wav_file.readframes(wav_file.getnframes())
-    if sample_width == 1:
-        pcm = np.frombuffer(audio_bytes, dtype=np.uint8)
-    elif sample_width == 2:
-        pcm = np.frombuffer(audio_bytes, dtype=np.int16)
-    else:
-        raise ValueError(f"不支持的采样位数: {sample_width}")
-    return pcm, sample_rate, n_channels
+    """WAV -> (pcm array as stored, sample_rate, n_channels): the library's native chunk walk
+    (csrc/wavio.cpp), which accepts and rejects what `wave.open` does, and the same ValueError
+    for other sample widths as load_wav (src/audio_processing.py:21-40)."""
+    return _wavio.read_wav_pcm(filepath)
 
 
 def load_wav(filepath):

@@ -204,6 +204,47 @@ int dsp_knn_merge_vote_device(dsp_context* ctx, const double* cand_sqdist, const
                               const int32_t* cand_label, int32_t n_lists, int64_t m, int32_t k,
                               int32_t* labels_out, int64_t* nbr_idx_out, double* nbr_sqdist_out);
 
+/* ---- batched WAV ingest ----------------------------------
+ * Replaces the per-file `wave.open` / `readframes` / `np.frombuffer` of load_wav
+ * (src/audio_processing.py:21-40) for whole file lists.  Host-only I/O: no CUDA device is
+ * needed for dsp_wav_scan / dsp_wav_read.  The chunk walk accepts and rejects what CPython's
+ * `wave` module does; dsp_wav_info.status says why a file was refused (the callers of the
+ * reference skip such files, run_experiments.py:109-111).  Sample widths other than 1 and 2
+ * parse fine and are refused by the caller like load_wav does (ValueError, :39-40). */
+typedef enum {
+  DSP_WAV_OK = 0,
+  DSP_WAV_ERR_OPEN = 1,      /* cannot open / stat the file */
+  DSP_WAV_ERR_NOT_RIFF = 2,  /* wave.Error: file does not start with RIFF id */
+  DSP_WAV_ERR_NOT_WAVE = 3,  /* wave.Error: not a WAVE file */
+  DSP_WAV_ERR_FORMAT = 4,    /* wave.Error: unknown format / unknown extended format */
+  DSP_WAV_ERR_WIDTH = 5,     /* wave.Error: bad sample width */
+  DSP_WAV_ERR_CHANNELS = 6,  /* wave.Error: bad # of channels */
+  DSP_WAV_ERR_ORDER = 7,     /* wave.Error: data chunk before fmt chunk */
+  DSP_WAV_ERR_MISSING = 8,   /* wave.Error: fmt chunk and/or data chunk missing */
+  DSP_WAV_ERR_TRUNCATED = 9  /* EOFError inside the fmt chunk, or the payload could not be read */
+} dsp_wav_status;
+
+typedef struct {
+  int32_t status;        /* dsp_wav_status */
+  int32_t channels;      /* getnchannels() */
+  int32_t sample_width;  /* getsampwidth(), bytes */
+  int32_t sample_rate;   /* getframerate() */
+  int64_t n_frames;      /* getnframes() */
+  int64_t data_offset;   /* file offset of the PCM payload */
+  int64_t data_bytes;    /* len(readframes(getnframes())): what the file really holds */
+} dsp_wav_info;
+
+/* Parse the headers of n_files files with `threads` host threads. */
+int dsp_wav_scan(const char* const* paths, int64_t n_files, int32_t threads, dsp_wav_info* info);
+/* Read the PCM payload of every file with status DSP_WAV_OK to dst + dst_byte_offsets[i]
+ * (data_bytes[i] bytes each, as stored: little-endian int16 / uint8, interleaved channels).
+ * dst is normally pinned memory from dsp_host_alloc, laid out for dsp_frontend_batch_host. */
+int dsp_wav_read(const char* const* paths, int64_t n_files, int32_t threads, dsp_wav_info* info,
+                 const int64_t* dst_byte_offsets, void* dst, int64_t dst_bytes);
+/* Page-locked host memory for staging buffers (cudaHostAlloc / cudaFreeHost). */
+int dsp_host_alloc(int64_t bytes, void** out);
+int dsp_host_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif
