@@ -83,6 +83,7 @@ SIGNATURES = {
     "dsp_knn_topk_device": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
     "dsp_knn_predict_host": (C.c_int, [_P, _P, _I64, _P]),
     "dsp_knn_predict_device": (C.c_int, [_P, _P, _I64, _P]),
+    "dsp_knn_last_stats": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I32)]),
     "dsp_knn_merge_vote_device": (C.c_int, [_P, _P, _P, _P, _I32, _I64, _I32, _P, _P, _P]),
     "dsp_wav_scan": (C.c_int, [_P, _I64, _I32, _P]),
     "dsp_wav_read": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _I64]),

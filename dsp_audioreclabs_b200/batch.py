@@ -329,6 +329,13 @@ class KNN:
         check(self.ctx.lib.dsp_knn_predict_host(self.handle, _ptr(Q), Q.shape[0], _ptr(out)))
         return self.classes_[out]
 
+    def last_stats(self):
+        """(queries rescanned in float64, scan kind) of the last kneighbors / predict call: 0 float64 only,
+        1 fp32 tiled scan, 2 tensor-core scan."""
+        n, kind = C.c_int64(), C.c_int32()
+        check(self.ctx.lib.dsp_knn_last_stats(self.handle, C.byref(n), C.byref(kind)))
+        return int(n.value), int(kind.value)
+
     def _free(self):
         if self.handle:
             self.ctx.lib.dsp_knn_free(self.handle)

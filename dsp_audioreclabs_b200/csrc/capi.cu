@@ -71,6 +71,8 @@ struct PinBuf {
 
 constexpr size_t kMaxSmemPerCta = 227 * 1024;
 constexpr int64_t kFastMaxLen = 1 << 20;          // exact-integer bounds of the fast kernel
+constexpr int kKnnDenseMaxDim = 16384;            // feature dimensions served by the tensor-core scan
+constexpr int64_t kKnnDenseQueryChunk = 32768;    // queries packed per scan launch
 constexpr size_t kHostChunkBytes = 96u << 20;     // samples per staged chunk of the host pipeline
 
 size_t dtype_size(int dtype) {
@@ -116,7 +118,9 @@ struct dsp_knn {
   int64_t n = 0, index_base = 0;
   int d = 0, dp = 0, k = 0;
   float tnorm_max = 0.f;
+  bool dense = false;          // tensor-core candidate scan (knn_dense.cu): feature dimension beyond the tiled scan
   DevBuf train64, train32, labels, tnorm, cand_idx, cand_worst, qnorm, redo_list, redo_count, nbr_label, q, o_idx, o_dist, o_lab;
+  DevBuf tpacked, tnorm_dense, qpacked, qnorm_chunk, dense_flags;
 };
 
 namespace {
@@ -768,7 +772,8 @@ int dsp_zscore_host(dsp_context* c, const double* x, int64_t n, int32_t d, int f
 // ---- KNN ----------------------------------------------------------------------------------------
 static void knn_release(dsp_knn* k) {
   DevBuf* all[] = {&k->train64, &k->train32, &k->labels, &k->tnorm, &k->cand_idx, &k->cand_worst, &k->qnorm,
-                   &k->redo_list, &k->redo_count, &k->nbr_label, &k->q, &k->o_idx, &k->o_dist, &k->o_lab};
+                   &k->redo_list, &k->redo_count, &k->nbr_label, &k->q, &k->o_idx, &k->o_dist, &k->o_lab,
+                   &k->tpacked, &k->tnorm_dense, &k->qpacked, &k->qnorm_chunk, &k->dense_flags};
   for (DevBuf* b : all) b->release();
 }
 
@@ -793,8 +798,25 @@ int dsp_knn_fit_device(dsp_context* c, const double* train, const int32_t* label
     if (e != cudaSuccess) return bail(fail(DSP_ERR_CUDA, "knn_pack: %s", cudaGetErrorString(e)));
     cudaMemcpyAsync(&h->tnorm_max, h->tnorm.p, sizeof(float), cudaMemcpyDeviceToHost, c->stream);
   }
+  int dense_flags[2] = {0, 0};
+  if (!h->dp && d <= kKnnDenseMaxDim && std::getenv("DSP_KNN_NO_DENSE") == nullptr) {
+    // sequence-feature sizes (compare_feature_methods.py:106-123): split-fp16 operands in tensor-core tile order
+    if (h->tpacked.ensure(knn_dense_packed_bytes(n, d)) != cudaSuccess ||
+        h->tnorm_dense.ensure(sizeof(float) * (size_t)knn_dense_row_blocks(n) * 128) != cudaSuccess ||
+        h->dense_flags.ensure(64) != cudaSuccess)
+      return bail(fail(DSP_ERR_NOMEM, "device allocation failed"));
+    cudaError_t e = knn_dense_pack(h->train64.as<double>(), n, d, h->tpacked.p, h->tnorm_dense.as<float>(), INFINITY,
+                                   h->dense_flags.as<int>(), c->stream);
+    c->launches++;
+    if (e != cudaSuccess) return bail(fail(DSP_ERR_CUDA, "knn_dense_pack: %s", cudaGetErrorString(e)));
+    cudaMemcpyAsync(dense_flags, h->dense_flags.p, sizeof dense_flags, cudaMemcpyDeviceToHost, c->stream);
+  }
   cudaError_t e = cudaStreamSynchronize(c->stream);
   if (e != cudaSuccess) return bail(fail(DSP_ERR_CUDA, "knn fit: %s", cudaGetErrorString(e)));
+  if (h->tpacked.p) {
+    std::memcpy(&h->tnorm_max, &dense_flags[0], sizeof(float));
+    h->dense = dense_flags[1] == 0;          // a value outside the fp16 range: every query takes the float64 scan instead
+  }
   *out = h;
   return DSP_OK;
 }
@@ -836,11 +858,44 @@ int dsp_knn_topk_device(dsp_knn* h, const double* q, int64_t m, int64_t* nbr_idx
                 h->qnorm.as<float>(), c->stream));
     CU(knn_rerank(h->train64.as<double>(), h->train32.as<float>(), h->dp, h->n, q, m, h->d, h->k, h->index_base,
                   h->labels.as<int32_t>(), h->cand_idx.as<int>(), h->cand_worst.as<float>(), h->qnorm.as<float>(),
-                  h->tnorm_max, nbr_idx, nbr_sqdist, nbr_label, h->redo_list.as<int32_t>(),
+                  h->tnorm_max, (double)(h->d + 4) * 1.1920929e-7, nbr_idx, nbr_sqdist, nbr_label, h->redo_list.as<int32_t>(),
                   h->redo_count.as<int32_t>(), c->stream));
     c->launches += 2;
+  } else if (h->dense) {
+    // tensor-core candidate scan in chunks of queries (bounded staging), float64 rerank + certificate per chunk;
+    // the rejected queries of every chunk accumulate in one redo list
+    CU(h->cand_idx.ensure(sizeof(int) * (size_t)m * kKnnCand));
+    CU(h->cand_worst.ensure(sizeof(float) * (size_t)m));
+    CU(h->qnorm.ensure(sizeof(float) * (size_t)m));
+    const int64_t chunk = std::min<int64_t>(m, kKnnDenseQueryChunk);
+    CU(h->qpacked.ensure(knn_dense_packed_bytes(chunk, h->d)));
+    CU(h->dense_flags.ensure(64));
+    bool all_fit = true;
+    for (int64_t q0 = 0; q0 < m && all_fit; q0 += chunk) {
+      const int64_t mc = std::min<int64_t>(chunk, m - q0);
+      // the pack kernel writes a norm for every padded row of the chunk: staged, then copied to the queries' slots
+      CU(h->qnorm_chunk.ensure(sizeof(float) * (size_t)knn_dense_row_blocks(mc) * 128));
+      CU(knn_dense_pack(q + q0 * h->d, mc, h->d, h->qpacked.p, h->qnorm_chunk.as<float>(), 0.f, h->dense_flags.as<int>(), c->stream));
+      CU(cudaMemcpyAsync(h->qnorm.as<float>() + q0, h->qnorm_chunk.p, sizeof(float) * (size_t)mc, cudaMemcpyDeviceToDevice, c->stream));
+      int qflags[2];
+      CU(cudaMemcpyAsync(qflags, h->dense_flags.p, sizeof qflags, cudaMemcpyDeviceToHost, c->stream));
+      CU(knn_dense_scan(h->qpacked.p, h->tpacked.p, h->tnorm_dense.as<float>(), mc, h->n, h->d,
+                        h->cand_idx.as<int>() + q0 * kKnnCand, h->cand_worst.as<float>() + q0, c->sm_count, c->stream));
+      c->launches += 2;
+      CU(cudaStreamSynchronize(c->stream));
+      if (qflags[1]) all_fit = false;        // a query value outside the fp16 range: float64 scan for everything
+    }
+    if (all_fit) {
+      CU(knn_rerank(h->train64.as<double>(), nullptr, 0, h->n, q, m, h->d, h->k, h->index_base,
+                    h->labels.as<int32_t>(), h->cand_idx.as<int>(), h->cand_worst.as<float>(), h->qnorm.as<float>(),
+                    h->tnorm_max, knn_dense_err_rel(h->d), nbr_idx, nbr_sqdist, nbr_label, h->redo_list.as<int32_t>(),
+                    h->redo_count.as<int32_t>(), c->stream));
+    } else {
+      CU(knn_redo_all(h->redo_list.as<int32_t>(), h->redo_count.as<int32_t>(), m, c->stream));
+    }
+    c->launches++;
   } else {
-    // feature dimension beyond the tiled scan: exhaustive float64 scan of every query
+    // feature dimension beyond both scans (or values outside the fp16 range): exhaustive float64 scan of every query
     CU(knn_redo_all(h->redo_list.as<int32_t>(), h->redo_count.as<int32_t>(), m, c->stream));
     c->launches++;
   }
@@ -848,6 +903,19 @@ int dsp_knn_topk_device(dsp_knn* h, const double* q, int64_t m, int64_t* nbr_idx
                 h->redo_list.as<int32_t>(), h->redo_count.as<int32_t>(), nbr_idx, nbr_sqdist, nbr_label,
                 c->sm_count, c->stream));
   c->launches++;
+  return DSP_OK;
+}
+
+int dsp_knn_last_stats(dsp_knn* h, int64_t* rescanned, int32_t* scan_kind) {
+  if (!h) return fail(DSP_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(h->ctx->device));
+  int32_t cnt = 0;
+  if (h->redo_count.p) {
+    CU(cudaMemcpyAsync(&cnt, h->redo_count.p, sizeof cnt, cudaMemcpyDeviceToHost, h->ctx->stream));
+    CU(cudaStreamSynchronize(h->ctx->stream));
+  }
+  if (rescanned) *rescanned = cnt;
+  if (scan_kind) *scan_kind = h->dp ? 1 : (h->dense ? 2 : 0);
   return DSP_OK;
 }
 

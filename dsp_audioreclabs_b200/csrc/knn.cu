@@ -122,7 +122,7 @@ __global__ void knn_rerank_kernel(const double* __restrict__ train, const float*
                                   int dp, int64_t n, const double* __restrict__ queries, int64_t m,
                                   int d, int k, int64_t index_base, const int32_t* __restrict__ labels,
                                   const int* __restrict__ cand_idx, const float* __restrict__ cand_worst,
-                                  const float* __restrict__ qnorm, float tnorm_max,
+                                  const float* __restrict__ qnorm, float tnorm_max, double err_rel,
                                   int64_t* __restrict__ nbr_idx, double* __restrict__ nbr_sqdist,
                                   int32_t* __restrict__ nbr_label, int32_t* __restrict__ redo_list,
                                   int32_t* __restrict__ redo_count) {
@@ -148,7 +148,7 @@ __global__ void knn_rerank_kernel(const double* __restrict__ train, const float*
     // |t|^2 - 2 q.t + |q|^2: (d+2) roundings on terms bounded by (|q| + |t|)^2.
     const float qn = qnorm[qi];
     const double bound = (double)(sqrtf(qn) + sqrtf(tnorm_max));
-    const double err = (double)(d + 4) * 1.1920929e-7 * bound * bound;
+    const double err = err_rel * bound * bound;
     const double lower = (double)cand_worst[qi] + (double)qn - err;
     ok = cd[kk - 1] < lower;
   }
@@ -331,12 +331,12 @@ cudaError_t knn_scan(int dp, const float* train32, int64_t n, const double* q, i
 cudaError_t knn_rerank(const double* train, const float* train32, int dp, int64_t n, const double* q,
                        int64_t m, int d, int k, int64_t index_base, const int32_t* labels,
                        const int* cand_idx, const float* cand_worst, const float* qnorm,
-                       float tnorm_max_host, int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label,
+                       float tnorm_max_host, double err_rel, int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label,
                        int32_t* redo_list, int32_t* redo_count, cudaStream_t st) {
   if (m == 0) return cudaSuccess;
   cudaMemsetAsync(redo_count, 0, sizeof(int32_t), st);
   knn_rerank_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(
-      train, train32, dp, n, q, m, d, k, index_base, labels, cand_idx, cand_worst, qnorm, tnorm_max_host,
+      train, train32, dp, n, q, m, d, k, index_base, labels, cand_idx, cand_worst, qnorm, tnorm_max_host, err_rel,
       nbr_idx, nbr_sqdist, nbr_label, redo_list, redo_count);
   return cudaGetLastError();
 }

@@ -16,7 +16,7 @@ cudaError_t knn_scan(int dp, const float* train32, int64_t n, const double* q, i
 cudaError_t knn_rerank(const double* train, const float* train32, int dp, int64_t n, const double* q,
                        int64_t m, int d, int k, int64_t index_base, const int32_t* labels,
                        const int* cand_idx, const float* cand_worst, const float* qnorm,
-                       float tnorm_max_host, int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label,
+                       float tnorm_max_host, double err_rel, int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label,
                        int32_t* redo_list, int32_t* redo_count, cudaStream_t st);
 cudaError_t knn_redo_all(int32_t* redo_list, int32_t* redo_count, int64_t m, cudaStream_t st);
 cudaError_t knn_rescan(const double* train, int64_t n, const double* q, int d, int k, int64_t index_base,
@@ -27,5 +27,18 @@ cudaError_t knn_vote(const int32_t* nbr_label, int64_t m, int k, int32_t* out, c
 cudaError_t knn_merge_vote(const double* cd, const int64_t* ci, const int32_t* cl, int r, int64_t m,
                            int k, int32_t* labels_out, int64_t* idx_out, double* dist_out,
                            cudaStream_t st);
+
+// knn_dense.cu: tensor-core candidate scan for feature dimensions beyond the tiled scan (sequence features, D = 2 * max_len)
+int knn_dense_kblocks(int d);
+int64_t knn_dense_row_blocks(int64_t rows);
+size_t knn_dense_packed_bytes(int64_t rows, int d);
+// flags[0] = max |x|^2 as float bits, flags[1] = 1 when a value does not fit fp16 (caller falls back to the float64 scan)
+cudaError_t knn_dense_pack(const double* x, int64_t rows, int d, void* packed, float* norms, float pad_norm, int* flags,
+                           cudaStream_t st);
+cudaError_t knn_dense_scan(const void* qpacked, const void* tpacked, const float* tnorm, int64_t m, int64_t n, int d,
+                           int* cand_idx, float* cand_worst, int sm_count, cudaStream_t st);
+// bound on |score_scan - score_exact| / (|q| + |t|max)^2 for the split-fp16 tensor-core evaluation: 3 * D / 16 fp32
+// accumulations of K = 16 partial sums, the dropped lo*lo term, the fp32 norms and the final multiply-add
+inline double knn_dense_err_rel(int d) { return (3.0 * d / 16.0 + 32.0) * 2.384185791015625e-07; }
 
 }  // namespace dsp

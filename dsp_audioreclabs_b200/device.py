@@ -134,6 +134,13 @@ class DeviceKNN:
         check(self.ctx.lib.dsp_knn_predict_device(self.handle, _dp(queries), queries.shape[0], _dp(out)))
         return out
 
+    def last_stats(self):
+        """(queries rescanned in float64, scan kind: 0 float64 only / 1 fp32 tiled / 2 tensor cores) of the last call."""
+        import ctypes as C
+        n, kind = C.c_int64(), C.c_int32()
+        check(self.ctx.lib.dsp_knn_last_stats(self.handle, C.byref(n), C.byref(kind)))
+        return int(n.value), int(kind.value)
+
     def merge_vote(self, cand_d2, cand_idx, cand_lab):
         """[R, m, k] candidate lists (e.g. all-gathered from R row shards) -> labels, idx, d2."""
         self._stream()

@@ -197,6 +197,10 @@ int dsp_knn_topk_device(dsp_knn* knn, const double* queries, int64_t m, int64_t*
                         double* nbr_sqdist, int32_t* nbr_label);
 /* predict = topk + majority vote, vote ties to the smallest label. */
 int dsp_knn_predict_host(dsp_knn* knn, const double* queries, int64_t m, int32_t* labels_out);
+/* Diagnostics of the last topk / predict call on this handle (waits for it): how many queries the
+ * float64 certificate sent to the exhaustive float64 rescan, and which candidate scan ran
+ * (0 = none: float64 only, 1 = fp32 tiled scan, 2 = tensor-core scan).  Results never depend on it. */
+int dsp_knn_last_stats(dsp_knn* knn, int64_t* rescanned, int32_t* scan_kind);
 int dsp_knn_predict_device(dsp_knn* knn, const double* queries, int64_t m, int32_t* labels_out);
 /* Merge R candidate lists (as gathered from R row shards, layout [R,m,k]) into the global
  * top-k and vote.  Device pointers. */

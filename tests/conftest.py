@@ -26,6 +26,12 @@ def golden_knn():
 
 
 @pytest.fixture(scope="session")
+def golden_seq():
+    """Sequence-feature KNN of compare_feature_methods.py, captured from the reference (oracle/gen_golden_seq.py)."""
+    return np.load(os.path.join(GOLDEN, "knn_seq_golden.npz"))
+
+
+@pytest.fixture(scope="session")
 def ctx():
     """CUDA context of the product library; fails loudly (no CPU fallback) without a GPU."""
     from dsp_audioreclabs_b200 import batch

@@ -128,3 +128,19 @@ def test_knn_merge_of_row_shards_equals_single_rank(golden_knn):
         mi, md = ko.merge_candidates(np.stack(cd), np.stack(ci), 3)
         assert np.array_equal(mi, ref_idx) and np.array_equal(md, ref_d)
         assert np.array_equal(ko.vote(y[mi], np.unique(y)), k["d15/pred"][:100])
+
+
+def test_sequence_knn_fixture_matches_the_oracle(golden_seq):
+    """compare_feature_methods.py's sequence variant (sklearn brute force, D = 76 / 258 / 105): the oracle's
+    neighbours, distances and votes equal the reference's; the sequence assembly restates :106-123."""
+    from oracle import frontend_oracle as fo, knn_oracle as ko
+    g = golden_seq
+    for tag in ("seq_default", "seq_256", "seq3_default"):
+        assert str(g[f"{tag}/fit_method"]) == "brute"
+        xn, mu, sd = fo.zscore(g[f"{tag}/train"])
+        qn, _, _ = fo.zscore(g[f"{tag}/query"], mu, sd)
+        assert np.array_equal(xn, g[f"{tag}/train_norm"]) and np.array_equal(qn, g[f"{tag}/query_norm"])
+        idx, d2 = ko.knn_topk(xn, qn, 3)
+        assert np.array_equal(idx, g[f"{tag}/nbr_idx"])
+        assert np.allclose(np.sqrt(d2), g[f"{tag}/nbr_dist"], rtol=1e-12, atol=0)
+        assert np.array_equal(ko.knn_predict(xn, g[f"{tag}/train_labels"], qn, 3), g[f"{tag}/pred"])
