@@ -120,7 +120,7 @@ struct dsp_knn {
   float tnorm_max = 0.f;
   bool dense = false;          // tensor-core candidate scan (knn_dense.cu): feature dimension beyond the tiled scan
   DevBuf train64, train32, labels, tnorm, cand_idx, cand_worst, qnorm, redo_list, redo_count, nbr_label, q, o_idx, o_dist, o_lab;
-  DevBuf tpacked, tnorm_dense, qpacked, qnorm_chunk, dense_flags;
+  DevBuf tpacked, tnorm_dense, qpacked, qnorm_chunk, dense_flags, part_d, part_i;
 };
 
 namespace {
@@ -773,7 +773,7 @@ int dsp_zscore_host(dsp_context* c, const double* x, int64_t n, int32_t d, int f
 static void knn_release(dsp_knn* k) {
   DevBuf* all[] = {&k->train64, &k->train32, &k->labels, &k->tnorm, &k->cand_idx, &k->cand_worst, &k->qnorm,
                    &k->redo_list, &k->redo_count, &k->nbr_label, &k->q, &k->o_idx, &k->o_dist, &k->o_lab,
-                   &k->tpacked, &k->tnorm_dense, &k->qpacked, &k->qnorm_chunk, &k->dense_flags};
+                   &k->tpacked, &k->tnorm_dense, &k->qpacked, &k->qnorm_chunk, &k->dense_flags, &k->part_d, &k->part_i};
   for (DevBuf* b : all) b->release();
 }
 
@@ -801,12 +801,12 @@ int dsp_knn_fit_device(dsp_context* c, const double* train, const int32_t* label
   int dense_flags[2] = {0, 0};
   if (!h->dp && d <= kKnnDenseMaxDim && std::getenv("DSP_KNN_NO_DENSE") == nullptr) {
     // sequence-feature sizes (compare_feature_methods.py:106-123): split-fp16 operands in tensor-core tile order
-    if (h->tpacked.ensure(knn_dense_packed_bytes(n, d)) != cudaSuccess ||
-        h->tnorm_dense.ensure(sizeof(float) * (size_t)knn_dense_row_blocks(n) * 128) != cudaSuccess ||
+    if (h->tpacked.ensure(knn_dense_packed_bytes(n, d, true)) != cudaSuccess ||
+        h->tnorm_dense.ensure(sizeof(float) * (size_t)knn_dense_padded_rows(n, true)) != cudaSuccess ||
         h->dense_flags.ensure(64) != cudaSuccess)
       return bail(fail(DSP_ERR_NOMEM, "device allocation failed"));
-    cudaError_t e = knn_dense_pack(h->train64.as<double>(), n, d, h->tpacked.p, h->tnorm_dense.as<float>(), INFINITY,
-                                   h->dense_flags.as<int>(), c->stream);
+    cudaError_t e = knn_dense_pack(h->train64.as<double>(), n, d, true, h->tpacked.p, h->tnorm_dense.as<float>(), INFINITY,
+                                   h->dense_flags.as<int>(), true, c->stream);
     c->launches++;
     if (e != cudaSuccess) return bail(fail(DSP_ERR_CUDA, "knn_dense_pack: %s", cudaGetErrorString(e)));
     cudaMemcpyAsync(dense_flags, h->dense_flags.p, sizeof dense_flags, cudaMemcpyDeviceToHost, c->stream);
@@ -868,23 +868,24 @@ int dsp_knn_topk_device(dsp_knn* h, const double* q, int64_t m, int64_t* nbr_idx
     CU(h->cand_worst.ensure(sizeof(float) * (size_t)m));
     CU(h->qnorm.ensure(sizeof(float) * (size_t)m));
     const int64_t chunk = std::min<int64_t>(m, kKnnDenseQueryChunk);
-    CU(h->qpacked.ensure(knn_dense_packed_bytes(chunk, h->d)));
+    CU(h->qpacked.ensure(knn_dense_packed_bytes(chunk, h->d, false)));
+    CU(h->qnorm_chunk.ensure(sizeof(float) * (size_t)knn_dense_padded_rows(chunk, false)));
     CU(h->dense_flags.ensure(64));
-    bool all_fit = true;
-    for (int64_t q0 = 0; q0 < m && all_fit; q0 += chunk) {
+    for (int64_t q0 = 0; q0 < m; q0 += chunk) {
       const int64_t mc = std::min<int64_t>(chunk, m - q0);
-      // the pack kernel writes a norm for every padded row of the chunk: staged, then copied to the queries' slots
-      CU(h->qnorm_chunk.ensure(sizeof(float) * (size_t)knn_dense_row_blocks(mc) * 128));
-      CU(knn_dense_pack(q + q0 * h->d, mc, h->d, h->qpacked.p, h->qnorm_chunk.as<float>(), 0.f, h->dense_flags.as<int>(), c->stream));
+      // the pack kernel writes a norm for every padded row of the chunk: staged, then copied to the queries' slots;
+      // the fp16-range flag accumulates over the chunks and is read once (stream order keeps the staging safe)
+      CU(knn_dense_pack(q + q0 * h->d, mc, h->d, false, h->qpacked.p, h->qnorm_chunk.as<float>(), 0.f, h->dense_flags.as<int>(),
+                        q0 == 0, c->stream));
       CU(cudaMemcpyAsync(h->qnorm.as<float>() + q0, h->qnorm_chunk.p, sizeof(float) * (size_t)mc, cudaMemcpyDeviceToDevice, c->stream));
-      int qflags[2];
-      CU(cudaMemcpyAsync(qflags, h->dense_flags.p, sizeof qflags, cudaMemcpyDeviceToHost, c->stream));
       CU(knn_dense_scan(h->qpacked.p, h->tpacked.p, h->tnorm_dense.as<float>(), mc, h->n, h->d,
                         h->cand_idx.as<int>() + q0 * kKnnCand, h->cand_worst.as<float>() + q0, c->sm_count, c->stream));
       c->launches += 2;
-      CU(cudaStreamSynchronize(c->stream));
-      if (qflags[1]) all_fit = false;        // a query value outside the fp16 range: float64 scan for everything
     }
+    int qflags[2] = {0, 0};
+    CU(cudaMemcpyAsync(qflags, h->dense_flags.p, sizeof qflags, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const bool all_fit = qflags[1] == 0;     // a query value outside the fp16 range: float64 scan for everything
     if (all_fit) {
       CU(knn_rerank(h->train64.as<double>(), nullptr, 0, h->n, q, m, h->d, h->k, h->index_base,
                     h->labels.as<int32_t>(), h->cand_idx.as<int>(), h->cand_worst.as<float>(), h->qnorm.as<float>(),
@@ -899,9 +900,13 @@ int dsp_knn_topk_device(dsp_knn* h, const double* q, int64_t m, int64_t* nbr_idx
     CU(knn_redo_all(h->redo_list.as<int32_t>(), h->redo_count.as<int32_t>(), m, c->stream));
     c->launches++;
   }
+  if (h->d > 64) {
+    CU(h->part_d.ensure(sizeof(double) * (size_t)knn_rescan_grid(c->sm_count) * kKnnMaxK));
+    CU(h->part_i.ensure(sizeof(long long) * (size_t)knn_rescan_grid(c->sm_count) * kKnnMaxK));
+  }
   CU(knn_rescan(h->train64.as<double>(), h->n, q, h->d, h->k, h->index_base, h->labels.as<int32_t>(),
                 h->redo_list.as<int32_t>(), h->redo_count.as<int32_t>(), nbr_idx, nbr_sqdist, nbr_label,
-                c->sm_count, c->stream));
+                c->sm_count, h->part_d.as<double>(), h->part_i.as<long long>(), (int)std::min<int64_t>(m, INT32_MAX), c->stream));
   c->launches++;
   return DSP_OK;
 }

@@ -16,6 +16,7 @@
 //           exact when the k-th exact distance is below the worst kept fp32 score minus a
 //           bound on the fp32 error -- otherwise the query is rescanned exhaustively in
 //           float64 (rescan kernel), so labels never depend on fp32 rounding.
+#include <algorithm>
 #include "kernels.cuh"
 #include "knn.cuh"
 
@@ -169,6 +170,82 @@ __global__ void knn_rerank_kernel(const double* __restrict__ train, const float*
   }
 }
 
+// The same rerank for wide feature vectors (the tensor-core path, D up to thousands): one WARP per query.  The
+// query and its 8 candidate rows are read 32 features at a time by the whole warp (coalesced) into shared memory;
+// lanes 0..7 each accumulate one candidate's distance over the features IN ORDER -- the very sum sqdist64 computes
+// (products and sums round separately, -fmad=false), so certified and rescanned queries agree to the last bit.
+constexpr int kRerankWarps = 8;
+__global__ void __launch_bounds__(32 * kRerankWarps)
+knn_rerank_wide_kernel(const double* __restrict__ train, int64_t n, const double* __restrict__ queries, int64_t m,
+                       int d, int k, int64_t index_base, const int32_t* __restrict__ labels,
+                       const int* __restrict__ cand_idx, const float* __restrict__ cand_worst,
+                       const float* __restrict__ qnorm, float tnorm_max, double err_rel,
+                       int64_t* __restrict__ nbr_idx, double* __restrict__ nbr_sqdist,
+                       int32_t* __restrict__ nbr_label, int32_t* __restrict__ redo_list,
+                       int32_t* __restrict__ redo_count) {
+  __shared__ double stage[kRerankWarps][32][kKnnCand + 1];      // [feature][candidate | query]: conflict-free for lanes 0..7
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t warps_total = (int64_t)gridDim.x * kRerankWarps;
+  for (int64_t qi = (int64_t)blockIdx.x * kRerankWarps + w; qi < m; qi += warps_total) {
+    const double* q = queries + qi * d;
+    const int my_cand = lane < kKnnCand ? cand_idx[qi * kKnnCand + lane] : -1;
+    double acc = 0.0;
+    for (int c0 = 0; c0 < d; c0 += 32) {
+      const int j = c0 + lane;
+      stage[w][lane][kKnnCand] = j < d ? q[j] : 0.0;
+#pragma unroll
+      for (int c = 0; c < kKnnCand; ++c) {
+        const int i = __shfl_sync(0xffffffffu, my_cand, c);
+        stage[w][lane][c] = (i >= 0 && j < d) ? train[(int64_t)i * d + j] : 0.0;
+      }
+      __syncwarp();
+      if (lane < kKnnCand) {
+        const int lim = min(32, d - c0);
+        for (int t = 0; t < lim; ++t) { const double x = stage[w][t][kKnnCand] - stage[w][t][lane]; acc += x * x; }
+      }
+      __syncwarp();
+    }
+    // lane 0 gathers the (distance, index) pairs and applies the certificate exactly like knn_rerank_kernel
+    double cd[kKnnCand];
+    int cidx[kKnnCand];
+    int nc = 0;
+#pragma unroll
+    for (int c = 0; c < kKnnCand; ++c) {
+      const double dd = __shfl_sync(0xffffffffu, acc, c);
+      const int i = __shfl_sync(0xffffffffu, my_cand, c);
+      if (i < 0) continue;
+      int s = nc++;
+      while (s > 0 && less_di(dd, i, cd[s - 1], cidx[s - 1])) { cd[s] = cd[s - 1]; cidx[s] = cidx[s - 1]; --s; }
+      cd[s] = dd; cidx[s] = i;
+    }
+    if (lane != 0) continue;
+    const int kk = (int)min((int64_t)k, n);
+    bool ok = (nc >= kk);
+    if (ok && n > kKnnCand) {
+      const float qn = qnorm[qi];
+      const double bound = (double)(sqrtf(qn) + sqrtf(tnorm_max));
+      const double err = err_rel * bound * bound;
+      const double lower = (double)cand_worst[qi] + (double)qn - err;
+      ok = cd[kk - 1] < lower;
+    }
+    if (!ok) {
+      const int slot = atomicAdd(redo_count, 1);
+      redo_list[slot] = (int)qi;
+      continue;
+    }
+    for (int c = 0; c < kk; ++c) {
+      if (nbr_idx) nbr_idx[qi * k + c] = index_base + cidx[c];
+      if (nbr_sqdist) nbr_sqdist[qi * k + c] = cd[c];
+      if (nbr_label) nbr_label[qi * k + c] = labels[cidx[c]];
+    }
+    for (int c = kk; c < k; ++c) {
+      if (nbr_idx) nbr_idx[qi * k + c] = -1;
+      if (nbr_sqdist) nbr_sqdist[qi * k + c] = INFINITY;
+      if (nbr_label) nbr_label[qi * k + c] = -1;
+    }
+  }
+}
+
 // Exhaustive float64 scan for the queries the certificate rejected: one warp per query.
 __global__ void knn_rescan_kernel(const double* __restrict__ train, int64_t n,
                                   const double* __restrict__ queries, int d, int k, int64_t index_base,
@@ -214,6 +291,124 @@ __global__ void knn_rescan_kernel(const double* __restrict__ train, int64_t n,
         if (nbr_label) nbr_label[qi * k + c] = valid ? labels[mi] : -1;
       }
     }
+  }
+}
+
+// The exhaustive float64 scan for wide feature vectors: one CTA (4 warps) per rejected query.  A warp takes 32 train
+// rows at a time; the 32 x 32 block of features is read row by row (coalesced) into shared memory and every lane sums
+// ITS row over the features in order -- the sum sqdist64 computes -- so the distances equal the other kernels' bit for bit.
+constexpr int kRescanWarps = 4;
+__host__ __device__ inline int rescan_parts(int grid, int total) { const int p = grid / (total > 0 ? total : 1); return p < 1 ? 1 : (p > 64 ? 64 : p); }
+__global__ void __launch_bounds__(32 * kRescanWarps)
+knn_rescan_wide_kernel(const double* __restrict__ train, int64_t n, const double* __restrict__ queries, int d, int k,
+                       int64_t index_base, const int32_t* __restrict__ labels, const int32_t* __restrict__ redo_list,
+                       const int32_t* __restrict__ redo_count, int64_t* __restrict__ nbr_idx,
+                       double* __restrict__ nbr_sqdist, int32_t* __restrict__ nbr_label,
+                       double* __restrict__ part_d, long long* __restrict__ part_i) {
+  __shared__ double stage[kRescanWarps][32][33];            // [feature][row], padded: conflict-free both ways
+  __shared__ double sq[kRescanWarps][32];
+  __shared__ double m_d[kRescanWarps][kKnnMaxK];
+  __shared__ long long m_i[kRescanWarps][kKnnMaxK];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int total = *redo_count;
+  if (total == 0) return;
+  // few rejected queries: the train rows of one query are split over `parts` CTAs (partial lists to part_d / part_i,
+  // merged by knn_rescan_merge_kernel); many: one CTA per query writes the result itself
+  const int parts = rescan_parts((int)gridDim.x, total);
+  const int64_t rows_per = ((n + parts - 1) / parts + 32 * kRescanWarps - 1) / (32 * kRescanWarps) * (32 * kRescanWarps);
+  for (int work = blockIdx.x; work < total * parts; work += gridDim.x) {
+    const int item = work / parts, part = work % parts;
+    const int64_t row_lo = (int64_t)part * rows_per, row_hi = min(n, row_lo + rows_per);
+    const int64_t qi = redo_list[item];
+    const double* q = queries + qi * d;
+    double bd[kKnnMaxK];
+    int64_t bi[kKnnMaxK];
+    for (int c = 0; c < k; ++c) { bd[c] = INFINITY; bi[c] = INT64_MAX; }
+    for (int64_t r0 = row_lo + (int64_t)w * 32; r0 < row_hi; r0 += 32 * kRescanWarps) {
+      const int64_t i = r0 + lane;
+      double acc = 0.0;
+      for (int c0 = 0; c0 < d; c0 += 32) {
+        const int j = c0 + lane;
+        sq[w][lane] = j < d ? q[j] : 0.0;
+        for (int rr = 0; rr < 32; ++rr)
+          stage[w][lane][rr] = (r0 + rr < row_hi && j < d) ? train[(r0 + rr) * d + j] : 0.0;
+        __syncwarp();
+        const int lim = min(32, d - c0);
+        for (int t = 0; t < lim; ++t) { const double x = sq[w][t] - stage[w][t][lane]; acc += x * x; }
+        __syncwarp();
+      }
+      if (i < row_hi && less_di(acc, i, bd[k - 1], bi[k - 1])) {
+        int s = k - 1;
+        while (s > 0 && less_di(acc, i, bd[s - 1], bi[s - 1])) { bd[s] = bd[s - 1]; bi[s] = bi[s - 1]; --s; }
+        bd[s] = acc; bi[s] = i;
+      }
+    }
+    // merge the warp's 32 sorted lists (k rounds of "global minimum, pop from its owner") into shared memory
+    int head = 0;
+    for (int c = 0; c < k; ++c) {
+      double md = head < k ? bd[head] : INFINITY;
+      int64_t mi = head < k ? bi[head] : INT64_MAX;
+      int owner = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, md, o);
+        const int64_t oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        const int oo = __shfl_xor_sync(0xffffffffu, owner, o);
+        if (less_di(od, oi, md, mi)) { md = od; mi = oi; owner = oo; }
+      }
+      if (owner == lane && mi != INT64_MAX) ++head;
+      if (lane == 0) { m_d[w][c] = md; m_i[w][c] = mi; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int hp[kRescanWarps] = {0, 0, 0, 0};
+      for (int c = 0; c < k; ++c) {
+        int best = -1;
+        for (int ww = 0; ww < kRescanWarps; ++ww)
+          if (hp[ww] < k && (best < 0 || less_di(m_d[ww][hp[ww]], m_i[ww][hp[ww]], m_d[best][hp[best]], m_i[best][hp[best]]))) best = ww;
+        const double md = best >= 0 ? m_d[best][hp[best]] : INFINITY;
+        const int64_t mi = best >= 0 ? (int64_t)m_i[best][hp[best]] : INT64_MAX;
+        if (best >= 0) ++hp[best];
+        const bool valid = (mi != INT64_MAX);
+        if (parts > 1) { part_d[(int64_t)work * kKnnMaxK + c] = valid ? md : INFINITY; part_i[(int64_t)work * kKnnMaxK + c] = mi; continue; }
+        if (nbr_idx) nbr_idx[qi * k + c] = valid ? index_base + mi : -1;
+        if (nbr_sqdist) nbr_sqdist[qi * k + c] = valid ? md : INFINITY;
+        if (nbr_label) nbr_label[qi * k + c] = valid ? labels[mi] : -1;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// merge of the per-part lists of knn_rescan_wide_kernel: one thread per rejected query
+__global__ void knn_rescan_merge_kernel(int grid_of_scan, int k, int64_t index_base, const int32_t* __restrict__ labels,
+                                        const int32_t* __restrict__ redo_list, const int32_t* __restrict__ redo_count,
+                                        const double* __restrict__ part_d, const long long* __restrict__ part_i,
+                                        int64_t* __restrict__ nbr_idx, double* __restrict__ nbr_sqdist,
+                                        int32_t* __restrict__ nbr_label) {
+  const int total = *redo_count;
+  if (total == 0) return;
+  const int parts = rescan_parts(grid_of_scan, total);
+  if (parts == 1) return;
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= total) return;
+  const int64_t qi = redo_list[item];
+  int hp[64];
+  for (int p = 0; p < parts; ++p) hp[p] = 0;
+  for (int c = 0; c < k; ++c) {
+    int best = -1;
+    double bdv = INFINITY; long long biv = INT64_MAX;
+    for (int p = 0; p < parts; ++p) {
+      if (hp[p] >= k) continue;
+      const int64_t o = ((int64_t)item * parts + p) * kKnnMaxK + hp[p];
+      const double dv = part_d[o]; const long long iv = part_i[o];
+      if (iv != INT64_MAX && (best < 0 || less_di(dv, iv, bdv, biv))) { best = p; bdv = dv; biv = iv; }
+    }
+    if (best >= 0) ++hp[best];
+    const bool valid = best >= 0;
+    if (nbr_idx) nbr_idx[qi * k + c] = valid ? index_base + biv : -1;
+    if (nbr_sqdist) nbr_sqdist[qi * k + c] = valid ? bdv : INFINITY;
+    if (nbr_label) nbr_label[qi * k + c] = valid ? labels[biv] : -1;
   }
 }
 
@@ -297,6 +492,8 @@ __global__ void knn_iota_kernel(int32_t* list, int32_t* count, int64_t m) {
 
 }  // namespace
 
+int knn_rescan_grid(int sm_count) { return sm_count * 4; }
+
 int knn_padded_dim(int d) {
   if (d + 1 <= 16) return 16;
   if (d + 1 <= 32) return 32;
@@ -335,6 +532,13 @@ cudaError_t knn_rerank(const double* train, const float* train32, int dp, int64_
                        int32_t* redo_list, int32_t* redo_count, cudaStream_t st) {
   if (m == 0) return cudaSuccess;
   cudaMemsetAsync(redo_count, 0, sizeof(int32_t), st);
+  if (d > 64) {
+    const unsigned grid = (unsigned)std::min<int64_t>((m + kRerankWarps - 1) / kRerankWarps, 148 * 32);
+    knn_rerank_wide_kernel<<<grid, 32 * kRerankWarps, 0, st>>>(train, n, q, m, d, k, index_base, labels, cand_idx, cand_worst, qnorm,
+                                                                tnorm_max_host, err_rel, nbr_idx, nbr_sqdist, nbr_label, redo_list,
+                                                                redo_count);
+    return cudaGetLastError();
+  }
   knn_rerank_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(
       train, train32, dp, n, q, m, d, k, index_base, labels, cand_idx, cand_worst, qnorm, tnorm_max_host, err_rel,
       nbr_idx, nbr_sqdist, nbr_label, redo_list, redo_count);
@@ -350,9 +554,19 @@ cudaError_t knn_redo_all(int32_t* redo_list, int32_t* redo_count, int64_t m, cud
 cudaError_t knn_rescan(const double* train, int64_t n, const double* q, int d, int k, int64_t index_base,
                        const int32_t* labels, const int32_t* redo_list, const int32_t* redo_count,
                        int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label, int sm_count,
-                       cudaStream_t st) {
-  knn_rescan_kernel<<<sm_count * 2, 256, 0, st>>>(train, n, q, d, k, index_base, labels, redo_list,
-                                                 redo_count, nbr_idx, nbr_sqdist, nbr_label);
+                       double* part_d, long long* part_i, int max_redo, cudaStream_t st) {
+  if (d > 64) {
+    const int grid = knn_rescan_grid(sm_count);
+    knn_rescan_wide_kernel<<<grid, 32 * kRescanWarps, 0, st>>>(train, n, q, d, k, index_base, labels, redo_list,
+                                                               redo_count, nbr_idx, nbr_sqdist, nbr_label, part_d, part_i);
+    // parts > 1 only when fewer than `grid` queries were rejected: that many merge threads are enough
+    const int mt = max_redo < grid ? max_redo : grid;
+    if (mt > 0)
+      knn_rescan_merge_kernel<<<(mt + 127) / 128, 128, 0, st>>>(grid, k, index_base, labels, redo_list, redo_count, part_d, part_i,
+                                                               nbr_idx, nbr_sqdist, nbr_label);
+  } else
+    knn_rescan_kernel<<<sm_count * 2, 256, 0, st>>>(train, n, q, d, k, index_base, labels, redo_list,
+                                                   redo_count, nbr_idx, nbr_sqdist, nbr_label);
   return cudaGetLastError();
 }
 

@@ -22,7 +22,10 @@ cudaError_t knn_redo_all(int32_t* redo_list, int32_t* redo_count, int64_t m, cud
 cudaError_t knn_rescan(const double* train, int64_t n, const double* q, int d, int k, int64_t index_base,
                        const int32_t* labels, const int32_t* redo_list, const int32_t* redo_count,
                        int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label, int sm_count,
-                       cudaStream_t st);
+                       double* part_d, long long* part_i, int max_redo, cudaStream_t st);
+// wide features (d > 64): the rows of a rejected query are split over several CTAs when few queries were rejected;
+// part_d / part_i hold knn_rescan_grid(sm_count) * kKnnMaxK partial results each
+int knn_rescan_grid(int sm_count);
 cudaError_t knn_vote(const int32_t* nbr_label, int64_t m, int k, int32_t* out, cudaStream_t st);
 cudaError_t knn_merge_vote(const double* cd, const int64_t* ci, const int32_t* cl, int r, int64_t m,
                            int k, int32_t* labels_out, int64_t* idx_out, double* dist_out,
@@ -30,11 +33,12 @@ cudaError_t knn_merge_vote(const double* cd, const int64_t* ci, const int32_t* c
 
 // knn_dense.cu: tensor-core candidate scan for feature dimensions beyond the tiled scan (sequence features, D = 2 * max_len)
 int knn_dense_kblocks(int d);
-int64_t knn_dense_row_blocks(int64_t rows);
-size_t knn_dense_packed_bytes(int64_t rows, int d);
-// flags[0] = max |x|^2 as float bits, flags[1] = 1 when a value does not fit fp16 (caller falls back to the float64 scan)
-cudaError_t knn_dense_pack(const double* x, int64_t rows, int d, void* packed, float* norms, float pad_norm, int* flags,
-                           cudaStream_t st);
+int64_t knn_dense_padded_rows(int64_t rows, bool train);      // rows rounded up to the tile height (queries 128, train 256)
+size_t knn_dense_packed_bytes(int64_t rows, int d, bool train);
+// norms: one float per PADDED row.  flags[0] = max |x|^2 as float bits, flags[1] = 1 when a value does not fit fp16
+// (the caller falls back to the float64 scan); reset_flags = false accumulates over several calls
+cudaError_t knn_dense_pack(const double* x, int64_t rows, int d, bool train, void* packed, float* norms, float pad_norm,
+                           int* flags, bool reset_flags, cudaStream_t st);
 cudaError_t knn_dense_scan(const void* qpacked, const void* tpacked, const float* tnorm, int64_t m, int64_t n, int d,
                            int* cand_idx, float* cand_worst, int sm_count, cudaStream_t st);
 // bound on |score_scan - score_exact| / (|q| + |t|max)^2 for the split-fp16 tensor-core evaluation: 3 * D / 16 fp32

@@ -12,10 +12,10 @@
 //           (8 x 16-byte core matrices, no swizzle), so one stage of the pipeline is two contiguous
 //           32 KB bulk copies (cp.async.bulk, no tensor map) -- plus |x|^2 per row.
 //   scan    persistent CTAs, one per block of 128 queries, three warp roles:
-//             warp 0    TMA producer: 3-stage ring of {Q_hi, Q_lo, T_hi, T_lo} 128x64 tiles
-//             warp 1    one thread issues tcgen05.mma (cta_group::1, kind::f16, M = N = 128, K = 16):
+//             warp 0    TMA producer: 2-stage ring of {Q_hi, Q_lo} 128x64 and {T_hi, T_lo} 256x64 tiles (96 KB a stage)
+//             warp 1    one thread issues tcgen05.mma (cta_group::1, kind::f16, M = 128, N = 256, K = 16):
 //                       acc += Q_hi.T_hi + Q_hi.T_lo + Q_lo.T_hi into a double-buffered fp32
-//                       accumulator in TMEM (2 x 128 columns); tcgen05.commit frees the ring slot
+//                       accumulator in TMEM (2 x 256 columns); tcgen05.commit frees the ring slot
 //             warps 2-5 epilogue: tcgen05.ld 32 columns at a time (one query row per thread), fused
 //                       score + running top-8 candidate list in registers -- the m x n distance
 //                       matrix never exists, the accumulator never leaves the SM
@@ -31,13 +31,14 @@ namespace dsp {
 
 namespace {
 
-constexpr int kBM = 128, kBN = 128, kBK = 64;          // CTA tile: queries x train rows x features per stage
-constexpr int kTileBytes = kBM * kBK * 2;                // one fp16 plane of one operand tile: 16 KB
-constexpr int kStageBytes = 4 * kTileBytes;              // Q_hi, Q_lo, T_hi, T_lo
-constexpr int kStages = 3;
+constexpr int kBM = 128, kBN = 256, kBK = 64;          // CTA tile: queries x train rows x features per stage
+constexpr int kQTileBytes = kBM * kBK * 2;               // one fp16 plane of a query tile: 16 KB
+constexpr int kTTileBytes = kBN * kBK * 2;               // one fp16 plane of a train tile: 32 KB
+constexpr int kStageBytes = 2 * kQTileBytes + 2 * kTTileBytes;   // Q_hi, Q_lo, T_hi, T_lo: 96 KB
+constexpr int kStages = 2;
 constexpr int kAccStages = 2;
 constexpr int kDenseThreads = 192;
-constexpr int kTmemCols = kAccStages * kBN;              // 256 fp32 columns
+constexpr int kTmemCols = kAccStages * kBN;              // 512 fp32 columns: all of TMEM
 constexpr size_t kDenseSmem = (size_t)kStages * kStageBytes + 256;
 // canonical K-major, no-swizzle layout of a 128 x 64 fp16 tile: core matrix = 8 rows x 16 bytes (128 B contiguous);
 // the 8 core matrices along K of one 8-row group are contiguous (LBO = 128 B), row groups follow (SBO = 1024 B)
@@ -106,13 +107,14 @@ __device__ __forceinline__ void cand_insert8(float (&cd)[kKnnCand], int (&ci)[kK
 // pack: one warp per (padded) row
 // ---------------------------------------------------------------------------------------
 __global__ void knn_dense_pack_kernel(const double* __restrict__ x, int64_t rows, int64_t rows_padded, int d, int kb_count,
-                                      unsigned char* __restrict__ packed, float* __restrict__ norms, float pad_norm,
-                                      int* __restrict__ flags) {
+                                      int block_rows, unsigned char* __restrict__ packed, float* __restrict__ norms,
+                                      float pad_norm, int* __restrict__ flags) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows_padded) return;
-  const int64_t rb = r / kBM;
-  const int rr = (int)(r % kBM), g = rr >> 3, r8 = rr & 7;
+  const int64_t rb = r / block_rows;
+  const int rr = (int)(r % block_rows), g = rr >> 3, r8 = rr & 7;
+  const size_t tile_bytes = (size_t)block_rows * kBK * 2;
   double ss = 0.0;
   bool big = false;
   for (int kc_global = lane; kc_global < kb_count * 8; kc_global += 32) {
@@ -129,9 +131,9 @@ __global__ void knn_dense_pack_kernel(const double* __restrict__ x, int64_t rows
       lo[j] = __float2half_rn((float)(v - (double)__half2float(h)));
     }
     const int kb = kc_global >> 3, kc = kc_global & 7;
-    unsigned char* dst = packed + ((size_t)(rb * kb_count + kb) * 2) * kTileBytes + g * kSBO + kc * kLBO + r8 * 16;
+    unsigned char* dst = packed + ((size_t)(rb * kb_count + kb) * 2) * tile_bytes + g * kSBO + kc * kLBO + r8 * 16;
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(dst + kTileBytes) = *reinterpret_cast<const uint4*>(lo);
+    *reinterpret_cast<uint4*>(dst + tile_bytes) = *reinterpret_cast<const uint4*>(lo);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
@@ -184,8 +186,8 @@ knn_dense_scan_kernel(const unsigned char* __restrict__ qpacked, const unsigned 
             mbar_wait(&bar_empty[s], ph ^ 1u);
             mbar_expect_tx(&bar_full[s], (uint32_t)kStageBytes);
             const uint32_t dst = ring + (uint32_t)s * kStageBytes;
-            bulk_g2s(dst, qpacked + ((size_t)qb * kb_count + kb) * (2 * kTileBytes), 2 * kTileBytes, &bar_full[s]);
-            bulk_g2s(dst + 2 * kTileBytes, tpacked + ((size_t)tb * kb_count + kb) * (2 * kTileBytes), 2 * kTileBytes, &bar_full[s]);
+            bulk_g2s(dst, qpacked + ((size_t)qb * kb_count + kb) * (2 * kQTileBytes), 2 * kQTileBytes, &bar_full[s]);
+            bulk_g2s(dst + 2 * kQTileBytes, tpacked + ((size_t)tb * kb_count + kb) * (2 * kTTileBytes), 2 * kTTileBytes, &bar_full[s]);
             if (++s == kStages) { s = 0; ph ^= 1u; }
           }
     }
@@ -202,7 +204,7 @@ knn_dense_scan_kernel(const unsigned char* __restrict__ qpacked, const unsigned 
           for (int kb = 0; kb < kb_count; ++kb) {
             mbar_wait(&bar_full[s], ph);
             tc_fence_after();
-            const uint32_t q_hi = ring + (uint32_t)s * kStageBytes, q_lo = q_hi + kTileBytes, t_hi = q_hi + 2 * kTileBytes, t_lo = q_hi + 3 * kTileBytes;
+            const uint32_t q_hi = ring + (uint32_t)s * kStageBytes, q_lo = q_hi + kQTileBytes, t_hi = q_hi + 2 * kQTileBytes, t_lo = t_hi + kTTileBytes;
 #pragma unroll
             for (int k4 = 0; k4 < kBK / 16; ++k4) {
               const uint32_t off = (uint32_t)k4 * 2u * kLBO;   // 16 features = two core matrices along K
@@ -280,26 +282,31 @@ knn_dense_scan_kernel(const unsigned char* __restrict__ qpacked, const unsigned 
 }  // namespace
 
 int knn_dense_kblocks(int d) { return (d + kBK - 1) / kBK; }
-int64_t knn_dense_row_blocks(int64_t rows) { return (rows + kBM - 1) / kBM; }
-size_t knn_dense_packed_bytes(int64_t rows, int d) {
-  return (size_t)knn_dense_row_blocks(rows) * (size_t)knn_dense_kblocks(d) * 2 * kTileBytes;
+int knn_dense_block_rows(bool train) { return train ? kBN : kBM; }
+int64_t knn_dense_padded_rows(int64_t rows, bool train) {
+  const int b = knn_dense_block_rows(train);
+  return (rows + b - 1) / b * b;
+}
+size_t knn_dense_packed_bytes(int64_t rows, int d, bool train) {
+  return (size_t)knn_dense_padded_rows(rows, train) * (size_t)knn_dense_kblocks(d) * kBK * 2 * 2;
 }
 
-cudaError_t knn_dense_pack(const double* x, int64_t rows, int d, void* packed, float* norms, float pad_norm, int* flags,
-                           cudaStream_t st) {
-  const int64_t rows_padded = knn_dense_row_blocks(rows) * kBM;
-  cudaMemsetAsync(flags, 0, 2 * sizeof(int), st);
+cudaError_t knn_dense_pack(const double* x, int64_t rows, int d, bool train, void* packed, float* norms, float pad_norm,
+                           int* flags, bool reset_flags, cudaStream_t st) {
+  const int64_t rows_padded = knn_dense_padded_rows(rows, train);
+  if (reset_flags) cudaMemsetAsync(flags, 0, 2 * sizeof(int), st);
   if (rows_padded == 0) return cudaSuccess;
   const int warps = 8;
   knn_dense_pack_kernel<<<(unsigned)((rows_padded + warps - 1) / warps), warps * 32, 0, st>>>(
-      x, rows, rows_padded, d, knn_dense_kblocks(d), static_cast<unsigned char*>(packed), norms, pad_norm, flags);
+      x, rows, rows_padded, d, knn_dense_kblocks(d), knn_dense_block_rows(train), static_cast<unsigned char*>(packed), norms,
+      pad_norm, flags);
   return cudaGetLastError();
 }
 
 cudaError_t knn_dense_scan(const void* qpacked, const void* tpacked, const float* tnorm, int64_t m, int64_t n, int d,
                            int* cand_idx, float* cand_worst, int sm_count, cudaStream_t st) {
   if (m == 0) return cudaSuccess;
-  const int q_blocks = (int)knn_dense_row_blocks(m), t_blocks = (int)knn_dense_row_blocks(n);
+  const int q_blocks = (int)(knn_dense_padded_rows(m, false) / kBM), t_blocks = (int)(knn_dense_padded_rows(n, true) / kBN);
   cudaError_t e = cudaFuncSetAttribute(knn_dense_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseSmem);
   if (e != cudaSuccess) return e;
   const int grid = q_blocks < sm_count ? q_blocks : sm_count;
