@@ -233,10 +233,12 @@ int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_
   // tuning knob (pcm_variant == pcm_num_variants()); misaligned utterances inside it are replayed
   const int kPipeVariant = pcm_num_variants();
   PipePlan plan{};
-  // automatic choice: the pipelined kernel for its specialised geometry (frame 256 / shift 128, BASELINE configs[1]:
-  // 0.84 ms vs 1.26 ms per 20k utterances); other geometries still run faster on frontend_pcm_kernel
-  // (tools/config_sweep.py), whose window pass reads the trimmed segment from shared memory
-  const bool pipe_geometry = (fl == 256 && fs == 128);
+  // automatic choice (tools/config_sweep.py, ms per 20k utterances, resident vs pipelined): the pipelined kernel when
+  // frames are whole 64-sample groups and the hop is at least 128 -- 256/128 1.25 vs 0.83 (BASELINE configs[1], its
+  // specialised instantiation), 512/256 1.20 vs 0.97, 1024/512 1.28 vs 1.00, 2048/1024 2.35 vs 0.99, 1024/256 1.44 vs 1.25;
+  // shorter hops (128/64 2.44 vs 3.29) and frames with ragged edges (1102/441 2.1 vs 6.0) stay on frontend_pcm_kernel,
+  // whose window pass reads the trimmed segment from shared memory
+  const bool pipe_geometry = (fl % 64 == 0 && fs % 64 == 0 && fs >= 128 && fl <= 16384);
   bool pipe = fast && (c->pcm_variant == kPipeVariant || (c->pcm_variant < 0 && p->aligned16 && pipe_geometry)) &&
               pipe_kernel_plan(max_len, (int)cap_frames64, fl, kMaxSmemPerCta, &plan);
   if (fast && !pipe && c->pcm_variant == kPipeVariant) variant = kAutoResident;

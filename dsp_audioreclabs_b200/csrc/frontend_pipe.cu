@@ -292,16 +292,22 @@ __device__ __noinline__ void tail_stats_regs(const float* fe, const float* fm, c
 #pragma unroll 1
   for (int q = 0; q < 3; ++q) {
     const float* src = q == 0 ? fe : fm;
+    // keys order like the values: float bit patterns for the non-negative energies / magnitudes, the integers
+    // themselves for the crossing counts (a handful of significant bits: the bisection below then takes <= 10
+    // rounds instead of walking the ~25 bits in which the float patterns of small integers differ)
+    const bool ints = q == 2;
+    auto val = [&](uint32_t k) { return ints ? (float)k : __uint_as_float(k); };
     uint32_t key[NJ];
     float ps = 0.f;
     uint32_t kmn = 0xffffffffu, kmx = 0u;
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
       const int i = lane + 32 * j;
-      float x = 0.f;
-      if (i < n) x = q == 2 ? (float)zf[i] : src[i];
-      key[j] = i < n ? __float_as_uint(x) : 0xffffffffu;
-      if (i < n) { ps += x; kmn = min(kmn, key[j]); kmx = max(kmx, key[j]); }
+      key[j] = 0xffffffffu;
+      if (i < n) {
+        key[j] = ints ? (uint32_t)zf[i] : __float_as_uint(src[i]);
+        ps += val(key[j]); kmn = min(kmn, key[j]); kmx = max(kmx, key[j]);
+      }
     }
     const float inv_n = 1.0f / (float)n;
     const float meanf = (float)warp_reduce((double)ps, OpAddD()) * inv_n;     // float32 result: float divide is enough
@@ -309,7 +315,7 @@ __device__ __noinline__ void tail_stats_regs(const float* fe, const float* fm, c
     kmn = __reduce_min_sync(0xffffffffu, kmn);
     float pss = 0.f;
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) if (lane + 32 * j < n) { const float d = __uint_as_float(key[j]) - meanf; pss += d * d; }
+    for (int j = 0; j < NJ; ++j) if (lane + 32 * j < n) { const float d = val(key[j]) - meanf; pss += d * d; }
     const double ss = warp_reduce((double)pss, OpAddD());
     const int rank = (n - 1) >> 1;
     uint32_t prefix = kmn;
@@ -336,7 +342,7 @@ __device__ __noinline__ void tail_stats_regs(const float* fe, const float* fm, c
         prefix = __reduce_min_sync(0xffffffffu, k);
       }
     }
-    const float sel = __uint_as_float(prefix);
+    const float sel = val(prefix);
     float sel2 = sel;
     if (!(n & 1)) {
       int le = 0;
@@ -345,13 +351,13 @@ __device__ __noinline__ void tail_stats_regs(const float* fe, const float* fm, c
       for (int j = 0; j < NJ; ++j) { if (key[j] <= prefix) ++le; else nxt = min(nxt, key[j]); }
       le = __reduce_add_sync(0xffffffffu, le);
       nxt = __reduce_min_sync(0xffffffffu, nxt);
-      if (le < rank + 2 && nxt != 0xffffffffu) sel2 = __uint_as_float(nxt);
+      if (le < rank + 2 && nxt != 0xffffffffu) sel2 = val(nxt);
     }
     if (lane == 0) {
       float* o = out15 + 5 * q;
       o[0] = meanf;
       o[1] = sqrtf((float)ss * inv_n);
-      o[2] = __uint_as_float(kmx); o[3] = __uint_as_float(kmn);
+      o[2] = val(kmx); o[3] = val(kmn);
       o[4] = (n & 1) ? sel : 0.5f * sel + 0.5f * sel2;
     }
   }

@@ -11,7 +11,8 @@ dev = torch.device("cuda", 0)
 ctx = batch.default_context(0)
 samples, row_offsets = bench.synth_batch_device(n, dev, seed=7)
 stream = torch.cuda.Stream(device=dev)
-cfgs = [(256, 128), (1102, 441), (64, 32), (512, 256), (2048, 1024), (2205, 441), (1102, 1323), (352, 441)]
+cfgs = [(256, 128), (1102, 441), (64, 32), (128, 64), (512, 256), (1024, 512), (2048, 1024), (1024, 256), (512, 64), (2205, 441), (1102, 1323), (352, 441)]
+if len(sys.argv) > 2: cfgs = [tuple(int(v) for v in c.split('/')) for c in sys.argv[2].split(',')]
 for fl, fs in cfgs:
     row = []
     for variant in (0, 10):
