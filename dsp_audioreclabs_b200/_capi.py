@@ -39,6 +39,13 @@ class FrontendOutputs(C.Structure):
     ]
 
 
+class MfccParams(C.Structure):
+    _fields_ = [
+        ("frame_length", C.c_int32), ("frame_shift", C.c_int32), ("n_fft", C.c_int32), ("n_mels", C.c_int32),
+        ("n_ceps", C.c_int32), ("window", C.c_int32), ("pre_emphasis", C.c_double), ("log_floor", C.c_double),
+    ]
+
+
 class WavInfo(C.Structure):
     _fields_ = [
         ("status", C.c_int32), ("channels", C.c_int32), ("sample_width", C.c_int32), ("sample_rate", C.c_int32),
@@ -85,6 +92,8 @@ SIGNATURES = {
     "dsp_knn_predict_device": (C.c_int, [_P, _P, _I64, _P]),
     "dsp_knn_last_stats": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I32)]),
     "dsp_knn_merge_vote_device": (C.c_int, [_P, _P, _P, _P, _I32, _I64, _I32, _P, _P, _P]),
+    "dsp_mfcc_batch_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, C.POINTER(MfccParams), _P, _P, _P, _P, _P]),
+    "dsp_dtw_topk_host": (C.c_int, [_P, _P, _P, _I64, _P, _P, _P, _I64, _I32, _I32, _I64, _P, _P, _P, _P]),
     "dsp_wav_scan": (C.c_int, [_P, _I64, _I32, _P]),
     "dsp_wav_read": (C.c_int, [_P, _I64, _I32, _P, _P, _P, _I64]),
     "dsp_host_alloc": (C.c_int, [_I64, C.POINTER(_P)]),

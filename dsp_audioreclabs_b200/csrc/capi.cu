@@ -12,6 +12,7 @@
 
 #include "kernels.cuh"
 #include "knn.cuh"
+#include "mfcc_dtw.cuh"
 #include "misc.cuh"
 
 using namespace dsp;
@@ -110,7 +111,7 @@ struct dsp_context {
   int tma_chunk = 4096;         // bytes per bulk copy; DSP_TMA_CHUNK overrides (tuning knob)
   int occ = 0;
   Slot slot[2];
-  DevBuf tmp[10];
+  DevBuf tmp[16];
 };
 
 struct dsp_knn {
@@ -910,6 +911,123 @@ int dsp_knn_topk_device(dsp_knn* h, const double* q, int64_t m, int64_t* nbr_idx
                 h->redo_list.as<int32_t>(), h->redo_count.as<int32_t>(), nbr_idx, nbr_sqdist, nbr_label,
                 c->sm_count, h->part_d.as<double>(), h->part_i.as<long long>(), (int)std::min<int64_t>(m, INT32_MAX), c->stream));
   c->launches++;
+  return DSP_OK;
+}
+
+// ---- MFCC + DTW (self-specified variant, oracle/mfcc_dtw_oracle.py) -------------------------------------
+int dsp_mfcc_batch_host(dsp_context* c, const int16_t* samples, const int64_t* offsets, const int32_t* lengths,
+                        const int32_t* seg_start, const int32_t* seg_end, int64_t n_utts, const dsp_mfcc_params* p,
+                        const float* filterbank, const float* dct, const int64_t* mfcc_offsets, float* mfcc_out,
+                        int32_t* n_frames_out) {
+  if (!c || !p || n_utts < 0 || (n_utts && (!samples || !offsets || !seg_start || !seg_end || !filterbank || !dct || !mfcc_offsets || !mfcc_out)))
+    return fail(DSP_ERR_INVALID, "bad argument");
+  if (p->frame_length < 1 || p->frame_shift < 1 || p->n_mels < 1 || p->n_ceps < 1 || p->n_ceps > p->n_mels)
+    return fail(DSP_ERR_INVALID, "bad MFCC geometry");
+  if (p->n_fft < 32 || (p->n_fft & (p->n_fft - 1)) || p->n_fft < p->frame_length || p->n_fft > 16384)
+    return fail(DSP_ERR_INVALID, "n_fft must be a power of two in [max(32, frame_length), 16384]");
+  if (mfcc_smem_bytes(p->n_fft, p->n_mels) > kMaxSmemPerCta) return fail(DSP_ERR_UNSUPPORTED, "n_fft too large for shared memory");
+  if (n_utts == 0) return DSP_OK;
+  CU(cudaSetDevice(c->device));
+  std::vector<double> w;
+  int rc = host_window(p->window, p->frame_length, w);
+  if (rc) return rc;
+  std::vector<float> wf(w.begin(), w.end());
+  const int n_bins = p->n_fft / 2 + 1;
+  std::vector<float> tw((size_t)p->n_fft);                                       // W[k] = exp(-2 pi i k / n_fft), k < n_fft / 2
+  for (int k = 0; k < p->n_fft / 2; ++k) {
+    const double a = -2.0 * M_PI * (double)k / (double)p->n_fft;
+    tw[2 * (size_t)k] = (float)std::cos(a); tw[2 * (size_t)k + 1] = (float)std::sin(a);
+  }
+  std::vector<int> range(2 * (size_t)p->n_mels);                                  // non-zero bins of every filter
+  for (int m = 0; m < p->n_mels; ++m) {
+    int lo = n_bins, hi = 0;
+    for (int b = 0; b < n_bins; ++b) if (filterbank[(size_t)m * n_bins + b] != 0.f) { lo = std::min(lo, b); hi = std::max(hi, b + 1); }
+    range[2 * (size_t)m] = std::min(lo, hi); range[2 * (size_t)m + 1] = hi;
+  }
+  const int64_t total_samples = lengths ? offsets[n_utts - 1] + lengths[n_utts - 1] : offsets[n_utts];
+  int64_t span = 0;
+  for (int64_t b = 0; b < n_utts; ++b) span = std::max<int64_t>(span, offsets[b] + (lengths ? lengths[b] : offsets[b + 1] - offsets[b]));
+  const int64_t total_frames = mfcc_offsets[n_utts];
+  (void)total_samples;
+  OneShot os(c);
+  int16_t* d_s = os.dev<int16_t>((size_t)span);
+  int64_t* d_off = os.dev<int64_t>((size_t)n_utts + 1);
+  int32_t* d_len = lengths ? os.dev<int32_t>((size_t)n_utts) : nullptr;
+  int32_t* d_st = os.dev<int32_t>((size_t)n_utts);
+  int32_t* d_en = os.dev<int32_t>((size_t)n_utts);
+  float* d_w = os.dev<float>(wf.size());
+  float* d_tw = os.dev<float>(tw.size());
+  float* d_fb = os.dev<float>((size_t)p->n_mels * n_bins);
+  int* d_rg = os.dev<int>(range.size());
+  float* d_dct = os.dev<float>((size_t)p->n_ceps * p->n_mels);
+  int64_t* d_mo = os.dev<int64_t>((size_t)n_utts + 1);
+  float* d_out = os.dev<float>((size_t)std::max<int64_t>(total_frames, 1) * p->n_ceps);
+  int32_t* d_nf = os.dev<int32_t>((size_t)n_utts);
+  unsigned int* d_cnt = os.dev<unsigned int>(4);
+  if (!d_s || !d_off || (lengths && !d_len) || !d_st || !d_en || !d_w || !d_tw || !d_fb || !d_rg || !d_dct || !d_mo || !d_out || !d_nf || !d_cnt)
+    return fail(DSP_ERR_NOMEM, "device allocation failed");
+  cudaStream_t st = c->stream;
+  CU(cudaMemcpyAsync(d_s, samples, sizeof(int16_t) * (size_t)span, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_off, offsets, sizeof(int64_t) * ((size_t)n_utts + 1), cudaMemcpyHostToDevice, st));
+  if (lengths) CU(cudaMemcpyAsync(d_len, lengths, sizeof(int32_t) * (size_t)n_utts, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_st, seg_start, sizeof(int32_t) * (size_t)n_utts, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_en, seg_end, sizeof(int32_t) * (size_t)n_utts, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_w, wf.data(), sizeof(float) * wf.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_tw, tw.data(), sizeof(float) * tw.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_fb, filterbank, sizeof(float) * (size_t)p->n_mels * n_bins, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_rg, range.data(), sizeof(int) * range.size(), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_dct, dct, sizeof(float) * (size_t)p->n_ceps * p->n_mels, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_mo, mfcc_offsets, sizeof(int64_t) * ((size_t)n_utts + 1), cudaMemcpyHostToDevice, st));
+  MfccArgs a{p->frame_length, p->frame_shift, p->n_fft, p->n_mels, p->n_ceps, p->pre_emphasis, (float)p->log_floor};
+  CU(launch_mfcc(d_s, d_off, d_len, d_st, d_en, n_utts, a, d_w, reinterpret_cast<const float2*>(d_tw), d_fb,
+                 reinterpret_cast<const int2*>(d_rg), d_dct, d_mo, d_out, d_nf, d_cnt, c->sm_count, st));
+  c->launches++;
+  if (total_frames > 0) CU(cudaMemcpyAsync(mfcc_out, d_out, sizeof(float) * (size_t)total_frames * p->n_ceps, cudaMemcpyDeviceToHost, st));
+  if (n_frames_out) CU(cudaMemcpyAsync(n_frames_out, d_nf, sizeof(int32_t) * (size_t)n_utts, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return DSP_OK;
+}
+
+int dsp_dtw_topk_host(dsp_context* c, const float* q_feats, const int64_t* q_offsets, int64_t nq, const float* t_feats,
+                      const int64_t* t_offsets, const int32_t* t_labels, int64_t nt, int32_t dim, int32_t k,
+                      int64_t index_base, float* cost_out, double* nbr_cost, int64_t* nbr_idx, int32_t* nbr_label) {
+  if (!c || nq < 0 || nt < 1 || dim < 1 || k < 1 || !q_offsets || !t_offsets || (nq && !q_feats) || !t_feats || (nbr_label && !t_labels))
+    return fail(DSP_ERR_INVALID, "bad argument");
+  if (k > kKnnMaxK) return fail(DSP_ERR_UNSUPPORTED, "k > %d is not supported", kKnnMaxK);
+  if (dim > dtw_max_dim()) return fail(DSP_ERR_UNSUPPORTED, "feature dimension > %d is not supported by the DTW kernel", dtw_max_dim());
+  if (nq == 0) return DSP_OK;
+  int64_t max_q = 0, max_t = 0;
+  for (int64_t i = 0; i < nq; ++i) max_q = std::max(max_q, q_offsets[i + 1] - q_offsets[i]);
+  for (int64_t i = 0; i < nt; ++i) max_t = std::max(max_t, t_offsets[i + 1] - t_offsets[i]);
+  if (max_q > dtw_max_query_frames()) return fail(DSP_ERR_UNSUPPORTED, "query sequences longer than %d frames are not supported", dtw_max_query_frames());
+  if ((size_t)max_t * dim * sizeof(float) > kMaxSmemPerCta) return fail(DSP_ERR_UNSUPPORTED, "template sequence too long for shared memory");
+  CU(cudaSetDevice(c->device));
+  OneShot os(c);
+  float* d_q = os.dev<float>((size_t)q_offsets[nq] * dim);
+  int64_t* d_qo = os.dev<int64_t>((size_t)nq + 1);
+  float* d_t = os.dev<float>((size_t)t_offsets[nt] * dim);
+  int64_t* d_to = os.dev<int64_t>((size_t)nt + 1);
+  int32_t* d_lab = os.dev<int32_t>((size_t)nt);
+  float* d_cost = os.dev<float>((size_t)nq * nt);
+  double* d_nc = os.dev<double>((size_t)nq * k);
+  int64_t* d_ni = os.dev<int64_t>((size_t)nq * k);
+  int32_t* d_nl = os.dev<int32_t>((size_t)nq * k);
+  if (!d_q || !d_qo || !d_t || !d_to || !d_lab || !d_cost || !d_nc || !d_ni || !d_nl) return fail(DSP_ERR_NOMEM, "device allocation failed");
+  cudaStream_t st = c->stream;
+  CU(cudaMemcpyAsync(d_q, q_feats, sizeof(float) * (size_t)q_offsets[nq] * dim, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_qo, q_offsets, sizeof(int64_t) * ((size_t)nq + 1), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_t, t_feats, sizeof(float) * (size_t)t_offsets[nt] * dim, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(d_to, t_offsets, sizeof(int64_t) * ((size_t)nt + 1), cudaMemcpyHostToDevice, st));
+  if (t_labels) CU(cudaMemcpyAsync(d_lab, t_labels, sizeof(int32_t) * (size_t)nt, cudaMemcpyHostToDevice, st));
+  else CU(cudaMemsetAsync(d_lab, 0, sizeof(int32_t) * (size_t)nt, st));
+  CU(launch_dtw(d_q, d_qo, nq, (int)max_q, d_t, d_to, nt, (int)max_t, dim, d_cost, st));
+  CU(launch_dtw_topk(d_cost, nq, nt, k, index_base, d_lab, d_nc, d_ni, d_nl, st));
+  c->launches += 2;
+  if (cost_out) CU(cudaMemcpyAsync(cost_out, d_cost, sizeof(float) * (size_t)nq * nt, cudaMemcpyDeviceToHost, st));
+  if (nbr_cost) CU(cudaMemcpyAsync(nbr_cost, d_nc, sizeof(double) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+  if (nbr_idx) CU(cudaMemcpyAsync(nbr_idx, d_ni, sizeof(int64_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+  if (nbr_label) CU(cudaMemcpyAsync(nbr_label, d_nl, sizeof(int32_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
   return DSP_OK;
 }
 

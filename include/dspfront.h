@@ -208,6 +208,37 @@ int dsp_knn_merge_vote_device(dsp_context* ctx, const double* cand_sqdist, const
                               const int32_t* cand_label, int32_t n_lists, int64_t m, int32_t k,
                               int32_t* labels_out, int64_t* nbr_idx_out, double* nbr_sqdist_out);
 
+/* ---- MFCC + DTW template matching (BASELINE config 5) -------------
+ * NOT in the reference (compare_feature_methods.py has no spectral features and no template
+ * matching): a self-specified variant, defined by oracle/mfcc_dtw_oracle.py ("self-oracle").  It
+ * composes with the path above: pre-processing as src/audio_processing.py:49-90, the trimmed
+ * segment [start, end) from endpoint_detection (:135-275), frames by frame_signal's rule
+ * (:299-333), then pre-emphasis, window, power spectrum of an n_fft-point FFT, the caller's
+ * mel filterbank [n_mels][n_fft/2+1], log(max(., log_floor)) and the caller's DCT matrix
+ * [n_ceps][n_mels].  mfcc_offsets[B+1] (in frames, from dsp_frame_count(end-start, ...))
+ * addresses the ragged output [frames][n_ceps]. */
+typedef struct {
+  int32_t frame_length, frame_shift, n_fft, n_mels, n_ceps;
+  int32_t window;        /* dsp_window_type */
+  double pre_emphasis;   /* y[i] = x[i] - pre_emphasis * x[i-1] inside the segment */
+  double log_floor;
+} dsp_mfcc_params;
+
+int dsp_mfcc_batch_host(dsp_context* ctx, const int16_t* samples, const int64_t* offsets,
+                        const int32_t* lengths, const int32_t* seg_start, const int32_t* seg_end,
+                        int64_t n_utts, const dsp_mfcc_params* params, const float* filterbank,
+                        const float* dct, const int64_t* mfcc_offsets, float* mfcc_out,
+                        int32_t* n_frames_out);
+/* DTW (Euclidean local distance, steps (1,0) (0,1) (1,1), accumulated cost D[n-1][m-1]) of every
+ * query sequence against every template sequence -- one CTA per pair, anti-diagonal wavefront --
+ * and the k cheapest templates per query (ties to the lower index).  Sequences are ragged
+ * [frames][dim] float32 with offsets in frames.  cost_out (optional) receives the full
+ * [nq][nt] matrix.  index_base lets row-sharded template sets be merged like KNN candidates. */
+int dsp_dtw_topk_host(dsp_context* ctx, const float* q_feats, const int64_t* q_offsets, int64_t nq,
+                      const float* t_feats, const int64_t* t_offsets, const int32_t* t_labels,
+                      int64_t nt, int32_t dim, int32_t k, int64_t index_base, float* cost_out,
+                      double* nbr_cost, int64_t* nbr_idx, int32_t* nbr_label);
+
 /* ---- batched WAV ingest ----------------------------------
  * Replaces the per-file `wave.open` / `readframes` / `np.frombuffer` of load_wav
  * (src/audio_processing.py:21-40) for whole file lists.  Host-only I/O: no CUDA device is
