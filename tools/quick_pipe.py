@@ -11,13 +11,15 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 ctx = batch.default_context(0)
 lens = synth.ragged_lengths(24, 0.2, 1.1, seed=3)
 utts = [synth.utterance_pcm(i, int(m), seed0=11) for i, m in enumerate(lens)]
-s, o, l = batch.pack_aligned(utts)
+reps = int(os.environ.get("QUICK_REPS", "30"))          # 24 x 30 = 720 utterances: enough for the split launch
+s, o, l = batch.pack_aligned(utts * reps)
 ctx.set_tuning("pcm_variant", 10)
 bad = 0
 for w in ("hamming", "hanning", "rectangular"):
     r = batch.frontend_batch(s, o, 256, 128, w, emit_epd_lists=True, lengths=l, ctx=ctx)
-    for b, u in enumerate(utts):
-        rr = fo.frontend_utterance(u, 256, 128, w)
+    refs = [fo.frontend_utterance(u, 256, 128, w) for u in utts]
+    for b in range(len(utts) * reps):
+        u, rr = utts[b % len(utts)], refs[b % len(utts)]
         e, m, z = r.frames(b)
         ok = (int(r.start[b]), int(r.end[b])) == (rr["start"], rr["end"]) and np.array_equal(z.astype(np.float64), rr["zcr"]) \
             and np.allclose(e, rr["energy"], rtol=1e-5, atol=0) and np.allclose(m, rr["magnitude"], rtol=1e-5, atol=0)
