@@ -65,6 +65,18 @@ constexpr int kBarStream = 1;              // named barrier of the stream warps
 // kBarRecEmpty + r is "record r is free again" (the tail warp arrives, the stream warps sync)
 constexpr int kBarRecFull = 2, kBarRecEmpty = 9;
 constexpr int kRecBarThreads = 32 * (kStreamWarps + 1);   // the stream warps + the record's tail warp
+// Batch mode: records are handed over kBatch at a time (one per tail warp), double-buffered: the stream warps arrive on
+// kBarBatchFull + b after the last record of batch b, ALL tail warps sync on it and therefore run decision / window /
+// statistics at the same time -- one walk through the tail's ~25 KB of code then serves kBatch utterances instead of one
+// (the instruction-miss path, gcc, runs at 94 % of its peak with staggered tail warps).  kBarBatchEmpty + b: the tail
+// warps arrive when they are done with batch b, the stream warps sync before they refill it.
+#ifndef DSP_PIPE_BATCH
+#define DSP_PIPE_BATCH 1
+#endif
+constexpr bool kBatchMode = DSP_PIPE_BATCH != 0;
+constexpr int kBatch = kMaxTailWarps;
+constexpr int kBarBatchFull = 2, kBarBatchEmpty = 4;
+constexpr int kBatchBarThreads = 32 * (kStreamWarps + kMaxTailWarps);
 
 struct PipeLayout {
   int ring, gsum, bits, meta, rec, scratch, win, desc, part, consts, bars, total;
@@ -475,15 +487,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
   // tail warps get the issue slots they can use, the throughput-bound stream warps fill the rest)
   const int twid = wid - kStreamWarps;
   if (twid >= 0 && twid < kMaxTailWarps) {
-    if (twid >= nrec) return;
-    unsigned char* rec = smem + L.rec + (size_t)twid * L.rec_bytes;
-    int* r_int = reinterpret_cast<int*>(rec);
-    double* r_dbl = reinterpret_cast<double*>(rec + 64);
-    double* r_e = reinterpret_cast<double*>(rec + L.rec_e);
-    const unsigned short* r_z = reinterpret_cast<const unsigned short*>(rec + L.rec_z);
-    unsigned short* r_zf = reinterpret_cast<unsigned short*>(rec + L.rec_zf);
-    float* s_fe = reinterpret_cast<float*>(rec + L.rec_fe);   // indexed by full-utterance frame number
-    float* s_fm = reinterpret_cast<float*>(rec + L.rec_fm);
+    if (!kBatchMode && twid >= nrec) return;
     double* cand = reinterpret_cast<double*>(smem + L.scratch + (size_t)twid * 256);
 
     // window coefficients of the hop-128 / length-256 chain: a lane owns samples 8*(lane&15) .. +8 of
@@ -499,9 +503,24 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
     long long tp[5] = {0, 0, 0, 0, 0}, tprev = clock64();
     auto tick = [&](int i) { if (a.prof) { const long long t = clock64(); tp[i] += t - tprev; tprev = t; } };
     for (int it = 0;; ++it) {
-      bar_sync(kBarRecFull + twid, kRecBarThreads);
+      const int batch = kBatchMode ? (it & 1) : 0;
+      unsigned char* rec = smem + L.rec + (size_t)(kBatchMode ? batch * kBatch + twid : twid) * L.rec_bytes;
+      int* r_int = reinterpret_cast<int*>(rec);
+      double* r_dbl = reinterpret_cast<double*>(rec + 64);
+      double* r_e = reinterpret_cast<double*>(rec + L.rec_e);
+      const unsigned short* r_z = reinterpret_cast<const unsigned short*>(rec + L.rec_z);
+      unsigned short* r_zf = reinterpret_cast<unsigned short*>(rec + L.rec_zf);
+      float* s_fe = reinterpret_cast<float*>(rec + L.rec_fe);   // indexed by full-utterance frame number
+      float* s_fm = reinterpret_cast<float*>(rec + L.rec_fm);
+      if constexpr (kBatchMode) bar_sync(kBarBatchFull + batch, kBatchBarThreads);
+      else bar_sync(kBarRecFull + twid, kRecBarThreads);
       const int u = r_int[0];
-      if (u < 0) break;
+      if constexpr (kBatchMode) {
+        if (u == -2) break;                                   // the closing batch: every tail warp leaves
+        if (u < 0) { __syncwarp(); bar_arrive(kBarBatchEmpty + batch, kBatchBarThreads); continue; }   // padding of the last batch
+      } else {
+        if (u < 0) break;
+      }
       tick(0);
       const int n = r_int[1], f1 = r_int[2], thr = r_int[4], kmn_s = r_int[5], kmx_s = r_int[6];
       const double phi_d = r_dbl[0], inv_m = r_dbl[1], mu = r_dbl[2];
@@ -850,7 +869,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
         if (flagged) { const int s = atomicAdd(a.flag_count, 1); a.flag_list[s] = u; }
       }
       __syncwarp();
-      bar_arrive(kBarRecEmpty + twid, kRecBarThreads);
+      if constexpr (kBatchMode) bar_arrive(kBarBatchEmpty + batch, kBatchBarThreads);
+      else bar_arrive(kBarRecEmpty + twid, kRecBarThreads);
       tick(3);
     }
     if (a.prof && twid == 0 && lane == 0) for (int i = 0; i < 4; ++i) atomicAdd((unsigned long long*)&a.prof[8 + i], (unsigned long long)tp[i]);
@@ -876,18 +896,27 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
     const int par = useq & 1;
     unsigned char* rec = smem + L.rec + (size_t)rec_id * L.rec_bytes;
     int* r_int = reinterpret_cast<int*>(rec);
+    // record slot hand-off with the tail warps: per record, or (batch mode) per batch of kBatch records
+    auto rec_acquire = [&]() {
+      if constexpr (kBatchMode) { if (rec_lap > 0 && rec_id % kBatch == 0) bar_sync(kBarBatchEmpty + rec_id / kBatch, kBatchBarThreads); }
+      else { if (rec_lap > 0) bar_sync(kBarRecEmpty + rec_id, kRecBarThreads); }
+    };
+    auto rec_publish = [&]() {
+      if constexpr (kBatchMode) { if (rec_id % kBatch == kBatch - 1) bar_arrive(kBarBatchFull + rec_id / kBatch, kBatchBarThreads); }
+      else bar_arrive(kBarRecFull + rec_id, kRecBarThreads);
+      if (++rec_id == nrec) { rec_id = 0; ++rec_lap; }
+    };
     if (dsc.y < 0) {
       // misaligned start: hand the utterance to the float64 replay, keep the pipeline's sequence numbers
-      if (rec_lap > 0) bar_sync(kBarRecEmpty + rec_id, kRecBarThreads);
+      rec_acquire();
       if (stid == 0) { const int s = atomicAdd(a.flag_count, 1); a.flag_list[s] = u; r_int[0] = u; r_int[1] = 0; r_int[2] = 0; r_int[3] = 0;
         r_int[4] = 0; r_int[5] = 0; r_int[6] = 0; double* rd = reinterpret_cast<double*>(rec + 64); rd[0] = 0.0; rd[1] = 1.0; rd[2] = 0.0; }
       __syncwarp();
       if (lane == 0 && (edges || swid == 0)) mbar_arrive(&bar_empty[cslot]);
       __syncwarp();
-      bar_arrive(kBarRecFull + rec_id, kRecBarThreads);
+      rec_publish();
       if (++cslot == R) { cslot = 0; ++clap; }
       ++useq;
-      if (++rec_id == nrec) { rec_id = 0; ++rec_lap; }
       continue;
     }
     const int n = dsc.y;
@@ -1085,7 +1114,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
     stick(4);
 
     // =========================== pass F: EPD frames -> record =========================
-    if (rec_lap > 0) bar_sync(kBarRecEmpty + rec_id, kRecBarThreads);
+    rec_acquire();
     stick(5);
     {
       const double phi_d = s_consts[par * 8 + 0], inv_m = s_consts[par * 8 + 1];
@@ -1184,13 +1213,27 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
     }
     if (edges) release_slots();
     __syncwarp();
-    bar_arrive(kBarRecFull + rec_id, kRecBarThreads);
+    rec_publish();
     cslot += nchunks; if (cslot >= R) { cslot -= R; ++clap; }
     ++useq;
-    if (++rec_id == nrec) { rec_id = 0; ++rec_lap; }
     stick(6);
   }
   if (a.prof && stid == 0) { for (int i = 0; i < 7; ++i) atomicAdd((unsigned long long*)&a.prof[i], (unsigned long long)sp[i]); atomicAdd((unsigned long long*)&a.prof[15], (unsigned long long)useq); }
+  if constexpr (kBatchMode) {
+    // pad the open batch with "skip" records, then one closing batch that makes every tail warp leave
+    auto mark = [&](int code) {
+      if (rec_lap > 0 && rec_id % kBatch == 0) bar_sync(kBarBatchEmpty + rec_id / kBatch, kBatchBarThreads);
+      if (stid == 0) *reinterpret_cast<int*>(smem + L.rec + (size_t)rec_id * L.rec_bytes) = code;
+      __syncwarp();
+      if (rec_id % kBatch == kBatch - 1) bar_arrive(kBarBatchFull + rec_id / kBatch, kBatchBarThreads);
+      if (++rec_id == nrec) { rec_id = 0; ++rec_lap; }
+    };
+#pragma unroll 1
+    while (rec_id % kBatch != 0) mark(-1);
+#pragma unroll 1
+    for (int k = 0; k < kBatch; ++k) mark(-2);
+    return;
+  }
   // tell the tail warps to stop: one terminator record each
 #pragma unroll 1
   for (int k = 0; k < nrec; ++k) {
@@ -1210,6 +1253,18 @@ bool pipe_kernel_plan(int64_t max_len, int cap_frames, int fl, size_t smem_limit
   if (max_len > 65535 || cap_frames > 65535 || fl > 65535) return false;      // 16-bit crossing counts, int32 sums
   const int chunks = (int)std::max<int64_t>((max_len + kChunkSamples - 1) / kChunkSamples, 1);
   const int capG = chunks * kGroupsPerChunk;
+  if (kBatchMode) {
+    // two batches of records; the ring keeps the utterance in flight plus at least a quarter of the next one
+    const int nrec = 2 * kBatch;
+    const PipeLayout fixed = make_pipe_layout(0, capG, cap_frames, fl, nrec);
+    const long long room = (long long)smem_limit - fixed.total - 1024;
+    int R = (int)(room / (kChunkBytes + 16));
+    if (R > kMaxRingSlots) R = kMaxRingSlots;
+    if (R < chunks + std::max(2, chunks / 4)) return false;
+    plan->ring_slots = R; plan->n_rec = nrec; plan->cap_groups = capG;
+    plan->smem = (size_t)make_pipe_layout(R, capG, cap_frames, fl, nrec).total;
+    return true;
+  }
   for (int nrec = kMaxTailWarps; nrec >= 2; --nrec) {
     const PipeLayout fixed = make_pipe_layout(0, capG, cap_frames, fl, nrec);
     const long long room = (long long)smem_limit - fixed.total - 1024;        // static shared memory + slack
