@@ -1043,6 +1043,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
           const uint32_t x1 = E ^ O, x2 = (O ^ (E >> 1)) & 0x7fffffffu;
           s_meta[g] = (uint32_t)(__popc(x1) + __popc(x2)) | ((E & 1u) << 8) | ((O & 1u) << 9) | ((E >> 31) << 10) | ((O >> 31) << 11);
         }
+        // this chunk's last read: hand the slot back now, not after the warp's other chunks (the producer refills
+        // the ring in order, and the next utterance's last chunks are the ones pass A ends up waiting for)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[s]);
       }
     } else {
 #pragma unroll 1
@@ -1111,7 +1115,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       if (edges) { for (int c = lane; c < nchunks; c += 32) { int s = cslot + c; if (s >= R) s -= R; mbar_arrive(&bar_empty[s]); } }
       else if (lane == 0) { for (int c = swid; c < nchunks; c += kStreamWarps) { int s = cslot + c; if (s >= R) s -= R; mbar_arrive(&bar_empty[s]); } }
     };
-    if (!edges) release_slots();
+    if (!edges && !fastb) release_slots();
     stick(3);
     bar_sync(kBarStream, kStreamThreads);
     stick(4);
