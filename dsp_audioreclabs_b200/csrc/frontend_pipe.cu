@@ -35,13 +35,16 @@ constexpr int kChunkSamples = 2048;        // samples per ring slot
 constexpr int kChunkBytes = 2 * kChunkSamples;
 constexpr int kGroupsPerChunk = kChunkSamples / kGroup;   // 32: one group per stream lane
 #ifndef DSP_PIPE_STREAM_WARPS
-#define DSP_PIPE_STREAM_WARPS 12
+#define DSP_PIPE_STREAM_WARPS 8
 #endif
+// 8 stream warps (512 threads, 128 registers each) measure best with the batch hand-off below: 3.12 ms per 100k
+// utterances against 3.26 (12 warps), 3.69 (16) and 3.57 (4) -- every stream warp repeats ~140 instructions of
+// per-utterance set-up, and 22 chunks split 3/3/3/3/3/3/2/2 over 8 warps.  More than 8 use the register split.
 constexpr int kStreamWarps = DSP_PIPE_STREAM_WARPS;       // a multiple of 4: whole warpgroups (setmaxnreg)
 constexpr int kMaxTailWarps = 7;
 constexpr int kPipeWarps = kStreamWarps + kMaxTailWarps + 1;
-constexpr int kPipeThreads = 32 * kPipeWarps;             // 768
-// Register split (setmaxnreg, per warpgroup): the stream warps run short integer loops and give their
+constexpr int kPipeThreads = 32 * kPipeWarps;             // 512
+// Register split (setmaxnreg, per warpgroup; only for kStreamWarps > 8): the stream warps run short integer loops and give their
 // registers to the tail warps, which keep whole sequences in registers.  The launch allocates
 // kLaunchRegs = 65536 / kPipeThreads registers per thread (rounded down to 8) and the CTA owns only those:
 // setmaxnreg.inc can take no more than the stream warps have given back, or it waits forever.
