@@ -1026,19 +1026,21 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
         if (g * kGroup + kGroup <= n) {
           const unsigned char* gp = s_ring + (size_t)s * kChunkBytes + lane * (2 * kGroup);
           const int rot = lane & 7;
+          // r = the two bits of a word at positions 0 and 16; r << c drops them into bit c of both planes at once, so a
+          // word costs one compare and one shift-add, with no doubling chain (word k of processing unit pp: bit 4 pp + k)
           uint32_t acc0 = 0, acc1 = 0;
 #pragma unroll
-          for (int pp = 3; pp >= 0; --pp) {      // descending: the first sample ends up in bit 0
+          for (int pp = 0; pp < 4; ++pp) {
             const int4 qa = *reinterpret_cast<const int4*>(gp + 16 * ((pp + rot) & 7));
             const int4 qb = *reinterpret_cast<const int4*>(gp + 16 * ((pp + 4 + rot) & 7));
-            acc0 = acc0 + acc0 + __viaddmin_s16x2_relu((uint32_t)qa.w, t2, 0x00010001u);
-            acc1 = acc1 + acc1 + __viaddmin_s16x2_relu((uint32_t)qb.w, t2, 0x00010001u);
-            acc0 = acc0 + acc0 + __viaddmin_s16x2_relu((uint32_t)qa.z, t2, 0x00010001u);
-            acc1 = acc1 + acc1 + __viaddmin_s16x2_relu((uint32_t)qb.z, t2, 0x00010001u);
-            acc0 = acc0 + acc0 + __viaddmin_s16x2_relu((uint32_t)qa.y, t2, 0x00010001u);
-            acc1 = acc1 + acc1 + __viaddmin_s16x2_relu((uint32_t)qb.y, t2, 0x00010001u);
-            acc0 = acc0 + acc0 + __viaddmin_s16x2_relu((uint32_t)qa.x, t2, 0x00010001u);
-            acc1 = acc1 + acc1 + __viaddmin_s16x2_relu((uint32_t)qb.x, t2, 0x00010001u);
+            acc0 += __viaddmin_s16x2_relu((uint32_t)qa.x, t2, 0x00010001u) << (4 * pp + 0);
+            acc1 += __viaddmin_s16x2_relu((uint32_t)qb.x, t2, 0x00010001u) << (4 * pp + 0);
+            acc0 += __viaddmin_s16x2_relu((uint32_t)qa.y, t2, 0x00010001u) << (4 * pp + 1);
+            acc1 += __viaddmin_s16x2_relu((uint32_t)qb.y, t2, 0x00010001u) << (4 * pp + 1);
+            acc0 += __viaddmin_s16x2_relu((uint32_t)qa.z, t2, 0x00010001u) << (4 * pp + 2);
+            acc1 += __viaddmin_s16x2_relu((uint32_t)qb.z, t2, 0x00010001u) << (4 * pp + 2);
+            acc0 += __viaddmin_s16x2_relu((uint32_t)qa.w, t2, 0x00010001u) << (4 * pp + 3);
+            acc1 += __viaddmin_s16x2_relu((uint32_t)qb.w, t2, 0x00010001u) << (4 * pp + 3);
           }
           // planes in processing order -> undo the rotation: bit a of E / O is sample 2a / 2a+1 of the group
           const uint32_t ep = __byte_perm(acc0, acc1, 0x5410), op = __byte_perm(acc0, acc1, 0x7632);
