@@ -704,6 +704,13 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
 
       // =========================== windowed frame features =============================
       const int seg = end - start;
+      // The trimmed segment has usually left L2 since the stream warps read it (the batch hand-off puts ~10 utterances
+      // per SM between the two uses): ask for all of it now, so that the chain below waits for DRAM once, not per block.
+      {
+        const char* pbase = reinterpret_cast<const char*>(x + start);
+#pragma unroll 1
+        for (int o = lane * 128; o < 2 * seg; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pbase + o));
+      }
       const int f2 = frame_count32(seg, fl, fs);
       const double sc_e = inv_m * inv_m, sc_m = inv_m;
       const int zbase = start / fs;        // start is a multiple of the hop: feature frame t is frame zbase + t
