@@ -266,3 +266,29 @@ def test_wav_encodings_through_the_batch_api(ctx, golden_fe):
         res = batch.frontend_batch(raw, np.array([0, raw.size]), 1102, 441, "hamming", channels=ch, ctx=ctx)
         assert [int(res.start[0]), int(res.end[0])] == list(g[f"wav/{key}/start_end"]), key
         assert np.allclose(res.stats[0], g[f"wav/{key}/stats"], rtol=2e-5, atol=0), key
+
+
+@pytest.mark.parametrize("n_utts", [1, 6, 7, 8, 149, 1036, 2100])
+def test_batch_handoff_sizes(ctx, n_utts):
+    """The pipelined kernel hands records to its tail warps 7 at a time, double-buffered, with padded and closing
+    batches at the end of a CTA's work: batch sizes around those boundaries (per CTA: 1 utterance ... ~14), ragged
+    lengths incl. utterances shorter than a frame, must give what the oracle gives for every utterance."""
+    from dsp_audioreclabs_b200 import batch
+    from oracle import frontend_oracle as fo, synth
+    lens = list(synth.ragged_lengths(22, 0.15, 1.2, seed=n_utts)) + [100, 255]
+    base = [synth.utterance_pcm(i, int(n), seed0=400 + n_utts) for i, n in enumerate(lens)]
+    utts = [base[(5 * i) % len(base)] for i in range(n_utts)]
+    s, o, l = batch.pack_aligned(utts)
+    ctx.set_tuning("pcm_variant", PIPE)
+    try:
+        res = batch.frontend_batch(s, o, 256, 128, "hanning", emit_epd_lists=True, lengths=l, ctx=ctx)
+    finally:
+        ctx.set_tuning("pcm_variant", -1)
+    refs = [fo.frontend_utterance(u, 256, 128, "hanning") for u in base]
+    for b in range(n_utts):
+        r = refs[(5 * b) % len(base)]
+        assert (int(res.start[b]), int(res.end[b]), int(res.n_frames[b])) == (r["start"], r["end"], len(r["zcr"])), b
+        if len(r["zcr"]):
+            e, m, z = res.frames(b)
+            assert np.array_equal(z.astype(np.float64), r["zcr"]), b
+            assert np.allclose(e, r["energy"], rtol=1e-5, atol=0) and np.allclose(m, r["magnitude"], rtol=1e-5, atol=0), b
