@@ -13,7 +13,7 @@ all: $(LIB)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $@.ptxas.log || (cat $@.ptxas.log; exit 1)
 
 %.o: %.cpp $(HDRS)
-	$(NVCC) -O3 -std=c++17 -Xcompiler -fPIC,-Wall -c $< -o $@
+	$(NVCC) -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC,-Wall -c $< -o $@
 
 $(LIB): $(OBJS)
 	$(NVCC) -shared -gencode arch=compute_100a,code=sm_100a -o $@ $(OBJS) -lcudart
