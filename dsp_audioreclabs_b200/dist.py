@@ -8,6 +8,9 @@
   (`ShardedKNN.predict`).  When the train matrix is small (D = 15) the cheaper equivalent is
   to all-gather the train rows once and classify locally (`ShardedKNN.predict_replicated`).
 
+* DTW template matching (the self-specified MFCC + DTW variant): templates sharded by row, queries replicated,
+  the same single all-gather of top-k candidates (`ShardedDTW`).
+
 torch.distributed is plumbing only; the compute callbacks default to the CUDA library and can
 be replaced (the CPU gloo tests plug in the oracle, since there is no CPU implementation here).
 """
@@ -118,6 +121,62 @@ class ShardedKNN:
             self._full = (tr.contiguous(), lb.contiguous())
         d2, idx, lab = self._topk(self._full[0], self._full[1], queries_local.contiguous(), self.k, 0)
         return self._merge(d2[None], idx[None], lab[None])
+
+
+class ShardedDTW:
+    """Row-sharded DTW template matching (BASELINE config 5: templates sharded by row, queries replicated, ONE
+    all-gather of the per-shard top-k candidates).  Sequences are lists of [frames, dim] float32 arrays.
+
+    local_topk(templates, labels, queries, k, index_base) -> (cost[m,k] f64, idx[m,k] i64, label[m,k] i32), sorted by
+    (cost, index); defaults to the CUDA library (mfcc_dtw.DTWClassifier).  The merge is a k-way selection over the
+    R sorted lists by (cost, global index) and a vote with ties to the smallest label."""
+
+    def __init__(self, n_neighbors=1, group=None, local_topk=None):
+        self.k = int(n_neighbors)
+        self.group = group
+        self._topk = local_topk or self._cuda_topk
+        self._clf = None
+
+    def _cuda_topk(self, templates, labels, queries, k, index_base):
+        from .mfcc_dtw import DTWClassifier
+        if self._clf is None:
+            self._clf = DTWClassifier(k, index_base=index_base).fit(templates, labels)
+        nc, ni, nl = self._clf.kneighbors(queries)
+        return nc, ni, self._clf.classes_[np.clip(nl, 0, None)].astype(np.int32) * (nl >= 0) - (nl < 0)
+
+    def fit(self, template_shard, labels_shard):
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        n = torch.tensor([len(template_shard)], dtype=torch.int64)
+        sizes = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(sizes, n, group=self.group)
+        self.index_base = int(sum(int(s.item()) for s in sizes[:rank]))
+        self.templates, self.labels = list(template_shard), np.asarray(labels_shard)
+        return self
+
+    def kneighbors(self, queries):
+        """(cost[m,k], global template index[m,k], label[m,k]) for the (replicated) queries."""
+        world = dist.get_world_size(self.group)
+        c, i, l = self._topk(self.templates, self.labels, queries, self.k, self.index_base)
+        c, i, l = (torch.from_numpy(np.ascontiguousarray(a)) for a in (c.astype(np.float64), i.astype(np.int64), l.astype(np.int32)))
+        cc = [torch.empty_like(c) for _ in range(world)]
+        ci = [torch.empty_like(i) for _ in range(world)]
+        cl = [torch.empty_like(l) for _ in range(world)]
+        dist.all_gather(cc, c, group=self.group)      # the single candidate exchange (three dtypes)
+        dist.all_gather(ci, i, group=self.group)
+        dist.all_gather(cl, l, group=self.group)
+        cost = torch.cat(cc, dim=1).numpy(); idx = torch.cat(ci, dim=1).numpy(); lab = torch.cat(cl, dim=1).numpy()
+        idx_key = np.where(idx < 0, np.iinfo(np.int64).max, idx)
+        order = np.lexsort((idx_key, cost), axis=1)[:, :self.k]
+        take = lambda a: np.take_along_axis(a, order, axis=1)
+        return take(cost), take(idx), take(lab)
+
+    def predict(self, queries):
+        _, _, lab = self.kneighbors(queries)
+        out = np.empty(len(lab), dtype=np.int64)
+        for q, row in enumerate(lab):
+            vals, cnt = np.unique(row[row >= 0], return_counts=True)
+            out[q] = vals[np.argmax(cnt)] if len(vals) else -1      # argmax: first maximum = smallest label
+        return out
 
 
 def zscore_stats_allreduce(x_local, group=None):

@@ -81,3 +81,48 @@ def test_utterance_shards_balance_by_samples():
         per = np.array([off[b[r + 1]] - off[b[r]] for r in range(world)])
         assert per.max() - per.min() <= 2 * lens.max()
     assert list(ddist.balanced_bounds(10, 4)) == [0, 3, 6, 8, 10]
+
+
+def _oracle_dtw_topk(templates, labels, queries, k, index_base):
+    from oracle import mfcc_dtw_oracle as mo
+    idx, cost = mo.dtw_topk(queries, templates, min(k, len(templates)))
+    return cost, idx + index_base, np.asarray(labels)[idx].astype(np.int32)
+
+
+def _dtw_data():
+    rng = np.random.default_rng(21)
+    def seq(n, c): return (rng.standard_normal((n, 4)) * 0.2 + np.cos(np.arange(n)[:, None] * (0.2 + 0.1 * c))).astype(np.float32)
+    labels = np.arange(11) % 3
+    temps = [seq(int(rng.integers(5, 30)), c) for c in labels]
+    quers = [seq(int(rng.integers(5, 30)), c) for c in (0, 1, 2, 1, 0)]
+    return temps, labels, quers
+
+
+def _dtw_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from dsp_audioreclabs_b200 import dist as ddist
+    temps, labels, quers = _dtw_data()
+    tb = ddist.balanced_bounds(len(temps), world)
+    sd = ddist.ShardedDTW(3, local_topk=_oracle_dtw_topk).fit(temps[tb[rank]:tb[rank + 1]], labels[tb[rank]:tb[rank + 1]])
+    assert sd.index_base == tb[rank]
+    cost, idx, lab = sd.kneighbors(quers)
+    np.savez(os.path.join(out_dir, f"d{rank}.npz"), cost=cost, idx=idx, lab=lab, pred=sd.predict(quers))
+    dist.destroy_process_group()
+
+
+def test_sharded_dtw_world2_matches_single_rank(tmp_path):
+    """Templates sharded by row over two ranks, one candidate all-gather: the merged neighbours equal the
+    single-rank result of the (self-)oracle on every rank."""
+    from oracle import mfcc_dtw_oracle as mo
+    world = 2
+    mp.spawn(_dtw_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    temps, labels, quers = _dtw_data()
+    ridx, rcost = mo.dtw_topk(quers, temps, 3)
+    for r in range(world):
+        o = np.load(tmp_path / f"d{r}.npz")
+        assert np.array_equal(o["idx"], ridx) and np.allclose(o["cost"], rcost, rtol=1e-12)
+        assert np.array_equal(o["lab"], labels[ridx])
+        votes = [np.bincount(labels[row], minlength=3).argmax() for row in ridx]
+        assert np.array_equal(o["pred"], votes)

@@ -70,3 +70,29 @@ def test_mfcc_dtw_template_matching_end_to_end(ctx):
     assert np.allclose(nc, rcost, rtol=2e-4, atol=0)             # fp32 MFCC features feed the costs
     agree = np.mean(ni[:, 0] == ridx[:, 0])
     assert agree >= 0.9, agree
+
+
+def test_sharded_dtw_with_the_cuda_callback(ctx):
+    """dist.ShardedDTW on a one-rank gloo group with its default (CUDA) scoring: the exchange logic itself is covered
+    for two ranks on CPU (tests/test_dist_gloo.py)."""
+    import socket
+    import torch.distributed as tdist
+    from dsp_audioreclabs_b200 import dist as ddist
+    from oracle import mfcc_dtw_oracle as mo
+    rng = np.random.default_rng(2)
+    def seq(n, c): return (rng.standard_normal((n, 13)) * 0.2 + np.cos(np.arange(n)[:, None] * (0.2 + 0.1 * c))).astype(np.float32)
+    labels = np.arange(12) % 4 + 10
+    temps = [seq(int(rng.integers(8, 60)), c) for c in labels]
+    quers = [seq(int(rng.integers(8, 60)), c) for c in (10, 11, 12, 13, 11)]
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]
+    tdist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        sd = ddist.ShardedDTW(3).fit(temps, labels)
+        cost, idx, lab = sd.kneighbors(quers)
+        ridx, rcost = mo.dtw_topk(quers, temps, 3)
+        assert np.array_equal(idx, ridx) and np.allclose(cost, rcost, rtol=1e-5)
+        assert np.array_equal(lab, labels[ridx])
+        assert np.array_equal(sd.predict(quers), [np.bincount(labels[r]).argmax() for r in ridx])
+    finally:
+        tdist.destroy_process_group()
