@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-knn", action="store_true", help="skip the secondary KNN numbers")
     ap.add_argument("--cpu-utts", type=int, default=600, help="utterances in the cpu_baseline sample")
     return ap.parse_args()
 
@@ -198,6 +199,42 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def knn_section(dev, ctx):
+    """Secondary numbers of the same run (not part of `value`): the KNN classify step of the full pipeline
+    (BASELINE configs[2] shape on one GPU: 1 M queries x 100 k train rows, D = 15, k = 3 -- fp32 tiled scan + float64
+    certificate) and the sequence-feature variant (D = 1024: tcgen05 tensor-core scan), device-resident, CUDA events."""
+    import torch
+    from dsp_audioreclabs_b200 import device as devapi
+    out = {}
+    try:
+        for tag, (m, n, d) in {"statistical_d15": (1000000, 100000, 15), "sequence_d1024": (131072, 50000, 1024)}.items():
+            g = torch.Generator(device=dev).manual_seed(5)
+            centers = torch.randn(10, d, device=dev, generator=g, dtype=torch.float64) * 1.5
+            ytr = torch.randint(0, 10, (n,), device=dev, generator=g)
+            xtr = centers[ytr] + torch.randn(n, d, device=dev, generator=g, dtype=torch.float64)
+            yq = torch.randint(0, 10, (m,), device=dev, generator=g)
+            xq = centers[yq] + torch.randn(m, d, device=dev, generator=g, dtype=torch.float64)
+            knn = devapi.DeviceKNN(3, ctx=ctx, device=dev).fit(xtr.contiguous(), ytr.to(torch.int32))
+            knn.predict(xq)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            knn.predict(xq)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            rescanned, kind = knn.last_stats()
+            out[tag] = {"queries": m, "train_rows": n, "dim": d, "ms": ms, "queries_per_s": m / (ms / 1e3),
+                        "algorithmic_TFLOPs": 2.0 * d * m * n / (ms / 1e3) / 1e12,
+                        "scan": {1: "fp32 tiled", 2: "tcgen05 split-fp16 (3 MMA passes)"}.get(kind, "float64"),
+                        "rescanned_in_float64": rescanned}
+            del xtr, xq, knn
+            torch.cuda.empty_cache()
+    except Exception as exc:      # secondary numbers must never break the bench line
+        out["error"] = repr(exc)
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -343,6 +380,8 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single(args.cpu_utts)
+        if world == 1 and not args.no_knn:
+            line["knn"] = knn_section(dev, ctx)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
