@@ -292,3 +292,27 @@ def test_batch_handoff_sizes(ctx, n_utts):
             e, m, z = res.frames(b)
             assert np.array_equal(z.astype(np.float64), r["zcr"]), b
             assert np.allclose(e, r["energy"], rtol=1e-5, atol=0) and np.allclose(m, r["magnitude"], rtol=1e-5, atol=0), b
+
+
+def test_pipelined_kernel_replays_misaligned_utterances(ctx):
+    """A packed (CSR) batch whose utterances do not start on 16-byte boundaries, forced through the pipelined
+    kernel: aligned utterances take the fast path, the others are handed to the float64 replay inside the same
+    call (records still travel through the batch hand-off) -- every result equals the oracle's."""
+    from dsp_audioreclabs_b200 import batch
+    from oracle import frontend_oracle as fo, synth
+    lens = [9001, 12347, 7777, 15003, 8192, 1000, 5000, 30001, 44100, 20011, 333, 25000, 26001, 40000, 12000, 13001]
+    utts = [synth.utterance_pcm(70 + i, n, seed0=3) for i, n in enumerate(lens)] * 3
+    samples, off = pack(utts)
+    ctx.set_tuning("pcm_variant", PIPE)
+    try:
+        res = batch.frontend_batch(samples, off, 256, 128, "hamming", emit_epd_lists=True, ctx=ctx)
+    finally:
+        ctx.set_tuning("pcm_variant", -1)
+    replayed = int((res.status >= 0x100).sum())
+    assert 0 < replayed < len(utts)                      # 8192-, 1000-, 40000-, 12000-sample boundaries keep some starts aligned
+    for b, u in enumerate(utts):
+        r = fo.frontend_utterance(u, 256, 128, "hamming")
+        assert (int(res.start[b]), int(res.end[b]), int(res.n_frames[b])) == (r["start"], r["end"], len(r["zcr"])), b
+        e, m, z = res.frames(b)
+        assert np.array_equal(z.astype(np.float64), r["zcr"]), b
+        assert np.allclose(e, r["energy"], rtol=1e-5, atol=0) and np.allclose(m, r["magnitude"], rtol=1e-5, atol=0), b
