@@ -36,6 +36,8 @@ class FrontendOutputs(C.Structure):
         ("n_frames", C.c_void_p), ("status", C.c_void_p),
         ("energy", C.c_void_p), ("magnitude", C.c_void_p), ("zcr", C.c_void_p),
         ("stats", C.c_void_p), ("epd_energy", C.c_void_p), ("epd_zcr", C.c_void_p),
+        ("energy_f64", C.c_void_p), ("magnitude_f64", C.c_void_p), ("zcr_f64", C.c_void_p),
+        ("stats_f64", C.c_void_p), ("epd_zcr_f64", C.c_void_p), ("frames_f64", C.c_void_p),
     ]
 
 

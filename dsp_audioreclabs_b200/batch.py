@@ -127,6 +127,11 @@ class FrontendResult:
         n = int(self.n_frames[b])
         return self.energy[o:o + n], self.magnitude[o:o + n], self.zcr[o:o + n]
 
+    def dense(self, b):
+        """frame_signal's (n_frames, frame_length) float64 matrix of utterance b (emit_dense_frames=True)."""
+        o = int(self.feat_offsets[b])
+        return self.dense_frames[o:o + int(self.n_frames[b])]
+
     def epd_lists(self, b):
         o = int(self.epd_offsets[b])
         n = int(self.n_epd_frames[b])
@@ -151,12 +156,16 @@ def pack_aligned(utterances, align=8):
 def frontend_batch(samples, offsets, frame_length, frame_shift, window_type="hamming",
                    do_endpoint_detection=True, energy_high_ratio=0.5, energy_low_ratio=0.1,
                    zcr_threshold_ratio=1.5, channels=1, emit_epd_lists=False, force_exact=False,
-                   emit_frames=True, lengths=None, ctx=None):
+                   emit_frames=True, lengths=None, ctx=None, float64_outputs=False, emit_dense_frames=False):
     """preprocess -> endpoint_detection -> frame_signal -> extract_frame_features -> 15 statistics
     for every utterance of a packed batch (src/audio_processing.py:364-394 and
     src/feature_extraction.py:91-112, batched).  `samples` is int16 / uint8 PCM or float32/64.
     emit_frames=False skips the download of the per-frame sequences (the callers of the
-    'statistical' method only consume the 15 statistics, run_experiments.py:102-107)."""
+    'statistical' method only consume the 15 statistics, run_experiments.py:102-107).
+    float64_outputs=True returns energy / magnitude / zcr / stats / epd_zcr as float64 computed by the
+    float64 replay kernel (bit-identical to the NumPy path; what the drop-in per-file API hands to the
+    reference's callers); emit_dense_frames=True adds `dense_frames`, the [total frames, frame_length]
+    float64 matrix of frame_signal (row feat_offsets[b] + t)."""
     ctx = _host_ctx(ctx)
     samples = np.ascontiguousarray(samples)
     if samples.dtype not in _DTYPES:
@@ -170,18 +179,27 @@ def frontend_batch(samples, offsets, frame_length, frame_shift, window_type="ham
     fo, eo, max_len = plan(offsets, p, lengths)
     if b and (offsets[0] < 0 or offsets[-1] > samples.size):
         raise ValueError("offsets exceed the sample buffer")
+    ft = np.float64 if float64_outputs else np.float32
     res = FrontendResult(
         start=np.zeros(b, np.int32), end=np.zeros(b, np.int32), n_epd_frames=np.zeros(b, np.int32),
         n_frames=np.zeros(b, np.int32), status=np.zeros(b, np.int32),
-        energy=np.zeros(int(fo[-1]), np.float32) if emit_frames else None,
-        magnitude=np.zeros(int(fo[-1]), np.float32) if emit_frames else None,
-        zcr=np.zeros(int(fo[-1]), np.float32) if emit_frames else None, stats=np.zeros((b, 15), np.float32),
+        energy=np.zeros(int(fo[-1]), ft) if emit_frames else None,
+        magnitude=np.zeros(int(fo[-1]), ft) if emit_frames else None,
+        zcr=np.zeros(int(fo[-1]), ft) if emit_frames else None, stats=np.zeros((b, 15), ft),
         feat_offsets=fo, epd_offsets=eo, max_len=max_len,
         epd_energy=np.zeros(int(eo[-1]), np.float64) if emit_epd_lists else None,
-        epd_zcr=np.zeros(int(eo[-1]), np.float32) if emit_epd_lists else None)
-    out = FrontendOutputs(_ptr(res.start), _ptr(res.end), _ptr(res.n_epd_frames), _ptr(res.n_frames),
-                          _ptr(res.status), _ptr(res.energy), _ptr(res.magnitude), _ptr(res.zcr),
-                          _ptr(res.stats), _ptr(res.epd_energy), _ptr(res.epd_zcr))
+        epd_zcr=np.zeros(int(eo[-1]), ft) if emit_epd_lists else None,
+        dense_frames=np.zeros((int(fo[-1]), int(frame_length)), np.float64) if emit_dense_frames else None)
+    if float64_outputs:
+        out = FrontendOutputs(_ptr(res.start), _ptr(res.end), _ptr(res.n_epd_frames), _ptr(res.n_frames),
+                              _ptr(res.status), None, None, None, None, _ptr(res.epd_energy), None,
+                              _ptr(res.energy), _ptr(res.magnitude), _ptr(res.zcr), _ptr(res.stats),
+                              _ptr(res.epd_zcr), _ptr(res.dense_frames))
+    else:
+        out = FrontendOutputs(_ptr(res.start), _ptr(res.end), _ptr(res.n_epd_frames), _ptr(res.n_frames),
+                              _ptr(res.status), _ptr(res.energy), _ptr(res.magnitude), _ptr(res.zcr),
+                              _ptr(res.stats), _ptr(res.epd_energy), _ptr(res.epd_zcr),
+                              None, None, None, None, None, _ptr(res.dense_frames))
     check(ctx.lib.dsp_frontend_batch_host(ctx.handle, _ptr(samples), _DTYPES[samples.dtype],
                                           _ptr(offsets), _ptr(lengths), b, C.byref(p), C.byref(out)))
     return res

@@ -91,7 +91,7 @@ size_t dtype_size(int dtype) {
 }
 
 struct Slot {
-  DevBuf samples, off, foff, eoff, ints, stats, feat, epd_e, epd_z;
+  DevBuf samples, off, foff, eoff, ints, stats, feat, epd_e, epd_z, f64;
   PinBuf h_off;
   cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;
   bool busy = false;
@@ -104,8 +104,13 @@ struct dsp_context {
   int sm_count = 0;
   cudaStream_t own = nullptr, stream = nullptr, s_in = nullptr, s_out = nullptr;
   int64_t launches = 0;
-  int win_type = -1, win_len = -1;
-  DevBuf win64, win32;
+  // window tables stay resident per (type, length): a context that alternates windows (three front ends sharing one
+  // context, a sweep over frame lengths) never re-uploads or synchronises, and kernels still running on a previously
+  // installed stream keep reading the table they were launched with
+  struct WinEntry { int type, len; DevBuf w64, w32; };
+  std::vector<WinEntry*> windows;
+  const double* win64 = nullptr;
+  const float* win32 = nullptr;
   DevBuf counters;   // [0] work counter (u32)  [1] flag count (i32)
   DevBuf flag_list, zbuf, seqbuf;
   size_t occ_smem = 0;
@@ -146,18 +151,27 @@ int host_window(int type, int n, std::vector<double>& w) {
 }
 
 int ensure_window(dsp_context* c, int type, int fl) {
-  if (c->win_type == type && c->win_len == fl) return DSP_OK;
+  for (auto* e : c->windows)
+    if (e->type == type && e->len == fl) { c->win64 = e->w64.as<double>(); c->win32 = e->w32.as<float>(); return DSP_OK; }
   std::vector<double> w;
   int rc = host_window(type, fl, w);
   if (rc) return rc;
   std::vector<float> wf(w.begin(), w.end());
-  CU(c->win64.ensure(sizeof(double) * (size_t)fl + 16));
-  CU(c->win32.ensure(sizeof(float) * (size_t)fl + 16));
-  // the previous window may still be in use by kernels on the stream
-  CU(cudaStreamSynchronize(c->stream));
-  CU(cudaMemcpy(c->win64.p, w.data(), sizeof(double) * (size_t)fl, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(c->win32.p, wf.data(), sizeof(float) * (size_t)fl, cudaMemcpyHostToDevice));
-  c->win_type = type; c->win_len = fl;
+  if (c->windows.size() >= 256) {            // a pathological sweep: drop the tables once nothing can be reading them
+    CU(cudaDeviceSynchronize());
+    for (auto* e : c->windows) { e->w64.release(); e->w32.release(); delete e; }
+    c->windows.clear();
+  }
+  auto* e = new dsp_context::WinEntry{type, fl, {}, {}};
+  if (e->w64.ensure(sizeof(double) * (size_t)fl + 16) != cudaSuccess || e->w32.ensure(sizeof(float) * (size_t)fl + 16) != cudaSuccess) {
+    e->w64.release(); e->w32.release(); delete e;
+    return fail(DSP_ERR_NOMEM, "device allocation failed");
+  }
+  // a fresh table nobody reads yet: blocking copies from the stack vectors are safe and happen once per (type, length)
+  CU(cudaMemcpy(e->w64.p, w.data(), sizeof(double) * (size_t)fl, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(e->w32.p, wf.data(), sizeof(float) * (size_t)fl, cudaMemcpyHostToDevice));
+  c->windows.push_back(e);
+  c->win64 = e->w64.as<double>(); c->win32 = e->w32.as<float>();
   return DSP_OK;
 }
 
@@ -165,7 +179,7 @@ int check_params(const dsp_frontend_params* p) {
   if (!p) return fail(DSP_ERR_INVALID, "params is NULL");
   if (p->frame_length < 1 || p->frame_shift < 1) return fail(DSP_ERR_INVALID, "frame_length and frame_shift must be >= 1");
   if (p->window < 0 || p->window > 2) return fail(DSP_ERR_INVALID, "unsupported window type: %d", p->window);
-  if (p->channels != 1 && p->channels != 2) return fail(DSP_ERR_INVALID, "channels must be 1 or 2");
+  if (p->channels != 1 && p->channels != 2) return fail(DSP_ERR_INVALID, "channels must be 1 or 2 (load_wav only down-mixes two channels, audio_processing.py:43-44: pass other files as 1 channel)");
   return DSP_OK;
 }
 
@@ -193,7 +207,7 @@ int launch_exact(dsp_context* c, const void* samples, int dtype, const int64_t* 
   a.fl = p->frame_length; a.fs = p->frame_shift;
   a.do_epd = p->do_endpoint_detection; a.pre_mode = ex.pre_mode; a.do_features = ex.do_features;
   a.hr = p->energy_high_ratio; a.lr = p->energy_low_ratio; a.zr = p->zcr_threshold_ratio;
-  a.win = c->win64.as<double>();
+  a.win = c->win64;
   a.zbuf = c->zbuf.as<double>(); a.zbuf_stride = std::max<int64_t>(max_len, 1);
   a.seqbuf = c->seqbuf.as<double>(); a.seq_cap = cap_frames;
   if (out) a.out = *out;
@@ -225,7 +239,13 @@ int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_
   const int fl = p->frame_length, fs = p->frame_shift;
   const int64_t cap_frames64 = std::max<int64_t>(frame_count_host_device(max_len, fl, fs), 1);
 
-  bool fast = dtype == DSP_S16 && p->channels == 1 && !p->force_exact && max_len <= kFastMaxLen &&
+  const bool want64 = out->energy_f64 || out->magnitude_f64 || out->zcr_f64 || out->stats_f64 || out->epd_zcr_f64 || out->frames_f64;
+  if (out->frames_f64 && !feat_offsets) return fail(DSP_ERR_INVALID, "feat_offsets is NULL");
+  if ((out->energy_f64 || out->magnitude_f64 || out->zcr_f64) && !(out->energy_f64 && out->magnitude_f64 && out->zcr_f64))
+    return fail(DSP_ERR_INVALID, "energy_f64, magnitude_f64 and zcr_f64 are written together: pass all three or none");
+  if (out->energy_f64 && !feat_offsets) return fail(DSP_ERR_INVALID, "feat_offsets is NULL");
+  if (out->epd_zcr_f64 && !epd_offsets) return fail(DSP_ERR_INVALID, "epd_offsets is NULL");
+  bool fast = dtype == DSP_S16 && p->channels == 1 && !p->force_exact && !want64 && max_len <= kFastMaxLen &&
               feat_offsets;
   size_t smem = 0;
   int cap_samples = 0;
@@ -256,7 +276,7 @@ int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_
     a.offsets = offsets; a.lengths = lengths; a.feat_offsets = feat_offsets; a.epd_offsets = epd_offsets;
     a.n_utts = B; a.fl = fl; a.fs = fs; a.window = p->window; a.do_epd = p->do_endpoint_detection;
     a.hr = p->energy_high_ratio; a.lr = p->energy_low_ratio; a.zr = p->zcr_threshold_ratio;
-    a.win_f32 = c->win32.as<float>();
+    a.win_f32 = c->win32;
     a.cap_frames = (int)cap_frames64;
     a.tma_chunk = std::getenv("DSP_PIPE_DEBUG") ? std::atoi(std::getenv("DSP_PIPE_DEBUG")) : 0;   // debug switches, 0 in production
     a.ring_slots = plan.ring_slots; a.n_rec = plan.n_rec; a.cap_groups = plan.cap_groups;
@@ -295,6 +315,8 @@ int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_
   if (!fast) {
     const int grid = (int)std::min<int64_t>(B, (int64_t)c->sm_count * 4);
     ExactExtras ex;
+    ex.feat_f64[0] = out->energy_f64; ex.feat_f64[1] = out->magnitude_f64; ex.feat_f64[2] = out->zcr_f64;
+    ex.stats_f64 = out->stats_f64; ex.epd_zcr_f64 = out->epd_zcr_f64; ex.frames_out = out->frames_f64;
     return launch_exact(c, samples, dtype, offsets, lengths, feat_offsets, epd_offsets, nullptr, nullptr, B, max_len,
                         p, out, ex, grid);
   }
@@ -312,7 +334,7 @@ int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_
   a.offsets = offsets; a.lengths = lengths; a.feat_offsets = feat_offsets; a.epd_offsets = epd_offsets;
   a.n_utts = B; a.fl = fl; a.fs = fs; a.window = p->window; a.do_epd = p->do_endpoint_detection;
   a.hr = p->energy_high_ratio; a.lr = p->energy_low_ratio; a.zr = p->zcr_threshold_ratio;
-  a.win_f32 = c->win32.as<float>();
+  a.win_f32 = c->win32;
   a.cap_samples = cap_samples; a.cap_frames = (int)cap_frames64;
   a.tma_chunk = c->tma_chunk;
   a.stagger_ns = c->stagger_ns;
@@ -400,13 +422,15 @@ int dsp_destroy(dsp_context* c) {
   cudaDeviceSynchronize();
   for (auto& s : c->slot) {
     s.samples.release(); s.off.release(); s.foff.release(); s.eoff.release(); s.ints.release();
-    s.stats.release(); s.feat.release(); s.epd_e.release(); s.epd_z.release(); s.h_off.release();
+    s.stats.release(); s.feat.release(); s.epd_e.release(); s.epd_z.release(); s.f64.release(); s.h_off.release();
     if (s.ev_in) cudaEventDestroy(s.ev_in);
     if (s.ev_k) cudaEventDestroy(s.ev_k);
     if (s.ev_out) cudaEventDestroy(s.ev_out);
   }
   for (auto& b : c->tmp) b.release();
-  c->win64.release(); c->win32.release(); c->counters.release(); c->flag_list.release();
+  for (auto* e : c->windows) { e->w64.release(); e->w32.release(); delete e; }
+  c->windows.clear();
+  c->counters.release(); c->flag_list.release();
   c->zbuf.release(); c->seqbuf.release();
   if (c->own) cudaStreamDestroy(c->own);
   if (c->s_in) cudaStreamDestroy(c->s_in);
@@ -549,6 +573,10 @@ int dsp_frontend_batch_host(dsp_context* c, const void* samples, int dtype, cons
     CU(s.feat.ensure(sizeof(float) * 3 * (size_t)std::max<int64_t>(f1 - f0, 1)));
     CU(s.epd_e.ensure(sizeof(double) * (size_t)std::max<int64_t>(g1 - g0, 1)));
     CU(s.epd_z.ensure(sizeof(float) * (size_t)std::max<int64_t>(g1 - g0, 1)));
+    const bool want64 = out->energy_f64 || out->magnitude_f64 || out->zcr_f64 || out->stats_f64 || out->epd_zcr_f64 || out->frames_f64;
+    const int64_t fn64 = std::max<int64_t>(f1 - f0, 1), gn64 = std::max<int64_t>(g1 - g0, 1);
+    const size_t dense64 = out->frames_f64 ? (size_t)fn64 * (size_t)p->frame_length : 0;
+    if (want64) CU(s.f64.ensure(sizeof(double) * ((size_t)(3 * fn64 + kStats * bc + gn64) + dense64)));
     // upload
     CU(cudaMemcpyAsync(s.samples.p, src + (size_t)e0 * esz, (size_t)(e1 - e0) * esz, cudaMemcpyHostToDevice, c->s_in));
     CU(cudaMemcpyAsync(s.off.p, h, sizeof(int64_t) * 4 * (size_t)(bc + 1), cudaMemcpyHostToDevice, c->s_in));
@@ -564,6 +592,13 @@ int dsp_frontend_batch_host(dsp_context* c, const void* samples, int dtype, cons
     o.stats = s.stats.as<float>();
     o.epd_energy = out->epd_energy ? s.epd_e.as<double>() : nullptr;
     o.epd_zcr = out->epd_zcr ? s.epd_z.as<float>() : nullptr;
+    if (want64) {
+      double* d64 = s.f64.as<double>();
+      if (out->energy_f64) { o.energy_f64 = d64; o.magnitude_f64 = d64 + fn64; o.zcr_f64 = d64 + 2 * fn64; }
+      if (out->stats_f64) o.stats_f64 = d64 + 3 * fn64;
+      if (out->epd_zcr_f64) o.epd_zcr_f64 = d64 + 3 * fn64 + kStats * bc;
+      if (out->frames_f64) o.frames_f64 = d64 + 3 * fn64 + kStats * bc + gn64;
+    }
     const int64_t* doff = s.off.as<int64_t>();
     dsp_frontend_params pc = *p;
     pc.aligned16 = 1;                               // staging buffers come from cudaMalloc (256-byte aligned)
@@ -589,6 +624,12 @@ int dsp_frontend_batch_host(dsp_context* c, const void* samples, int dtype, cons
     CU(d2h(out->zcr ? out->zcr + f0 : nullptr, o.zcr, sizeof(float) * (size_t)(f1 - f0)));
     CU(d2h(out->epd_energy ? out->epd_energy + g0 : nullptr, o.epd_energy, sizeof(double) * (size_t)(g1 - g0)));
     CU(d2h(out->epd_zcr ? out->epd_zcr + g0 : nullptr, o.epd_zcr, sizeof(float) * (size_t)(g1 - g0)));
+    CU(d2h(out->energy_f64 ? out->energy_f64 + f0 : nullptr, o.energy_f64, sizeof(double) * (size_t)(f1 - f0)));
+    CU(d2h(out->magnitude_f64 ? out->magnitude_f64 + f0 : nullptr, o.magnitude_f64, sizeof(double) * (size_t)(f1 - f0)));
+    CU(d2h(out->zcr_f64 ? out->zcr_f64 + f0 : nullptr, o.zcr_f64, sizeof(double) * (size_t)(f1 - f0)));
+    CU(d2h(out->stats_f64 ? out->stats_f64 + b0 * kStats : nullptr, o.stats_f64, sizeof(double) * kStats * (size_t)bc));
+    CU(d2h(out->epd_zcr_f64 ? out->epd_zcr_f64 + g0 : nullptr, o.epd_zcr_f64, sizeof(double) * (size_t)(g1 - g0)));
+    CU(d2h(out->frames_f64 ? out->frames_f64 + (size_t)f0 * (size_t)p->frame_length : nullptr, o.frames_f64, sizeof(double) * (size_t)(f1 - f0) * (size_t)p->frame_length));
     CU(cudaEventRecord(s.ev_out, c->s_out));
     s.busy = true;
     b0 = b1;

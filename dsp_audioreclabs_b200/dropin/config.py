@@ -2,9 +2,9 @@
 environment overrides (config.py:13,22), so experiments/run_experiments.py, train_model.py,
 ablation_study.py and compare_feature_methods.py read identical values.
 
-One deliberate difference: RESULTS_DIR is created lazily under the current working directory
-when `DSP_RESULTS_DIR` is unset and this package directory is not writable, instead of always
-next to this file (config.py:25-26 creates it at import time); the name and meaning are unchanged.
+One deliberate difference: RESULTS_DIR is `DSP_RESULTS_DIR` if set, else `./results` under the
+current working directory, instead of a directory next to this file (config.py:24 uses BASE_DIR);
+like the reference (config.py:25-26) it is created at import time.  The name and meaning are unchanged.
 """
 import os
 

@@ -4,10 +4,13 @@ returns an object with fit / predict / evaluate whose neighbours come from the C
 the semantics of sklearn's KNeighborsClassifier the reference wraps).
 
 The other classifier types are outside this hot path: they are
-delegated unchanged to the reference's own module when one is importable as
-`reference_models` or given by DSP_REFERENCE_MODELS, otherwise they raise."""
+delegated unchanged to the reference's own src/models.py, loaded by file from the reference `src/`
+directory this package found on sys.path (src/__init__.py), or to the module named by
+DSP_REFERENCE_MODELS; without either they raise."""
 import importlib
+import importlib.util
 import os
+import sys
 
 import numpy as np
 
@@ -65,12 +68,35 @@ class TraditionalClassifier:
                 'confusion_matrix': cm}
 
 
+_ref_models = None
+
+
 def _reference_models():
-    name = os.environ.get('DSP_REFERENCE_MODELS', 'reference_models')
+    global _ref_models
+    if _ref_models is not None:
+        return _ref_models
+    name = os.environ.get('DSP_REFERENCE_MODELS')
+    if name:
+        try:
+            _ref_models = importlib.import_module(name)
+            return _ref_models
+        except ImportError:
+            pass
+    import src as _pkg
+    for d in getattr(_pkg, 'REFERENCE_SRC_DIRS', []):
+        path = os.path.join(d, 'models.py')
+        if os.path.isfile(path):
+            spec = importlib.util.spec_from_file_location('src._reference_models', path)
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules['src._reference_models'] = mod
+            spec.loader.exec_module(mod)
+            _ref_models = mod
+            return mod
     try:
-        return importlib.import_module(name)
+        _ref_models = importlib.import_module('reference_models')
     except ImportError:
-        return None
+        _ref_models = None
+    return _ref_models
 
 
 def create_classifier(classifier_type, **kwargs):
@@ -80,7 +106,8 @@ def create_classifier(classifier_type, **kwargs):
     if classifier_type in ('naive_bayes', 'decision_tree', 'svm', 'mlp'):
         ref = _reference_models()
         if ref is None:
-            raise ValueError(f"classifier '{classifier_type}' is outside the CUDA hot path; make the reference's "
-                             "src/models.py importable as `reference_models` to delegate it")
+            raise ValueError(f"classifier '{classifier_type}' is outside the CUDA hot path and the reference's "
+                             "src/models.py was not found (run through `python -m dsp_audioreclabs_b200.run`, or "
+                             "set DSP_REFERENCE_ROOT / DSP_REFERENCE_MODELS)")
         return ref.create_classifier(classifier_type, **kwargs)
     raise ValueError(f"不支持的分类器类型: {classifier_type}")

@@ -79,7 +79,9 @@ def read_packed(paths, threads=None):
     for i in range(n):
         w = info[i]
         if w.status == 0 and w.sample_width in (1, 2) and w.data_bytes % w.sample_width == 0:
-            by_enc.setdefault((w.sample_width, w.channels), []).append(i)
+            # load_wav only down-mixes n_channels == 2 (src/audio_processing.py:43-44); any other count is used as the
+            # flat interleaved array it is, i.e. as one channel
+            by_enc.setdefault((w.sample_width, 2 if w.channels == 2 else 1), []).append(i)
     groups = []
     arr, _keep = _path_array(paths)
     for (width, ch), idx in sorted(by_enc.items()):

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DSPFRONT_ABI_VERSION 1
+#define DSPFRONT_ABI_VERSION 2
 
 typedef enum {
   DSP_OK = 0,
@@ -90,6 +90,18 @@ typedef struct {
   float* stats;          /* [B,15] extract_statistical_features (:65-88) */
   double* epd_energy;    /* ragged, energy_list of endpoint_detection (:183) */
   float* epd_zcr;        /* ragged, zcr_list (:184) */
+  /* ABI 2: the same results as the reference holds them, in float64.  Requesting ANY of these routes the
+   * whole batch through the float64 replay kernel, whose values are bit-identical to the NumPy path
+   * (the drop-in process_audio_file / extract_features_from_frames use them; the float outputs above
+   * are the throughput path, held to the north star's 1e-5 relative). */
+  double* energy_f64;    /* ragged like `energy` */
+  double* magnitude_f64; /* ragged like `magnitude` */
+  double* zcr_f64;       /* ragged like `zcr` */
+  double* stats_f64;     /* [B,15] */
+  double* epd_zcr_f64;   /* ragged like `epd_zcr` */
+  double* frames_f64;    /* dense windowed frames of frame_signal (:299-333): row feat_offsets[b] + t holds
+                          * frame t of utterance b, frame_length values each -- only for callers that really
+                          * read the (F, fl) matrix process_audio_file returns */
 } dsp_frontend_outputs;
 
 typedef struct dsp_context dsp_context;

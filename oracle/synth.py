@@ -50,3 +50,26 @@ def batch_pcm(batch, n_samples=SAMPLE_RATE, seed0=1234, first_index=0, lengths=N
     for b in range(batch):
         samples[offsets[b]:offsets[b + 1]] = utterance_pcm(first_index + b, int(lengths[b]), seed0)
     return samples, offsets
+
+
+def write_wav(path, pcm, width=2, channels=1, sample_rate=SAMPLE_RATE):
+    import wave
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(channels)
+        w.setsampwidth(width)
+        w.setframerate(sample_rate)
+        w.writeframes(np.ascontiguousarray(pcm).tobytes())
+
+
+def write_config1_dataset(root, classes=10, clips=20, seed=1234):
+    """BASELINE configs[0] / SURVEY.md 8(d) config 1: class folders '0'..'9' x `clips` 16-bit mono WAVs of
+    U(0.8, 1.2) s (class c, clip i is utterance 10 i + c of the generator).  Returns the number of files."""
+    import os
+    rng = np.random.default_rng(seed)
+    for c in range(classes):
+        d = os.path.join(str(root), str(c))
+        os.makedirs(d, exist_ok=True)
+        for i in range(clips):
+            n = int(rng.uniform(0.8, 1.2) * SAMPLE_RATE)
+            write_wav(os.path.join(d, f"clip_{i:02d}.wav"), utterance_pcm(10 * i + c, n, seed0=seed))
+    return classes * clips

@@ -32,7 +32,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in dspfront.h but not exported"
     assert sorted(_capi.SIGNATURES) == declared      # the ctypes stub binds exactly the header
-    assert lib.dsp_abi_version() == 1
+    assert lib.dsp_abi_version() == 2
 
 
 def test_no_cpu_fallback(lib):

@@ -1,6 +1,6 @@
 """GPU checks of the MFCC + DTW variant (BASELINE config 5) against its SELF-ORACLE (oracle/mfcc_dtw_oracle.py):
 the reference has no MFCC / DTW code, so parity here is unpinned by construction.
-Tolerances (north star): MFCC 1e-4 of the frame's coefficient scale, DTW costs 1e-5 relative (fp32)."""
+Tolerances (north star): MFCC 1e-4 relative per coefficient (floor: 5 % of the frame's largest coefficient), DTW costs 1e-5 relative (fp32)."""
 import numpy as np
 import pytest
 
@@ -22,8 +22,11 @@ def test_mfcc_matches_the_self_oracle(ctx):
         assert (st, en) == (int(res.start[b]), int(res.end[b]))
         got = mf[off[b]:off[b + 1]]
         assert got.shape == ref.shape, b
+        # north star: 1e-4 relative per coefficient.  Floor for near-zero coefficients: a coefficient is a signed sum of
+        # 26 log-mel energies, so below 5 % of the frame's largest coefficient it is held to 1e-4 of that floor instead
         scale = np.abs(ref).max(axis=1, keepdims=True) if len(ref) else 1.0
-        assert np.all(np.abs(got - ref) <= 1e-4 * scale), (b, np.abs(got - ref).max())
+        tol = 1e-4 * np.maximum(np.abs(ref), 0.05 * scale)
+        assert np.all(np.abs(got - ref) <= tol), (b, float((np.abs(got - ref) / tol).max()))
 
 
 @pytest.mark.parametrize("dim", [13, 1, 16])
