@@ -1,7 +1,7 @@
 # Build libdspfront.so (CUDA, sm_100a only) and the C oracle.
 NVCC ?= nvcc
 CSRC := dsp_audioreclabs_b200/csrc
-SRCS := $(CSRC)/capi.cu $(CSRC)/frontend_pcm.cu $(CSRC)/frontend_pipe.cu $(CSRC)/frontend_exact.cu $(CSRC)/knn.cu $(CSRC)/knn_dense.cu $(CSRC)/mfcc_dtw.cu $(CSRC)/misc.cu
+SRCS := $(CSRC)/capi.cu $(CSRC)/frontend_pcm.cu $(CSRC)/frontend_pipe.cu $(CSRC)/frontend_exact.cu $(CSRC)/knn.cu $(CSRC)/knn_dense.cu $(CSRC)/knn_tc16.cu $(CSRC)/mfcc_dtw.cu $(CSRC)/misc.cu
 HDRS := $(wildcard $(CSRC)/*.cuh) include/dspfront.h
 OBJS := $(SRCS:.cu=.o) $(CSRC)/wavio.o
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC,-Wall,-Wno-unused-function --expt-relaxed-constexpr

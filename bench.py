@@ -1,19 +1,25 @@
 #!/usr/bin/env python3
-"""Headline benchmark: audio-seconds processed per second by the batched front end.
+"""Headline benchmark: audio-seconds processed per second by the full pipeline --
+features + endpoints + KNN classify (BASELINE.json `metric`).
 
-Workload (BASELINE.json configs[1]): 100,000 synthetic 1 s utterances per GPU (44.1 kHz int16
-PCM, SURVEY.md 8(d) recipe generated on the device), frame 256 / shift 128, the three window
-types cycled across steps.  One step = one pass of the fused front end (DC removal, peak
-normalisation, endpoint detection, framing + window, energy / magnitude / ZCR, 15 statistics)
-over the whole batch.
+Workload per GPU and step (BASELINE.json configs[1] batch through the pipeline of configs[2]): 100,000 synthetic
+1 s utterances (44.1 kHz int16 PCM, SURVEY.md 8(d) recipe generated on the device), frame 256 / shift 128, the three
+window types cycled across steps -> fused front end (DC removal, peak normalisation, endpoint detection, framing +
+window, energy / magnitude / ZCR, 15 statistics) -> z-score with the train set's mean / std -> KNN (k = 3) against a
+100,000-utterance train set whose features were extracted by the same front end before the timed region.
+N = 1: the whole train set lives on the GPU.  N > 1 (one rank per GPU, weak scaling: 100,000 query utterances per
+GPU): the train rows are sharded over the ranks; every step all-gathers the ranks' query features, scores ALL of them
+against the local rows, exchanges the packed top-k candidates in ONE NCCL all-gather and merges + votes
+(`dist.ShardedKNN.predict_sharded`).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]           # our CUDA path
-  python bench.py --impl reference ...                          # reference algorithm on host cores
-  torchrun --nproc-per-node N ... bench.py --gpus N ...         # N>1: one rank per GPU, weak scaling
+  python bench.py --impl reference ...                          # the reference's own code on the host cores
+  torchrun --nproc-per-node N ... bench.py --gpus N ...         # N>1
 
-Rank 0 prints ONE JSON line.  `value` is device-resident throughput (CUDA events, max over
-ranks); `e2e` is the same metric through the host-buffer C-ABI call with the H2D / D2H copies
-inside the timed region.
+Rank 0 prints ONE JSON line.  `value` is device-resident throughput of the whole pipeline (CUDA events, max over
+ranks); `roofline` is the dominant kernel (the fused front end) from CUDA events around its launches inside the same
+timed region; `frontend_only` is configs[1] by itself; `e2e` is the same pipeline through the host-buffer API with
+the H2D / D2H copies inside the timed region.
 """
 import argparse
 import json
@@ -31,8 +37,8 @@ sys.path.insert(0, ROOT)
 SR = 44100
 FL, FS = 256, 128
 WINDOWS = ("rectangular", "hamming", "hanning")
-UTT_LEN = 44104        # samples per utterance: 1 s rounded up to a multiple of 8 samples, so every
-                       # utterance of the packed batch starts 16-byte aligned (TMA bulk copies)
+UTT_LEN = 44100        # samples per utterance: exactly 1 s, packed CSR (every other utterance starts 8 bytes off a
+                       # 16-byte boundary: the kernel's producer realigns those on chip)
 
 
 def parse():
@@ -47,13 +53,17 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-knn", action="store_true", help="skip the secondary KNN numbers")
     ap.add_argument("--cpu-utts", type=int, default=600, help="utterances in the cpu_baseline sample")
+    ap.add_argument("--train-utts", type=int, default=100000, help="utterances of the KNN train set (whole job)")
+    ap.add_argument("--knn-path", default="sharded", choices=["sharded", "replicated"],
+                    help="N>1: row-sharded train set with the candidate all-gather (north star), or train rows replicated")
     return ap.parse_args()
 
 
 # --------------------------------------------------------------------------------------------
-def synth_batch_device(n_utts, device, seed, chunk=2048):
+def synth_batch_device(n_utts, device, seed, chunk=2048, first_index=0):
     """SURVEY.md 8(d) generator on the GPU: noise floor, 50 ms unvoiced onset, Hann-enveloped
-    two-partial burst, DC offset, truncation to int16.  Returns (samples, CSR offsets[n+1])."""
+    two-partial burst, DC offset, truncation to int16.  Utterance i has class (first_index + i) mod 10.
+    Returns (samples, CSR offsets[n+1])."""
     import torch
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
@@ -65,7 +75,7 @@ def synth_batch_device(n_utts, device, seed, chunk=2048):
     on = int(0.050 * SR)
     for c0 in range(0, n_utts, chunk):
         c = min(chunk, n_utts - c0)
-        cls = (torch.arange(c0, c0 + c, device=device) % 10).float()[:, None]
+        cls = (torch.arange(first_index + c0, first_index + c0 + c, device=device) % 10).float()[:, None]
         u = torch.rand(c, 3, device=device, generator=gen)
         b0 = torch.floor((0.15 + 0.15 * u[:, 0:1]) * n)
         b1 = torch.floor((0.60 + 0.25 * u[:, 1:2]) * n)
@@ -143,38 +153,116 @@ def measured_hbm_peak():
 
 
 # --------------------------------------------------------------------------------------------
+# CPU legs: the reference's own code (oracle/_ref, an unmodified copy made by oracle/make_ref.py) when it travelled
+# with the snapshot, else the oracle port.  Test/bench infrastructure only -- never on the product path.
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+N_TRAIN_CPU = 100000
+_cpu = {}
+
+
+def _cpu_setup():
+    """-> dict(kind, fe(pcm, window) -> 15 stats, zscore(X, mu, sd), clf with predict): the reference's modules when
+    oracle/_ref exists (kind 'reference'), else the oracle port (kind 'port')."""
+    if _cpu:
+        return _cpu
+    if os.path.isfile(os.path.join(REF_DIR, "src", "audio_processing.py")):
+        sys.path.insert(0, REF_DIR)
+        import src.audio_processing as ap
+        import src.feature_extraction as fe
+        import src.models as mo
+
+        def front(pcm, window):
+            # process_audio_file minus the WAV decode (src/audio_processing.py:364-394) + the 'statistical' features
+            x = ap.preprocess(pcm / 32768.0)
+            s, e, _, _ = ap.endpoint_detection(x, FL, FS, 0.5, 0.1, 1.5)
+            frames = ap.frame_signal(x[s:e], FL, FS, window)
+            return fe.extract_features_from_frames(frames, method="statistical")[0]
+
+        _cpu.update(kind="reference", front=front, zscore=fe.normalize_features,
+                    make_clf=lambda: mo.create_classifier("knn", n_neighbors=3),
+                    what="oracle/_ref: the reference's own src.audio_processing / src.feature_extraction / src.models (sklearn KNN)")
+    else:
+        from oracle import frontend_oracle as fo, knn_oracle as ko
+
+        class _Clf:
+            def fit(self, X, y):
+                self.X, self.y = X, y
+
+            def predict(self, Q):
+                return ko.knn_predict(self.X, self.y, Q, 3)
+
+        _cpu.update(kind="port", front=lambda pcm, window: fo.frontend_utterance(pcm, FL, FS, window)["stats"],
+                    zscore=fo.zscore, make_clf=_Clf,
+                    what="oracle/frontend_oracle.py + oracle/knn_oracle.py (oracle/_ref is absent)")
+    return _cpu
+
+
+def _cpu_train_set(n_base=512):
+    """A 100,000 x 15 train matrix for the CPU KNN: the reference front end on `n_base` generated utterances, resampled
+    with 5 % per-feature jitter (running the CPU front end on 100,000 utterances would take ~7 CPU-minutes per core)."""
+    from oracle import synth
+    c = _cpu_setup()
+    base = np.stack([c["front"](synth.utterance_pcm(900000 + i, UTT_LEN, 4242), "hamming") for i in range(n_base)])
+    rng = np.random.default_rng(7)
+    pick = rng.integers(0, n_base, N_TRAIN_CPU)
+    X = base[pick] + rng.standard_normal((N_TRAIN_CPU, 15)) * 0.05 * base.std(axis=0)
+    y = (900000 + pick) % 10
+    Xn, mu, sd = c["zscore"](X)
+    clf = c["make_clf"]()
+    clf.fit(Xn, y)
+    c.update(clf=clf, mu=mu, sd=sd)
+
+
+_UTTS = []          # the CPU sample, generated before the timed region (and before the fork: shared copy-on-write)
+
+
+def _cpu_sample(n):
+    from oracle import synth
+    while len(_UTTS) < n:
+        _UTTS.append(synth.utterance_pcm(len(_UTTS), UTT_LEN, 777))
+
+
 def _cpu_worker(args):
-    """Reference algorithm (oracle port, per-frame NumPy loops) over a slice of utterances."""
-    first, count, seed0 = args
-    from oracle import frontend_oracle as fo, synth
-    utts = [synth.utterance_pcm(first + i, UTT_LEN, seed0) for i in range(count)]
+    """The whole pipeline for a slice of the resident sample on one core: front end per utterance, z-score, KNN predict."""
+    first, count = args
+    c = _cpu_setup()
+    utts = _UTTS[first:first + count]
     t0 = time.perf_counter()
-    for i, pcm in enumerate(utts):
-        fo.frontend_utterance(pcm, FL, FS, WINDOWS[i % 3])
-    return time.perf_counter() - t0
+    X = np.stack([c["front"](pcm, WINDOWS[i % 3]) for i, pcm in enumerate(utts)])
+    t1 = time.perf_counter()
+    c["clf"].predict(c["zscore"](X, c["mu"], c["sd"])[0])
+    t2 = time.perf_counter()
+    return t2 - t0, t1 - t0
 
 
 def cpu_baseline_single(n_utts):
-    dt = _cpu_worker((0, n_utts, 777))
-    return {"value": n_utts * (UTT_LEN / SR) / dt, "unit": "audio-s/s", "cores": 1, "kind": "port",
-            "sample": f"{n_utts} utterances of the same generator/config (1 s, 256/128, windows cycled), "
-                      f"oracle/frontend_oracle.py (NumPy float64, per-frame loops as the reference), {dt:.1f} s"}
+    c = _cpu_setup()
+    _cpu_train_set()
+    _cpu_sample(n_utts)
+    dt, dt_fe = _cpu_worker((0, n_utts))
+    return {"value": n_utts * (UTT_LEN / SR) / dt, "unit": "audio-s/s", "cores": 1, "kind": c["kind"],
+            "frontend_only_value": n_utts * (UTT_LEN / SR) / dt_fe,
+            "sample": f"{n_utts} utterances of the same generator/config (1 s, 256/128, windows cycled) through {c['what']}: "
+                      f"front end {dt_fe:.1f} s + z-score + KNN(3) predict against a {N_TRAIN_CPU}-row train set {dt - dt_fe:.1f} s"}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm on all host cores (rank 0 only)."""
+    """--impl reference: the reference's CPU implementation of the pipeline on all host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
     for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
         os.environ[v] = "1"
-    cores = os.cpu_count() or 1
+    c = _cpu_setup()
+    _cpu_train_set()                    # before the fork: the workers share the fitted classifier copy-on-write
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     per_worker = 24
+    _cpu_sample(cores * per_worker)     # inputs resident before the timed region, the same sample every step (as on the GPU arm)
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         def step(s):
-            jobs = [(s * cores * per_worker + w * per_worker, per_worker, 777) for w in range(cores)]
+            jobs = [(w * per_worker, per_worker) for w in range(cores)]
             t0 = time.perf_counter()
             pool.map(_cpu_worker, jobs)
             return time.perf_counter() - t0
@@ -184,25 +272,30 @@ def run_reference(args):
     n = cores * per_worker * args.steps
     val = n * (UTT_LEN / SR) / total
     line = {
-        "impl": "reference", "metric": "audio-seconds processed/sec (features+endpoints)", "value": val,
+        "impl": "reference", "metric": METRIC, "value": val,
         "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: batched front end, 1 s utterances, frame 256 / shift 128, three windows cycled",
-                   "sample_per_step": f"{cores * per_worker} utterances (bounded sample of the 100k-utterance batch)"},
-        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
-                         "sample": f"{cores * per_worker} utterances per step x {args.steps} steps, multiprocessing.Pool({cores}), "
-                                   "oracle/frontend_oracle.py (the reference is pure Python and does not travel to the GPU box)"},
+        "config": {"workload": WORKLOAD,
+                   "sample_per_step": f"{cores * per_worker} utterances (bounded sample of the 100k-utterance batch; per-utterance cost is constant)"},
+        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": c["kind"],
+                         "sample": f"{cores * per_worker} utterances per step x {args.steps} steps, multiprocessing.Pool({cores}), {c['what']}; "
+                                   f"KNN against a {N_TRAIN_CPU}-row train set fitted before the timed region"},
         "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+METRIC = "audio-seconds processed/sec (features+endpoints+KNN)"
+WORKLOAD = ("configs[1] batch through the configs[2] pipeline: 100k synthetic 1 s utterances per GPU, frame 256 / shift 128, three windows "
+            "cycled over steps -> fused front end -> z-score -> KNN(3) vs a 100k-utterance train set")
+
+
 def knn_section(dev, ctx):
-    """Secondary numbers of the same run (not part of `value`): the KNN classify step of the full pipeline
-    (BASELINE configs[2] shape on one GPU: 1 M queries x 100 k train rows, D = 15, k = 3 -- fp32 tiled scan + float64
-    certificate) and the sequence-feature variant (D = 1024: tcgen05 tensor-core scan), device-resident, CUDA events."""
+    """Secondary numbers of the same run (not part of `value`): the classify step alone at BASELINE configs[2] size on one GPU
+    (1 M queries x 100 k train rows, D = 15, k = 3: tcgen05 K = 16 candidate filter + float64 certificate) and the
+    sequence-feature variant (D = 1024: tcgen05 tensor-core scan), device-resident, CUDA events."""
     import torch
     from dsp_audioreclabs_b200 import device as devapi
     out = {}
@@ -226,7 +319,8 @@ def knn_section(dev, ctx):
             rescanned, kind = knn.last_stats()
             out[tag] = {"queries": m, "train_rows": n, "dim": d, "ms": ms, "queries_per_s": m / (ms / 1e3),
                         "algorithmic_TFLOPs": 2.0 * d * m * n / (ms / 1e3) / 1e12,
-                        "scan": {1: "fp32 tiled", 2: "tcgen05 split-fp16 (3 MMA passes)"}.get(kind, "float64"),
+                        "scan": {1: "fp32 tiled", 2: "tcgen05 split-fp16 (3 MMA passes)",
+                                 3: "tcgen05 K=16 filter, split-fp16 (3 MMA passes), |t|^2 as 16th feature"}.get(kind, "float64"),
                         "rescanned_in_float64": rescanned}
             del xtr, xq, knn
             torch.cuda.empty_cache()
@@ -235,11 +329,24 @@ def knn_section(dev, ctx):
     return out
 
 
+def traffic_of_record(kernel_src):
+    """dram bytes per launch of the front-end kernel from the committed ncu capture of THIS source file (profiles/
+    traffic_r02.json carries the sha of csrc/frontend_pipe.cu it was taken on); None when the kernel changed since."""
+    import hashlib
+    tp = os.path.join(ROOT, "profiles", "traffic_r02.json")
+    try:
+        rec = json.load(open(tp))
+        sha = hashlib.sha256(open(kernel_src, "rb").read()).hexdigest()[:16]
+        return rec.get("dram_bytes_per_launch") if rec.get("source_sha16") == sha else None
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from dsp_audioreclabs_b200 import batch, device as devapi
+    from dsp_audioreclabs_b200 import batch, device as devapi, dist as ddist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -258,21 +365,58 @@ def run_ours(args):
 
     n_utts = args.utts
     ctx = batch.default_context(local)
-    # utterance shards: rank r owns utterances [r*n_utts, (r+1)*n_utts) of the global batch; the
-    # front end needs no collective
-    samples, row_offsets = synth_batch_device(n_utts, dev, seed=1234 + rank)
     stream = torch.cuda.Stream(device=dev)
-    frontends = {w: devapi.DeviceFrontend(row_offsets, FL, FS, w, ctx=ctx, device=dev) for w in WINDOWS}
     audio_s_per_step = n_utts * (UTT_LEN / SR)
 
-    def step(i):
-        frontends[WINDOWS[i % 3]].run(samples, stream=stream)
+    # ---- train set (outside the timed region, like model weights): rank r owns rows [tb[r], tb[r+1]) -----------------
+    tb = ddist.balanced_bounds(args.train_utts, world)
+    n_tr = int(tb[rank + 1] - tb[rank])
+    with torch.cuda.stream(stream):
+        tr_samples, tr_offsets = synth_batch_device(n_tr, dev, seed=990000 + rank, first_index=int(tb[rank]))
+        tr_fe = devapi.DeviceFrontend(tr_offsets, FL, FS, "hamming", ctx=ctx, device=dev)
+        tr_fe.run(tr_samples, stream=stream)
+        x_tr = tr_fe.stats.double().contiguous()
+        y_tr = (torch.arange(int(tb[rank]), int(tb[rank + 1]), device=dev) % 10).to(torch.int32)
+        if world > 1:
+            mean, std = ddist.zscore_stats_allreduce(x_tr)          # one tiny all-reduce (fit time)
+            std = torch.where(std == 0, torch.ones_like(std), std)
+            x_tr_n, _, _ = devapi.zscore_device(x_tr, mean, std, ctx=ctx)
+        else:
+            x_tr_n, mean, std = devapi.zscore_device(x_tr, ctx=ctx)
+        if world > 1:
+            knn = ddist.ShardedKNN(3, replicate_below=(0 if args.knn_path == "sharded" else 1 << 62)).fit(x_tr_n.contiguous(), y_tr)
+            predict = knn.predict
+        else:
+            knn = devapi.DeviceKNN(3, ctx=ctx, device=dev).fit(x_tr_n.contiguous(), y_tr)
+            predict = knn.predict
+    stream.synchronize()
+    del tr_samples, tr_fe
+    torch.cuda.empty_cache()
+
+    # ---- query utterances: rank r owns utterances [r*n_utts, (r+1)*n_utts) of the global batch ------------------------
+    samples, row_offsets = synth_batch_device(n_utts, dev, seed=1234 + rank, first_index=rank * n_utts)
+    y_q = (torch.arange(rank * n_utts, (rank + 1) * n_utts, device=dev) % 10).to(torch.int32)
+    frontends = {w: devapi.DeviceFrontend(row_offsets, FL, FS, w, ctx=ctx, device=dev) for w in WINDOWS}
+    qn = torch.empty(n_utts, 15, dtype=torch.float64, device=dev)
+    ev_fe = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    labels = [None]
+
+    def step(i, timed=None):
+        """One pass of the hot path over the rank's batch; everything is enqueued on `stream`."""
+        fe = frontends[WINDOWS[i % 3]]
+        if timed is not None:
+            ev_fe[timed][0].record(stream)
+        fe.run(samples, stream=stream)
+        if timed is not None:
+            ev_fe[timed][1].record(stream)
+        devapi.zscore_apply_f32(fe.stats, mean, std, out=qn, ctx=ctx)
+        labels[0] = predict(qn)
 
     with torch.cuda.stream(stream):
         for i in range(max(args.warmup, 3)):
             step(i)
     barrier()
-    # ---- timed region: K steps, CUDA events on the launching stream -------------------------
+    # ---- timed region: K steps, CUDA events on the launching stream ---------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -281,10 +425,11 @@ def run_ours(args):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
     torch.cuda.cudart().cudaProfilerStart()      # `ncu --profile-from-start off` lists exactly the timed region's launches
-    ev[0].record(stream)
-    for i in range(args.steps):
-        step(i)
-        ev[i + 1].record(stream)
+    with torch.cuda.stream(stream):
+        ev[0].record(stream)
+        for i in range(args.steps):
+            step(i, timed=i)
+            ev[i + 1].record(stream)
     stream.synchronize()
     torch.cuda.cudart().cudaProfilerStop()
     barrier()
@@ -292,40 +437,80 @@ def run_ours(args):
     launches = ctx.launch_count - launches0
     total_ms = ev[0].elapsed_time(ev[-1])
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    fe_ms = [a.elapsed_time(b) for a, b in ev_fe]
+    tmax = torch.tensor([total_ms, float(np.mean(fe_ms))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms_max = float(tmax.item())
+    total_ms_max, fe_ms_max = float(tmax[0].item()), float(tmax[1].item())
     value = world * audio_s_per_step * args.steps / (total_ms_max / 1000.0)
 
-    # ---- roofline of the dominant kernel (frontend_pipe_kernel, csrc/frontend_pipe.cu) --------
+    # ---- roofline of the dominant kernel (frontend_pipe_kernel, csrc/frontend_pipe.cu): CUDA events around its
+    # launches inside the timed region --------------------------------------------------------------------------------
     per_window = {}
     for wi, w in enumerate(WINDOWS):
-        ms = [step_ms[i] for i in range(args.steps) if i % 3 == wi]
+        ms = [fe_ms[i] for i in range(args.steps) if i % 3 == wi]
         if ms:
             per_window[w] = {"ms": float(np.mean(ms)), "algorithmic_bytes": frontends[w].algorithmic_bytes()}
     alg_bytes = float(np.mean([v["algorithmic_bytes"] for v in per_window.values()]))
-    avg_ms = float(np.mean(step_ms))
+    avg_fe_ms = float(np.mean(fe_ms))
+    avg_step_ms = float(np.mean(step_ms))
     peak, peak_src = measured_hbm_peak()
-    achieved = alg_bytes / (avg_ms / 1000.0) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    achieved = alg_bytes / (avg_fe_ms / 1000.0) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "frontend_pipe_kernel<true>", "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": avg_ms}
+                "traffic": traffic_of_record(os.path.join(ROOT, "dsp_audioreclabs_b200", "csrc", "frontend_pipe.cu")),
+                "kernel": "frontend_pipe_kernel<true>", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": avg_fe_ms,
+                "share_of_step": avg_fe_ms / avg_step_ms}
+    # pipeline-level HBM fraction: the front end's bytes + 4 D per query + 4 D n_train once + 4 per label
+    pipe_bytes = alg_bytes + 4.0 * 15 * n_utts + 4.0 * 15 * args.train_utts + 4.0 * n_utts
+    pipeline = {"ms_per_step": avg_step_ms, "frontend_ms": avg_fe_ms, "zscore_knn_ms": avg_step_ms - avg_fe_ms,
+                "algorithmic_bytes_per_step": pipe_bytes, "hbm_GBps": pipe_bytes / (avg_step_ms / 1e3) / 1e9,
+                "hbm_frac": pipe_bytes / (avg_step_ms / 1e3) / 1e9 / peak,
+                "knn": {"queries_per_gpu_per_step": n_utts, "train_rows": args.train_utts, "dim": 15, "k": 3,
+                        "train_layout": "whole train set on the GPU" if world == 1 else
+                        (f"rows sharded x{world}; per step: all-gather of the query features, ONE NCCL all-gather of the packed top-k candidates "
+                         f"({world * n_utts} queries x 3 x 24 B per rank), merge + vote" if args.knn_path == "sharded" else
+                         f"rows all-gathered once at fit (replicated), no per-step exchange")}}
+    frontend_only = {"workload": "configs[1]: batched front end only", "value": world * audio_s_per_step / (fe_ms_max / 1e3),
+                     "unit": "audio-s/s", "ms_per_launch_max_over_ranks": fe_ms_max}
 
-    # ---- parity spot check against the oracle on a few of the benchmarked utterances --------
+    # ---- the ragged variant of configs[1] (L ~ U(0.8, 1.2) s): the same sample stream cut at
+    # ragged offsets, i.e. utterances of arbitrary length AND arbitrary alignment; front end only, Hamming ---------------------
+    per_config = {}
+    try:
+        rng = np.random.default_rng(99 + rank)
+        lens = (rng.uniform(0.8, 1.2, int(n_utts * 1.05)) * SR).astype(np.int64)
+        r_off = np.concatenate([[0], np.cumsum(lens)])
+        r_off = r_off[: int(np.searchsorted(r_off, n_utts * UTT_LEN, side="right"))]
+        rf = devapi.DeviceFrontend(r_off, FL, FS, "hamming", ctx=ctx, device=dev)
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                rf.run(samples, stream=stream)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(6):
+                rf.run(samples, stream=stream)
+            e1.record(stream)
+        stream.synchronize()
+        r_ms = e0.elapsed_time(e1) / 6
+        r_bytes = rf.algorithmic_bytes()
+        per_config["ragged_0.8-1.2s_packed_csr"] = {
+            "utterances": int(len(r_off) - 1), "audio_s": float(r_off[-1] / SR), "ms": r_ms,
+            "audio_s_per_s": float(r_off[-1] / SR) / (r_ms / 1e3), "hbm_frac": r_bytes / (r_ms / 1e3) / 1e9 / peak,
+            "replayed_in_float64": int((rf.status >= 0x100).sum().item()),
+            "odd_sample_offsets": int((r_off[:-1] & 1).sum()), "starts_not_16B_aligned": int(((r_off[:-1] * 2) % 16 != 0).sum())}
+        del rf
+    except Exception as exc:      # secondary numbers must never break the bench line
+        per_config["error"] = repr(exc)
+
+    # ---- parity spot check against the oracle on a few of the benchmarked utterances -------------------------------------
     parity = None
     if rank == 0:
         from oracle import frontend_oracle as fo
-        f = frontends["hamming"]
-        f.run(samples, stream=stream)
+        with torch.cuda.stream(stream):
+            step(1)                               # hamming
         stream.synchronize()
+        f = frontends["hamming"]
         nchk = 24
         host = samples[: nchk * UTT_LEN].cpu().numpy()
         st, en, nf = f.start[:nchk].cpu().numpy(), f.end[:nchk].cpu().numpy(), f.n_frames[:nchk].cpu().numpy()
@@ -337,46 +522,69 @@ def run_ours(args):
             bad += not (r["start"] == st[b] and r["end"] == en[b] and r["n_frames"] == nf[b]
                         and np.array_equal(r["zcr"], zc[o:o + nf[b]].astype(np.float64)))
         parity = {"utterances_checked": nchk, "endpoint_or_zcr_mismatches": int(bad),
-                  "replayed_in_float64": int((f.status >= 0x100).sum().item())}
+                  "replayed_in_float64": int((f.status >= 0x100).sum().item()),
+                  "knn_accuracy_on_generated_classes": float((labels[0] == y_q).double().mean().item())}
+        if world == 1:
+            # KNN labels of the first queries against the float64 oracle on the SAME z-scored features
+            from oracle import knn_oracle as ko
+            nq = 64
+            ref = ko.knn_predict(x_tr_n.cpu().numpy(), y_tr.cpu().numpy(), qn[:nq].cpu().numpy(), 3)
+            parity["knn_label_mismatches_vs_oracle"] = int((ref != labels[0][:nq].cpu().numpy()).sum())
+            parity["knn_rescanned_in_float64,scan_kind"] = list(knn.last_stats())
 
-    # ---- e2e: host buffers through dsp_frontend_batch_host (H2D + D2H inside) ----------------
+    # ---- e2e: the same pipeline through the host-buffer API (H2D + D2H inside) --------------------------------------------
     e2e = None
     if not args.no_e2e:
+        if world > 1:
+            xt = torch.cat(ddist._all_gather_rows(x_tr_n.contiguous()), dim=0).cpu().numpy()
+            yt = torch.cat(ddist._all_gather_rows(y_tr.contiguous()), dim=0).cpu().numpy()
+        else:
+            xt, yt = x_tr_n.cpu().numpy(), y_tr.cpu().numpy()
+        mu_h, sd_h = mean.cpu().numpy(), std.cpu().numpy()
+        hknn = batch.KNN(3, ctx=ctx).fit(xt, yt)
         h_samples = torch.empty(samples.numel(), dtype=torch.int16, pin_memory=True)
         h_samples.copy_(samples)
         torch.cuda.synchronize()
         hs = h_samples.numpy()
-        res = None
-        for i in range(1):
+
+        def e2e_step(i):
             res = batch.frontend_batch(hs, row_offsets, FL, FS, WINDOWS[i % 3], emit_frames=False, ctx=ctx)
+            q = batch.zscore(res.stats.astype(np.float64), mu_h, sd_h, ctx=ctx)[0]
+            return res, q, hknn.predict(q)
+
+        res, q, pred = e2e_step(0)
         barrier()
         t0 = time.perf_counter()
         for i in range(args.e2e_steps):
-            res = batch.frontend_batch(hs, row_offsets, FL, FS, WINDOWS[i % 3], emit_frames=False, ctx=ctx)
+            res, q, pred = e2e_step(i)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        d2h = sum(a.nbytes for a in (res.start, res.end, res.n_epd_frames, res.n_frames, res.status, res.stats))
+        d2h = sum(a.nbytes for a in (res.start, res.end, res.n_epd_frames, res.n_frames, res.status, res.stats)) + 2 * q.nbytes + pred.nbytes
         e2e = {"value": world * audio_s_per_step * args.e2e_steps / dt, "unit": "audio-s/s",
-               "h2d_bytes_per_step": int(hs.nbytes + 3 * row_offsets.nbytes), "d2h_bytes_per_step": int(d2h),
-               "steps": args.e2e_steps, "call": "batch.frontend_batch -> dsp_frontend_batch_host (pinned host samples, chunked H2D/compute/D2H overlap; "
-                       "result read back = endpoints + frame counts + status + the 15 statistics per utterance)"}
+               "h2d_bytes_per_step": int(hs.nbytes + 3 * row_offsets.nbytes + 2 * q.nbytes), "d2h_bytes_per_step": int(d2h),
+               "steps": args.e2e_steps, "h2d_GBps_per_gpu": hs.nbytes * args.e2e_steps / dt / 1e9,
+               "call": "batch.frontend_batch (dsp_frontend_batch_host: pinned host samples, chunked H2D/compute/D2H overlap; endpoints + frame counts + "
+                       "status + 15 statistics read back) -> batch.zscore (dsp_zscore_host) -> batch.KNN.predict (dsp_knn_predict_host): host arrays in, labels out"}
         del h_samples, hs
 
     if rank == 0:
         line = {
-            "metric": "audio-seconds processed/sec (features+endpoints)", "value": value, "unit": "audio-s/s",
+            "metric": METRIC, "value": value, "unit": "audio-s/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16->f32/f64", "data": "synthetic",
-            "config": {"workload": "configs[1]: batched front end only, 100k synthetic 1 s utterances per GPU, frame 256 / shift 128, three windows cycled over steps",
+            "config": {"workload": WORKLOAD,
                        "utterances_per_gpu": n_utts, "samples_per_utterance": UTT_LEN, "frame_length": FL, "frame_shift": FS,
-                       "windows": list(WINDOWS), "parallelism": f"utterance shards x{world}, no collective",
+                       "windows": list(WINDOWS), "train_utterances": args.train_utts, "knn_k": 3,
+                       "parallelism": f"utterance shards x{world}" + ("" if world == 1 else f", KNN train rows {args.knn_path} x{world} (NCCL)"),
+                       "layout": "packed CSR, no padding between utterances",
                        "l2_policy": f"input {samples.numel() * 2 / 1e9:.2f} GB per pass >> 126 MB L2 (no flush needed)"},
-            "roofline": roofline, "per_window": per_window, "clocks": clocks, "e2e": e2e,
-            "gpu_launches": int(launches), "parity": parity,
+            "roofline": roofline, "pipeline": pipeline, "frontend_only": frontend_only, "per_window": per_window,
+            "per_config": per_config, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches), "parity": parity,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single(args.cpu_utts)

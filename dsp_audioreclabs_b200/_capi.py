@@ -85,6 +85,7 @@ SIGNATURES = {
     "dsp_sequence_stats_host": (C.c_int, [_P, _P, _I64, _P]),
     "dsp_zscore_host": (C.c_int, [_P, _P, _I64, _I32, C.c_int, _P, _P, _P]),
     "dsp_zscore_device": (C.c_int, [_P, _P, _I64, _I32, C.c_int, _P, _P, _P]),
+    "dsp_zscore_apply_f32_device": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P]),
     "dsp_knn_fit_host": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _I64, C.POINTER(_P)]),
     "dsp_knn_fit_device": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _I64, C.POINTER(_P)]),
     "dsp_knn_free": (C.c_int, [_P]),

@@ -129,6 +129,8 @@ struct dsp_knn {
   int d = 0, dp = 0, k = 0;
   float tnorm_max = 0.f;
   bool dense = false;          // tensor-core candidate scan (knn_dense.cu): feature dimension beyond the tiled scan
+  bool tc16 = false;           // d <= 15: tensor-core candidate filter (knn_tc16.cu); the fp32 tiled scan stands in when a value leaves its range
+  DevBuf tc_train, tc_q, tc_flags;
   DevBuf train64, train32, labels, tnorm, cand_idx, cand_worst, qnorm, redo_list, redo_count, nbr_label, q, o_idx, o_dist, o_lab;
   DevBuf tpacked, tnorm_dense, qpacked, qnorm_chunk, dense_flags, part_d, part_i;
 };
@@ -254,8 +256,8 @@ int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_
   constexpr int kAutoStream = 2, kAutoResident = 0;
   int variant = (c->pcm_variant >= 0 && c->pcm_variant < pcm_num_variants()) ? c->pcm_variant : (p->aligned16 ? kAutoStream : kAutoResident);
   if (pcm_variant_streams(variant) && !p->aligned16 && c->pcm_variant < 0) variant = kAutoResident;
-  // the pipelined kernel (frontend_pipe.cu): automatic for 16-byte aligned layouts, or forced by the
-  // tuning knob (pcm_variant == pcm_num_variants()); misaligned utterances inside it are replayed
+  // the pipelined kernel (frontend_pipe.cu): automatic for its geometries, or forced by the
+  // tuning knob (pcm_variant == pcm_num_variants())
   const int kPipeVariant = pcm_num_variants();
   PipePlan plan{};
   // automatic choice (tools/config_sweep.py, ms per 20k utterances, resident vs pipelined): the pipelined kernel when
@@ -264,7 +266,11 @@ int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_
   // shorter hops (128/64 2.44 vs 3.29) and frames with ragged edges (1102/441 2.1 vs 6.0) stay on frontend_pcm_kernel,
   // whose window pass reads the trimmed segment from shared memory
   const bool pipe_geometry = (fl % 64 == 0 && fs % 64 == 0 && fs >= 128 && fl <= 16384);
-  bool pipe = fast && (c->pcm_variant == kPipeVariant || (c->pcm_variant < 0 && p->aligned16 && pipe_geometry)) &&
+  // (any alignment: its producer realigns utterances that do not start on a 16-byte boundary, csrc/frontend_pipe.cu)
+  // frame 256 / shift 128 (its specialised instantiation) takes any alignment at full speed; the other whole-group
+  // geometries read the trimmed segment with 16-byte loads and are routed here only for aligned layouts
+  const bool chain_geometry = (fl == 256 && fs == 128);
+  bool pipe = fast && (c->pcm_variant == kPipeVariant || (c->pcm_variant < 0 && pipe_geometry && (chain_geometry || p->aligned16))) &&
               pipe_kernel_plan(max_len, (int)cap_frames64, fl, kMaxSmemPerCta, &plan);
   if (fast && !pipe && c->pcm_variant == kPipeVariant) variant = kAutoResident;
   if (pipe) {
@@ -793,6 +799,15 @@ int dsp_zscore_device(dsp_context* c, const double* x, int64_t n, int32_t d, int
   return DSP_OK;
 }
 
+int dsp_zscore_apply_f32_device(dsp_context* c, const float* x, int64_t n, int32_t d, const double* mean,
+                                const double* std, double* out) {
+  if (!c || n < 0 || d < 1 || !mean || !std || (n && (!x || !out))) return fail(DSP_ERR_INVALID, "bad argument");
+  CU(cudaSetDevice(c->device));
+  CU(zscore_apply_f32(x, n, d, mean, std, out, c->stream));
+  c->launches++;
+  return DSP_OK;
+}
+
 int dsp_zscore_host(dsp_context* c, const double* x, int64_t n, int32_t d, int fit, double* mean, double* std,
                     double* out) {
   if (!c || n < 0 || d < 1 || !mean || !std || (!x && n)) return fail(DSP_ERR_INVALID, "bad argument");
@@ -821,7 +836,8 @@ int dsp_zscore_host(dsp_context* c, const double* x, int64_t n, int32_t d, int f
 static void knn_release(dsp_knn* k) {
   DevBuf* all[] = {&k->train64, &k->train32, &k->labels, &k->tnorm, &k->cand_idx, &k->cand_worst, &k->qnorm,
                    &k->redo_list, &k->redo_count, &k->nbr_label, &k->q, &k->o_idx, &k->o_dist, &k->o_lab,
-                   &k->tpacked, &k->tnorm_dense, &k->qpacked, &k->qnorm_chunk, &k->dense_flags, &k->part_d, &k->part_i};
+                   &k->tpacked, &k->tnorm_dense, &k->qpacked, &k->qnorm_chunk, &k->dense_flags, &k->part_d, &k->part_i,
+                   &k->tc_train, &k->tc_q, &k->tc_flags};
   for (DevBuf* b : all) b->release();
 }
 
@@ -846,6 +862,16 @@ int dsp_knn_fit_device(dsp_context* c, const double* train, const int32_t* label
     if (e != cudaSuccess) return bail(fail(DSP_ERR_CUDA, "knn_pack: %s", cudaGetErrorString(e)));
     cudaMemcpyAsync(&h->tnorm_max, h->tnorm.p, sizeof(float), cudaMemcpyDeviceToHost, c->stream);
   }
+  int tc_flags[2] = {0, 1};
+  if (h->dp == 16 && n >= 64 && k < kKnnCand && std::getenv("DSP_KNN_NO_TC16") == nullptr) {
+    // the 15-dim statistical features: split-fp16 operands in tensor-core tile order, |t|^2 as the 16th feature
+    if (h->tc_train.ensure(knn_tc16_packed_bytes(n, false)) != cudaSuccess || h->tc_flags.ensure(64) != cudaSuccess)
+      return bail(fail(DSP_ERR_NOMEM, "device allocation failed"));
+    cudaError_t e = knn_tc16_pack(h->train64.as<double>(), n, d, false, h->tc_train.p, nullptr, h->tc_flags.as<int>(), c->stream);
+    c->launches++;
+    if (e != cudaSuccess) return bail(fail(DSP_ERR_CUDA, "knn_tc16_pack: %s", cudaGetErrorString(e)));
+    cudaMemcpyAsync(tc_flags, h->tc_flags.p, sizeof tc_flags, cudaMemcpyDeviceToHost, c->stream);
+  }
   int dense_flags[2] = {0, 0};
   if (!h->dp && d <= kKnnDenseMaxDim && std::getenv("DSP_KNN_NO_DENSE") == nullptr) {
     // sequence-feature sizes (compare_feature_methods.py:106-123): split-fp16 operands in tensor-core tile order
@@ -861,6 +887,7 @@ int dsp_knn_fit_device(dsp_context* c, const double* train, const int32_t* label
   }
   cudaError_t e = cudaStreamSynchronize(c->stream);
   if (e != cudaSuccess) return bail(fail(DSP_ERR_CUDA, "knn fit: %s", cudaGetErrorString(e)));
+  h->tc16 = h->tc_train.p && tc_flags[1] == 0;      // a train row outside the filter's range: fp32 scan for every call
   if (h->tpacked.p) {
     std::memcpy(&h->tnorm_max, &dense_flags[0], sizeof(float));
     h->dense = dense_flags[1] == 0;          // a value outside the fp16 range: every query takes the float64 scan instead
@@ -902,11 +929,26 @@ int dsp_knn_topk_device(dsp_knn* h, const double* q, int64_t m, int64_t* nbr_idx
     CU(h->cand_idx.ensure(sizeof(int) * (size_t)m * kKnnCand));
     CU(h->cand_worst.ensure(sizeof(float) * (size_t)m));
     CU(h->qnorm.ensure(sizeof(float) * (size_t)m));
+    const int* gate = nullptr;
+    double err_rel = (double)(h->d + 4) * 1.1920929e-7, err_floor = 0.0;
+    if (h->tc16) {
+      // tensor-core filter; the fp32 scan below is launched behind a device-side gate and runs only when a query
+      // left the filter's range (no host round trip either way)
+      CU(h->tc_q.ensure(knn_tc16_packed_bytes(m, true)));
+      int* qflags = h->tc_flags.as<int>() + 4;
+      CU(knn_tc16_pack(q, m, h->d, true, h->tc_q.p, h->qnorm.as<float>(), qflags, c->stream));
+      CU(knn_tc16_filter(h->tc_q.p, h->tc_train.p, m, h->n, h->k, qflags, h->cand_idx.as<int>(), h->cand_worst.as<float>(),
+                         c->sm_count, c->stream));
+      c->launches += 2;
+      gate = qflags;
+      err_rel = std::max(err_rel, knn_dense_err_rel(16));      // covers whichever of the two scans produced the candidates
+      err_floor = 1.0;
+    }
     CU(knn_scan(h->dp, h->train32.as<float>(), h->n, q, m, h->d, h->cand_idx.as<int>(), h->cand_worst.as<float>(),
-                h->qnorm.as<float>(), c->stream));
+                h->qnorm.as<float>(), gate, c->stream));
     CU(knn_rerank(h->train64.as<double>(), h->train32.as<float>(), h->dp, h->n, q, m, h->d, h->k, h->index_base,
                   h->labels.as<int32_t>(), h->cand_idx.as<int>(), h->cand_worst.as<float>(), h->qnorm.as<float>(),
-                  h->tnorm_max, (double)(h->d + 4) * 1.1920929e-7, nbr_idx, nbr_sqdist, nbr_label, h->redo_list.as<int32_t>(),
+                  h->tnorm_max, err_rel, err_floor, nbr_idx, nbr_sqdist, nbr_label, h->redo_list.as<int32_t>(),
                   h->redo_count.as<int32_t>(), c->stream));
     c->launches += 2;
   } else if (h->dense) {
@@ -937,7 +979,7 @@ int dsp_knn_topk_device(dsp_knn* h, const double* q, int64_t m, int64_t* nbr_idx
     if (all_fit) {
       CU(knn_rerank(h->train64.as<double>(), nullptr, 0, h->n, q, m, h->d, h->k, h->index_base,
                     h->labels.as<int32_t>(), h->cand_idx.as<int>(), h->cand_worst.as<float>(), h->qnorm.as<float>(),
-                    h->tnorm_max, knn_dense_err_rel(h->d), nbr_idx, nbr_sqdist, nbr_label, h->redo_list.as<int32_t>(),
+                    h->tnorm_max, knn_dense_err_rel(h->d), 0.0, nbr_idx, nbr_sqdist, nbr_label, h->redo_list.as<int32_t>(),
                     h->redo_count.as<int32_t>(), c->stream));
     } else {
       CU(knn_redo_all(h->redo_list.as<int32_t>(), h->redo_count.as<int32_t>(), m, c->stream));
@@ -948,10 +990,8 @@ int dsp_knn_topk_device(dsp_knn* h, const double* q, int64_t m, int64_t* nbr_idx
     CU(knn_redo_all(h->redo_list.as<int32_t>(), h->redo_count.as<int32_t>(), m, c->stream));
     c->launches++;
   }
-  if (h->d > 64) {
-    CU(h->part_d.ensure(sizeof(double) * (size_t)knn_rescan_grid(c->sm_count) * kKnnMaxK));
-    CU(h->part_i.ensure(sizeof(long long) * (size_t)knn_rescan_grid(c->sm_count) * kKnnMaxK));
-  }
+  CU(h->part_d.ensure(sizeof(double) * (size_t)knn_rescan_grid(c->sm_count) * kKnnMaxK));
+  CU(h->part_i.ensure(sizeof(long long) * (size_t)knn_rescan_grid(c->sm_count) * kKnnMaxK));
   CU(knn_rescan(h->train64.as<double>(), h->n, q, h->d, h->k, h->index_base, h->labels.as<int32_t>(),
                 h->redo_list.as<int32_t>(), h->redo_count.as<int32_t>(), nbr_idx, nbr_sqdist, nbr_label,
                 c->sm_count, h->part_d.as<double>(), h->part_i.as<long long>(), (int)std::min<int64_t>(m, INT32_MAX), c->stream));
@@ -1045,7 +1085,7 @@ int dsp_dtw_topk_host(dsp_context* c, const float* q_feats, const int64_t* q_off
   for (int64_t i = 0; i < nq; ++i) max_q = std::max(max_q, q_offsets[i + 1] - q_offsets[i]);
   for (int64_t i = 0; i < nt; ++i) max_t = std::max(max_t, t_offsets[i + 1] - t_offsets[i]);
   if (max_q > dtw_max_query_frames()) return fail(DSP_ERR_UNSUPPORTED, "query sequences longer than %d frames are not supported", dtw_max_query_frames());
-  if ((size_t)max_t * dim * sizeof(float) > kMaxSmemPerCta) return fail(DSP_ERR_UNSUPPORTED, "template sequence too long for shared memory");
+  if (dtw_smem_bytes((int)max_t, dim) > kMaxSmemPerCta) return fail(DSP_ERR_UNSUPPORTED, "template sequence too long for shared memory (%lld frames x %d features)", (long long)max_t, dim);
   CU(cudaSetDevice(c->device));
   OneShot os(c);
   float* d_q = os.dev<float>((size_t)q_offsets[nq] * dim);
@@ -1085,7 +1125,7 @@ int dsp_knn_last_stats(dsp_knn* h, int64_t* rescanned, int32_t* scan_kind) {
     CU(cudaStreamSynchronize(h->ctx->stream));
   }
   if (rescanned) *rescanned = cnt;
-  if (scan_kind) *scan_kind = h->dp ? 1 : (h->dense ? 2 : 0);
+  if (scan_kind) *scan_kind = h->dp ? (h->tc16 ? 3 : 1) : (h->dense ? 2 : 0);
   return DSP_OK;
 }
 

@@ -76,13 +76,19 @@ constexpr int kRecBarThreads = 32 * (kStreamWarps + 1);   // the stream warps + 
 #ifndef DSP_PIPE_BATCH
 #define DSP_PIPE_BATCH 1
 #endif
+#ifndef DSP_CHAIN_PACKED
+#define DSP_CHAIN_PACKED 1          // window chain on packed fp32x2 arithmetic (0: the scalar FFMA build)
+#endif
 constexpr bool kBatchMode = DSP_PIPE_BATCH != 0;
 constexpr int kBatch = kMaxTailWarps;
 constexpr int kBarBatchFull = 2, kBarBatchEmpty = 4;
 constexpr int kBatchBarThreads = 32 * (kStreamWarps + kMaxTailWarps);
 
+constexpr int kStageSlots = 4;              // realigning producer: staging pieces of kChunkBytes in flight (power of two)
+constexpr int kStageBytes = kStageSlots * kChunkBytes;
+
 struct PipeLayout {
-  int ring, gsum, bits, meta, rec, scratch, win, desc, part, consts, bars, total;
+  int ring, stage, gsum, bits, meta, rec, scratch, win, desc, part, consts, bars, total;
   int rec_bytes, rec_e, rec_fe, rec_fm, rec_z, rec_zf;
 };
 
@@ -93,6 +99,7 @@ __host__ __device__ inline PipeLayout make_pipe_layout(int R, int capG, int capF
   PipeLayout L;
   int o = 0;
   L.ring = o;    o += R * kChunkBytes;
+  L.stage = o;   o += kStageBytes;
   L.gsum = o;    o += 2 * 8 * capG;
   L.bits = o;    o += al16(8 * capG + 16);
   L.meta = o;    o += al16(4 * capG);
@@ -108,7 +115,7 @@ __host__ __device__ inline PipeLayout make_pipe_layout(int R, int capG, int capF
   L.desc = o;    o += kDescRing * 8;
   L.part = o;    o += 2 * kStreamWarps * 16;
   L.consts = o;  o += 2 * 64;
-  L.bars = o;    o += 8 * (2 * R + 2 * nrec);
+  L.bars = o;    o += 8 * (2 * R + 2 * nrec + kStageSlots);
   L.total = o;
   return L;
 }
@@ -398,6 +405,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
   double* s_consts = reinterpret_cast<double*>(smem + L.consts);                        // [2][8]
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* bar_empty = bar_full + R;
+  uint64_t* bar_stage = bar_empty + R + 2 * nrec;       // staging pieces of the realigning producer
+  unsigned char* s_stage = smem + L.stage;
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   // kChain fixes frame 256 / shift 128 at compile time: divisions, edge handling and the generic loops fold away
@@ -410,6 +419,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
   for (int j = tid; j < fl; j += kPipeThreads) s_win[j] = a.win_f32[j];
   if (tid == 0) {
     for (int i = 0; i < R; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], edges ? kStreamWarps : 1); }
+    for (int i = 0; i < kStageSlots; ++i) mbar_init(&bar_stage[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -421,26 +431,33 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
   if (wid >= kStreamWarps) {
   if constexpr (kSplitRegs) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTailRegs));
   if (wid == kPipeWarps - 1) {
-    if (lane != 0) return;
+    // Lane 0 schedules and issues the bulk copies.  An utterance that starts on a 16-byte boundary goes straight into
+    // the ring.  Any other start (packed CSR batches of odd lengths, ragged data, sliced tensors) is fetched from the
+    // 16-byte boundary below it into a small staging area, and the WHOLE warp moves it into the ring shifted by the
+    // 1..7 samples in between (two 16-byte loads, a funnel shift per word for odd sample offsets, one 16-byte store):
+    // the stream warps always see sample 0 of the utterance at byte 0 of its first slot.  TMA cannot do this shift
+    // itself: bulk copies need 16-byte aligned addresses on both sides, and the tiled tensor-map form faults on an
+    // inner coordinate that is not a multiple of 16 bytes (tools/tma_probe.cu).
     int slot = 0, lap = 0, useq = 0;
-    unsigned int u_next = atomicAdd(a.work_counter, 1u);
+    uint32_t stage_phase = 0;                      // bit s: parity the next completion of staging slot s will have
+    unsigned int u_next = 0;
+    if (lane == 0) u_next = atomicAdd(a.work_counter, 1u);
+    u_next = __shfl_sync(0xffffffffu, u_next, 0);
     for (;;) {
       const long long u = (long long)u_next;
       const bool done = u >= a.n_utts;
       int n = 0;
       const int16_t* src = nullptr;
       if (!done) {
-        u_next = atomicAdd(a.work_counter, 1u);       // one index ahead: its latency hides behind the copies
+        if (lane == 0) u_next = atomicAdd(a.work_counter, 1u);       // one index ahead: its latency hides behind the copies
+        u_next = __shfl_sync(0xffffffffu, u_next, 0);
         const int64_t off = a.offsets[u];
         n = a.lengths ? a.lengths[u] : (int)(a.offsets[u + 1] - off);
         src = a.samples + off;
-        if (reinterpret_cast<uintptr_t>(src) & 15) n = -1 - n;        // misaligned: not this kernel's layout
       }
-      s_desc[useq & (kDescRing - 1)] = make_int2(done ? -1 : (int)u, n);
-      // full 4 KB chunks first (running shared / global addresses, no per-chunk arithmetic), then the last,
-      // possibly partial one
+      if (lane == 0) s_desc[useq & (kDescRing - 1)] = make_int2(done ? -1 : (int)u, n);
       const int nchunks = n > 0 ? (n + kChunkSamples - 1) / kChunkSamples : 1;
-      const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(src);
+      const int shift = (int)((reinterpret_cast<uintptr_t>(src) & 15) >> 1);     // samples above the 16-byte boundary
       uint32_t dst32 = smem_u32(s_ring) + (uint32_t)slot * kChunkBytes, full32 = smem_u32(&bar_full[slot]), empty32 = smem_u32(&bar_empty[slot]);
       auto next_slot = [&]() {
         dst32 += kChunkBytes; full32 += 8; empty32 += 8;
@@ -451,31 +468,110 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
           asm volatile("{\n\t.reg .pred p;\n\tWE_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t@p bra DE_%=;\n\tbra WE_%=;\n\tDE_%=:\n\t}"
                        ::"r"(empty32), "r"((uint32_t)((lap - 1) & 1)), "r"(0x989680u) : "memory");
       };
+      if (shift == 0 || n <= 0) {
+        if (lane == 0) {
+          // full 4 KB chunks first (running shared / global addresses, no per-chunk arithmetic), then the last,
+          // possibly partial one
+          const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(src);
 #pragma unroll 1
-      for (int c = 0; c + 1 < nchunks; ++c) {
-        wait_empty();
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full32), "r"((uint32_t)kChunkBytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(dst32), "l"(gsrc), "r"((uint32_t)kChunkBytes), "r"(full32) : "memory");
-        gsrc += kChunkBytes;
-        next_slot();
-      }
-      {
-        wait_empty();
-        const int s0 = (nchunks - 1) * kChunkSamples;
-        const int cnt = n > 0 ? n - s0 : 0;
-        const uint32_t bytes = ((uint32_t)cnt * 2u) & ~15u;
-        // tail of < 8 samples by plain loads; the release of the arrive below publishes them
-        int16_t* dst = reinterpret_cast<int16_t*>(s_ring + (size_t)slot * kChunkBytes);
-        for (int i = (int)(bytes >> 1); i < cnt; ++i) dst[i] = src[s0 + i];
-        if (bytes) {
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full32), "r"(bytes) : "memory");
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(dst32), "l"(gsrc), "r"(bytes), "r"(full32) : "memory");
+          for (int c = 0; c + 1 < nchunks; ++c) {
+            wait_empty();
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full32), "r"((uint32_t)kChunkBytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst32), "l"(gsrc), "r"((uint32_t)kChunkBytes), "r"(full32) : "memory");
+            gsrc += kChunkBytes;
+            next_slot();
+          }
+          {
+            wait_empty();
+            const int s0 = (nchunks - 1) * kChunkSamples;
+            const int cnt = n > 0 ? n - s0 : 0;
+            const uint32_t bytes = ((uint32_t)cnt * 2u) & ~15u;
+            // tail of < 8 samples by plain loads; the release of the arrive below publishes them
+            int16_t* dst = reinterpret_cast<int16_t*>(s_ring + (size_t)slot * kChunkBytes);
+            for (int i = (int)(bytes >> 1); i < cnt; ++i) dst[i] = src[s0 + i];
+            if (bytes) {
+              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full32), "r"(bytes) : "memory");
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                           ::"r"(dst32), "l"(gsrc), "r"(bytes), "r"(full32) : "memory");
+            } else {
+              asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full32) : "memory");
+            }
+            next_slot();
+          }
         } else {
-          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full32) : "memory");
+          // keep the other lanes' view of the ring position in step with lane 0
+          for (int c = 0; c < nchunks; ++c) next_slot();
         }
-        next_slot();
+        __syncwarp();
+      } else {
+        // ---- realigning path --------------------------------------------------------------------------------
+        const unsigned char* gal = reinterpret_cast<const unsigned char*>(src) - 2 * shift;     // 16-byte aligned
+        const uint32_t lb = (2u * (uint32_t)(n + shift)) & ~15u;      // bytes of the aligned stream the bulk copies fetch
+        const int pieces = (int)((lb + kChunkBytes - 1) / kChunkBytes);
+        const int nvec = lb >= 2u * shift ? (int)((lb - 2u * shift) >> 4) : 0;                  // whole output vectors they cover
+        auto issue_piece = [&](int p) {
+          const uint32_t bytes = min((uint32_t)kChunkBytes, lb - (uint32_t)p * kChunkBytes);
+          const uint32_t bar = smem_u32(&bar_stage[p & (kStageSlots - 1)]);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_u32(s_stage) + (uint32_t)(p & (kStageSlots - 1)) * kChunkBytes), "l"(gal + (size_t)p * kChunkBytes), "r"(bytes), "r"(bar)
+                       : "memory");
+        };
+        if (lane == 0)
+          for (int p = 0; p < min(pieces, kStageSlots); ++p) issue_piece(p);
+        int waited = 0;
+        const int ws = shift >> 1;                 // whole words of the shift
+        const uint32_t hs = (shift & 1) ? 16u : 0u;   // and the odd sample
+#pragma unroll 1
+        for (int c = 0; c < nchunks; ++c) {
+          // pieces c and c + 1 hold the bytes of output chunk c
+#pragma unroll 1
+          while (waited < min(c + 2, pieces)) {
+            const int ss = waited & (kStageSlots - 1);
+            mbar_wait(&bar_stage[ss], (stage_phase >> ss) & 1u);
+            stage_phase ^= 1u << ss;
+            ++waited;
+          }
+          wait_empty();
+          unsigned char* ring_slot = s_ring + (size_t)slot * kChunkBytes;
+          const int v_end = min(kChunkBytes / 16, nvec - c * (kChunkBytes / 16));    // output vectors of this chunk
+#pragma unroll 1
+          for (int v = lane; v < v_end; v += 32) {
+            const uint32_t so = ((uint32_t)c * kChunkBytes + 16u * (uint32_t)v) & (kStageBytes - 1);
+            const int4 q0 = *reinterpret_cast<const int4*>(s_stage + so);
+            const int4 q1 = *reinterpret_cast<const int4*>(s_stage + ((so + 16u) & (kStageBytes - 1)));
+            const uint32_t w[8] = {(uint32_t)q0.x, (uint32_t)q0.y, (uint32_t)q0.z, (uint32_t)q0.w, (uint32_t)q1.x, (uint32_t)q1.y, (uint32_t)q1.z, (uint32_t)q1.w};
+            int4 o;
+            switch (ws) {            // warp-uniform
+              case 0: o = make_int4(__funnelshift_r(w[0], w[1], hs), __funnelshift_r(w[1], w[2], hs), __funnelshift_r(w[2], w[3], hs), __funnelshift_r(w[3], w[4], hs)); break;
+              case 1: o = make_int4(__funnelshift_r(w[1], w[2], hs), __funnelshift_r(w[2], w[3], hs), __funnelshift_r(w[3], w[4], hs), __funnelshift_r(w[4], w[5], hs)); break;
+              case 2: o = make_int4(__funnelshift_r(w[2], w[3], hs), __funnelshift_r(w[3], w[4], hs), __funnelshift_r(w[4], w[5], hs), __funnelshift_r(w[5], w[6], hs)); break;
+              default: o = make_int4(__funnelshift_r(w[3], w[4], hs), __funnelshift_r(w[4], w[5], hs), __funnelshift_r(w[5], w[6], hs), __funnelshift_r(w[6], w[7], hs)); break;
+            }
+            *reinterpret_cast<int4*>(ring_slot + 16 * v) = o;
+          }
+          // samples of this chunk beyond the last whole vector (at most 15, at the end of the utterance): plain loads
+          {
+            const int lo = max(c * kChunkSamples, 8 * nvec), hi = min((c + 1) * kChunkSamples, n);
+            int16_t* dst = reinterpret_cast<int16_t*>(ring_slot);
+            for (int i = lo + lane; i < hi; i += 32) dst[i - c * kChunkSamples] = src[i];
+          }
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full32) : "memory");
+            if (c + kStageSlots < pieces) issue_piece(c + kStageSlots);      // piece c has been consumed: its slot is free
+          }
+          next_slot();
+        }
+        // pieces beyond the last chunk's needs (none by construction) would leave a phase open: drain to be safe
+#pragma unroll 1
+        while (waited < pieces) {
+          const int ss = waited & (kStageSlots - 1);
+          mbar_wait(&bar_stage[ss], (stage_phase >> ss) & 1u);
+          stage_phase ^= 1u << ss;
+          ++waited;
+        }
       }
       ++useq;
       if (done) break;
@@ -733,6 +829,44 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
           const float c1f = -(8388608.f + 32768.f) - (float)thr;
           const float scale = hi8 ? (float)sc_m : (float)sc_e;
           float* dst = (hi8 ? s_fm : s_fe) + zbase + fa - 1;   // frame fa + i - 1 at dst[i]
+#if DSP_CHAIN_PACKED
+          // Packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2): the two samples of a 32-bit word travel as one
+          // 64-bit register pair from the conversion on -- (x + c1f) - phi, d * d and the four multiply-adds of a word are
+          // ONE instruction each instead of two.  Same FMA-pipe time, two thirds of the issue slots (12 instead of 17
+          // per word), and issue slots are what this kernel runs out of.  Even and odd samples accumulate separately and
+          // are added when a block's sums leave the lane.
+          f32x2 cep = pk2(0.f, 0.f), cmp = pk2(0.f, 0.f);   // first-half partials of the previous block
+          f32x2 cwp[2][4], cw2p[2][4];
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { cwp[c][k] = pk2(cw[c][2 * k], cw[c][2 * k + 1]); cw2p[c][k] = pk2(cw2[c][2 * k], cw2[c][2 * k + 1]); }
+          const f32x2 c1f2 = pk2(c1f, c1f), nphi2 = pk2(-phi, -phi);
+          auto step = [&](const int4& q, int i) {
+            const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+            f32x2 e0 = pk2(0.f, 0.f), m0 = e0, e1 = cep, m1 = cmp;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t ub = w[k] ^ 0x80008000u;
+              const float xlo = __uint_as_float(__byte_perm(ub, 0x4b000000u, 0x7610));
+              const float xhi = __uint_as_float(__byte_perm(ub, 0x4b000000u, 0x7632));
+              const f32x2 d = add2(add2(pk2(xlo, xhi), c1f2), nphi2);
+              const f32x2 qq = mul2(d, d);
+              const f32x2 aa = d & 0x7fffffff7fffffffull;
+              e0 = fma2(cw2p[0][k], qq, e0); m0 = fma2(cwp[0][k], aa, m0);
+              e1 = fma2(cw2p[1][k], qq, e1); m1 = fma2(cwp[1][k], aa, m1);
+            }
+            cep = e0; cmp = m0;
+            const float e1s = hsum2(e1), m1s = hsum2(m1);
+            // transposed reduction of (e1, m1) over the chain's 16 lanes
+            const float send = hi8 ? e1s : m1s, keep = hi8 ? m1s : e1s;
+            float vv = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            vv += __shfl_xor_sync(0xffffffffu, vv, 4);
+            vv += __shfl_xor_sync(0xffffffffu, vv, 2);
+            vv += __shfl_xor_sync(0xffffffffu, vv, 1);
+            if (writer && i >= 1 && i <= nfr) dst[i] = vv * scale;
+          };
+#else
           float ce = 0.f, cm = 0.f;                          // first-half partials of the previous block
           auto step = [&](const int4& q, int i) {
             const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
@@ -758,6 +892,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
             vv += __shfl_xor_sync(0xffffffffu, vv, 1);
             if (writer && i >= 1 && i <= nfr) dst[i] = vv * scale;
           };
+#endif
           // kInFlight hop blocks in flight per lane (the tail warps run this phase together and wait on L2 / HBM together:
           // 4 -> 6 in flight is 3.65 -> 3.24 ms per 100k utterances; before the batch hand-off the larger loop body cost
           // more in instruction misses than it hid in latency); loads past the chain's last block re-read that block.
@@ -766,11 +901,36 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
           constexpr int kInFlight = 6;
           int4 q[kInFlight];
 #pragma unroll
-          for (int j = 0; j < kInFlight; ++j) q[j] = __ldcs(ptr + 16 * min(j, last));
+          // The utterance may start anywhere (packed CSR): hop block i of the lane sits at ptr + 16 i, a 16-byte vector
+          // that is 16-, 8- or only 2-byte aligned in global memory -- one alignment per utterance, i.e. per warp.
+          // 16: one LDG.128; 8 (every other utterance of a packed batch of 1 s clips): two LDG.64; anything else: the
+          // two aligned vectors around it and a funnel shift per word (the loads hit L1 for the half the neighbour
+          // lane also reads).
+          const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(ptr) & 15u);
+          const uint32_t mws = mis >> 2, mhs = (mis & 2u) ? 16u : 0u;
+          auto load_block = [&](int bi) -> int4 {
+            const int4* p = ptr + 16 * bi;
+            if (mis == 0) return __ldcs(p);
+            if (mis == 8) {
+              const int2 lo = __ldcs(reinterpret_cast<const int2*>(p)), hi = __ldcs(reinterpret_cast<const int2*>(p) + 1);
+              return make_int4(lo.x, lo.y, hi.x, hi.y);
+            }
+            const int4* pa = reinterpret_cast<const int4*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)15);
+            const int4 q0 = __ldg(pa), q1 = __ldg(pa + 1);
+            const uint32_t w[8] = {(uint32_t)q0.x, (uint32_t)q0.y, (uint32_t)q0.z, (uint32_t)q0.w, (uint32_t)q1.x, (uint32_t)q1.y, (uint32_t)q1.z, (uint32_t)q1.w};
+            switch (mws) {
+              case 0: return make_int4(__funnelshift_r(w[0], w[1], mhs), __funnelshift_r(w[1], w[2], mhs), __funnelshift_r(w[2], w[3], mhs), __funnelshift_r(w[3], w[4], mhs));
+              case 1: return make_int4(__funnelshift_r(w[1], w[2], mhs), __funnelshift_r(w[2], w[3], mhs), __funnelshift_r(w[3], w[4], mhs), __funnelshift_r(w[4], w[5], mhs));
+              case 2: return make_int4(__funnelshift_r(w[2], w[3], mhs), __funnelshift_r(w[3], w[4], mhs), __funnelshift_r(w[4], w[5], mhs), __funnelshift_r(w[5], w[6], mhs));
+              default: return make_int4(__funnelshift_r(w[3], w[4], mhs), __funnelshift_r(w[4], w[5], mhs), __funnelshift_r(w[5], w[6], mhs), __funnelshift_r(w[6], w[7], mhs));
+            }
+          };
+#pragma unroll
+          for (int j = 0; j < kInFlight; ++j) q[j] = load_block(min(j, last));
 #pragma unroll 1
           for (int i = 0; i <= per; i += kInFlight) {       // uniform trip count: the shuffles are warp-wide
 #pragma unroll
-            for (int j = 0; j < kInFlight; ++j) { step(q[j], i + j); q[j] = __ldcs(ptr + 16 * min(i + j + kInFlight, last)); }
+            for (int j = 0; j < kInFlight; ++j) { step(q[j], i + j); q[j] = load_block(min(i + j + kInFlight, last)); }
           }
         }
       }
@@ -778,7 +938,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
         const int sub = lane & (kLanesPerFrame - 1);
         const int slot = lane / kLanesPerFrame;
         constexpr int kSlots = 32 / kLanesPerFrame;
-        const bool vec_ok = ((start & 7) == 0) && ((fs & 7) == 0);
+        const bool vec_ok = ((start & 7) == 0) && ((fs & 7) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
 #pragma unroll 1
         for (int t0 = f2_chain; t0 < f2; t0 += kSlots) {
           const int t = t0 + slot;

@@ -50,8 +50,9 @@ template <int DP, int QPT>
 __global__ void __launch_bounds__(kScanThreads)
 knn_scan_kernel(const float* __restrict__ train32, int64_t n, const double* __restrict__ queries,
                 int64_t m, int d, int* __restrict__ cand_idx, float* __restrict__ cand_worst,
-                float* __restrict__ qnorm_out) {
+                float* __restrict__ qnorm_out, const int* __restrict__ gate) {
   __shared__ __align__(16) float tile[kTileRows * DP];
+  if (gate && gate[1] == 0) return;
   const int64_t q0 = ((int64_t)blockIdx.x * kScanThreads + threadIdx.x) * QPT;
   float q[QPT][DP - 1];
   float cd[QPT][kKnnCand];
@@ -123,8 +124,9 @@ constexpr int kPairQpt = 2;
 __global__ void __launch_bounds__(kScanThreads)
 knn_scan_pair_kernel(const float* __restrict__ train32, int64_t n, const double* __restrict__ queries,
                      int64_t m, int d, int* __restrict__ cand_idx, float* __restrict__ cand_worst,
-                     float* __restrict__ qnorm_out) {
+                     float* __restrict__ qnorm_out, const int* __restrict__ gate) {
   constexpr int DP = 16;
+  if (gate && gate[1] == 0) return;          // the tensor-core filter served this call
   __shared__ __align__(16) float tile[kTileRows * DP];            // [row pair][column][2]
   const int64_t q0 = ((int64_t)blockIdx.x * kScanThreads + threadIdx.x) * kPairQpt;
   f32x2_t qq[kPairQpt][DP - 1];
@@ -204,7 +206,7 @@ __global__ void knn_rerank_kernel(const double* __restrict__ train, const float*
                                   int dp, int64_t n, const double* __restrict__ queries, int64_t m,
                                   int d, int k, int64_t index_base, const int32_t* __restrict__ labels,
                                   const int* __restrict__ cand_idx, const float* __restrict__ cand_worst,
-                                  const float* __restrict__ qnorm, float tnorm_max, double err_rel,
+                                  const float* __restrict__ qnorm, float tnorm_max, double err_rel, double err_floor,
                                   int64_t* __restrict__ nbr_idx, double* __restrict__ nbr_sqdist,
                                   int32_t* __restrict__ nbr_label, int32_t* __restrict__ redo_list,
                                   int32_t* __restrict__ redo_count) {
@@ -230,7 +232,9 @@ __global__ void knn_rerank_kernel(const double* __restrict__ train, const float*
     // |t|^2 - 2 q.t + |q|^2: (d+2) roundings on terms bounded by (|q| + |t|)^2.
     const float qn = qnorm[qi];
     const double bound = (double)(sqrtf(qn) + sqrtf(tnorm_max));
-    const double err = err_rel * bound * bound;
+    // err_floor: the split-fp16 filter also has an ABSOLUTE error (fp16 subnormal spacing of the lo planes), covered
+    // by evaluating the relative bound at (|q| + |t|max)^2 >= err_floor
+    const double err = err_rel * fmax(bound * bound, err_floor);
     const double lower = (double)cand_worst[qi] + (double)qn - err;
     ok = cd[kk - 1] < lower;
   }
@@ -327,23 +331,34 @@ knn_rerank_wide_kernel(const double* __restrict__ train, int64_t n, const double
   }
 }
 
-// Exhaustive float64 scan for the queries the certificate rejected: one warp per query.
+__host__ __device__ inline int rescan_parts(int grid, int total) { const int p = grid / (total > 0 ? total : 1); return p < 1 ? 1 : (p > 64 ? 64 : p); }
+
+// Exhaustive float64 scan for the queries the certificate rejected: one warp per (query, slice of the train rows).
+// A handful of rejected queries (the usual case: tens in a million) are split over up to 64 warps each -- partial
+// lists to part_d / part_i, merged by knn_rescan_merge_kernel -- instead of leaving one warp to walk 10^5 rows
+// (5 ms for 11 queries before the split); many rejected queries get one warp each and write their result directly.
 __global__ void knn_rescan_kernel(const double* __restrict__ train, int64_t n,
                                   const double* __restrict__ queries, int d, int k, int64_t index_base,
                                   const int32_t* __restrict__ labels, const int32_t* __restrict__ redo_list,
                                   const int32_t* __restrict__ redo_count, int64_t* __restrict__ nbr_idx,
-                                  double* __restrict__ nbr_sqdist, int32_t* __restrict__ nbr_label) {
+                                  double* __restrict__ nbr_sqdist, int32_t* __restrict__ nbr_label,
+                                  double* __restrict__ part_d, long long* __restrict__ part_i) {
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int total = *redo_count;
-  for (int item = blockIdx.x * warps_per_block + (threadIdx.x >> 5); item < total;
-       item += gridDim.x * warps_per_block) {
+  if (total == 0) return;
+  const int workers = gridDim.x * warps_per_block;
+  const int parts = rescan_parts(workers, total);
+  const int64_t rows_per = ((n + parts - 1) / parts + 31) / 32 * 32;
+  for (int work = blockIdx.x * warps_per_block + (threadIdx.x >> 5); work < total * parts; work += workers) {
+    const int item = work / parts, part = work % parts;
+    const int64_t row_lo = (int64_t)part * rows_per, row_hi = min(n, row_lo + rows_per);
     const int64_t qi = redo_list[item];
     const double* q = queries + qi * d;
     double bd[kKnnMaxK];
     int64_t bi[kKnnMaxK];
     for (int c = 0; c < k; ++c) { bd[c] = INFINITY; bi[c] = INT64_MAX; }
-    for (int64_t i = lane; i < n; i += 32) {
+    for (int64_t i = row_lo + lane; i < row_hi; i += 32) {
       const double dd = sqdist64(q, train + i * d, d);
       if (less_di(dd, i, bd[k - 1], bi[k - 1])) {
         int s = k - 1;
@@ -367,6 +382,7 @@ __global__ void knn_rescan_kernel(const double* __restrict__ train, int64_t n,
       if (owner == lane && mi != INT64_MAX) ++head;
       if (lane == 0) {
         const bool valid = (mi != INT64_MAX);
+        if (parts > 1) { part_d[(int64_t)work * kKnnMaxK + c] = valid ? md : INFINITY; part_i[(int64_t)work * kKnnMaxK + c] = mi; continue; }
         if (nbr_idx) nbr_idx[qi * k + c] = valid ? index_base + mi : -1;
         if (nbr_sqdist) nbr_sqdist[qi * k + c] = md;
         if (nbr_label) nbr_label[qi * k + c] = valid ? labels[mi] : -1;
@@ -379,7 +395,6 @@ __global__ void knn_rescan_kernel(const double* __restrict__ train, int64_t n,
 // rows at a time; the 32 x 32 block of features is read row by row (coalesced) into shared memory and every lane sums
 // ITS row over the features in order -- the sum sqdist64 computes -- so the distances equal the other kernels' bit for bit.
 constexpr int kRescanWarps = 4;
-__host__ __device__ inline int rescan_parts(int grid, int total) { const int p = grid / (total > 0 ? total : 1); return p < 1 ? 1 : (p > 64 ? 64 : p); }
 __global__ void __launch_bounds__(32 * kRescanWarps)
 knn_rescan_wide_kernel(const double* __restrict__ train, int64_t n, const double* __restrict__ queries, int d, int k,
                        int64_t index_base, const int32_t* __restrict__ labels, const int32_t* __restrict__ redo_list,
@@ -573,7 +588,7 @@ __global__ void knn_iota_kernel(int32_t* list, int32_t* count, int64_t m) {
 
 }  // namespace
 
-int knn_rescan_grid(int sm_count) { return sm_count * 4; }
+int knn_rescan_grid(int sm_count) { return sm_count * 16; }      // work items of either rescan kernel (narrow: 2 blocks x 8 warps per SM)
 
 int knn_padded_dim(int d) {
   if (d + 1 <= 16) return 16;
@@ -590,20 +605,20 @@ cudaError_t knn_pack(const double* train, int64_t n, int d, int dp, float* train
 }
 
 cudaError_t knn_scan(int dp, const float* train32, int64_t n, const double* q, int64_t m, int d,
-                     int* cand_idx, float* cand_worst, float* qnorm, cudaStream_t st) {
+                     int* cand_idx, float* cand_worst, float* qnorm, const int* gate, cudaStream_t st) {
   if (m == 0) return cudaSuccess;
   if (dp == 16) {
     constexpr int QPT = 2;
     const unsigned grid = (unsigned)((m + (int64_t)kScanThreads * QPT - 1) / ((int64_t)kScanThreads * QPT));
     static const bool scalar = std::getenv("DSP_KNN_SCALAR_SCAN") != nullptr;      // tuning: the scalar FFMA build
-    if (scalar) knn_scan_kernel<16, QPT><<<grid, kScanThreads, 0, st>>>(train32, n, q, m, d, cand_idx, cand_worst, qnorm);
-    else knn_scan_pair_kernel<<<grid, kScanThreads, 0, st>>>(train32, n, q, m, d, cand_idx, cand_worst, qnorm);
+    if (scalar) knn_scan_kernel<16, QPT><<<grid, kScanThreads, 0, st>>>(train32, n, q, m, d, cand_idx, cand_worst, qnorm, gate);
+    else knn_scan_pair_kernel<<<grid, kScanThreads, 0, st>>>(train32, n, q, m, d, cand_idx, cand_worst, qnorm, gate);
   } else if (dp == 32) {
     const unsigned grid = (unsigned)((m + kScanThreads - 1) / kScanThreads);
-    knn_scan_kernel<32, 1><<<grid, kScanThreads, 0, st>>>(train32, n, q, m, d, cand_idx, cand_worst, qnorm);
+    knn_scan_kernel<32, 1><<<grid, kScanThreads, 0, st>>>(train32, n, q, m, d, cand_idx, cand_worst, qnorm, gate);
   } else {
     const unsigned grid = (unsigned)((m + kScanThreads - 1) / kScanThreads);
-    knn_scan_kernel<64, 1><<<grid, kScanThreads, 0, st>>>(train32, n, q, m, d, cand_idx, cand_worst, qnorm);
+    knn_scan_kernel<64, 1><<<grid, kScanThreads, 0, st>>>(train32, n, q, m, d, cand_idx, cand_worst, qnorm, gate);
   }
   return cudaGetLastError();
 }
@@ -611,7 +626,7 @@ cudaError_t knn_scan(int dp, const float* train32, int64_t n, const double* q, i
 cudaError_t knn_rerank(const double* train, const float* train32, int dp, int64_t n, const double* q,
                        int64_t m, int d, int k, int64_t index_base, const int32_t* labels,
                        const int* cand_idx, const float* cand_worst, const float* qnorm,
-                       float tnorm_max_host, double err_rel, int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label,
+                       float tnorm_max_host, double err_rel, double err_floor, int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label,
                        int32_t* redo_list, int32_t* redo_count, cudaStream_t st) {
   if (m == 0) return cudaSuccess;
   cudaMemsetAsync(redo_count, 0, sizeof(int32_t), st);
@@ -623,7 +638,7 @@ cudaError_t knn_rerank(const double* train, const float* train32, int dp, int64_
     return cudaGetLastError();
   }
   knn_rerank_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(
-      train, train32, dp, n, q, m, d, k, index_base, labels, cand_idx, cand_worst, qnorm, tnorm_max_host, err_rel,
+      train, train32, dp, n, q, m, d, k, index_base, labels, cand_idx, cand_worst, qnorm, tnorm_max_host, err_rel, err_floor,
       nbr_idx, nbr_sqdist, nbr_label, redo_list, redo_count);
   return cudaGetLastError();
 }
@@ -647,9 +662,15 @@ cudaError_t knn_rescan(const double* train, int64_t n, const double* q, int d, i
     if (mt > 0)
       knn_rescan_merge_kernel<<<(mt + 127) / 128, 128, 0, st>>>(grid, k, index_base, labels, redo_list, redo_count, part_d, part_i,
                                                                nbr_idx, nbr_sqdist, nbr_label);
-  } else
-    knn_rescan_kernel<<<sm_count * 2, 256, 0, st>>>(train, n, q, d, k, index_base, labels, redo_list,
-                                                   redo_count, nbr_idx, nbr_sqdist, nbr_label);
+  } else {
+    const int blocks = sm_count * 2, workers = blocks * 8;          // knn_rescan_grid(sm_count) >= workers: the partial lists fit
+    knn_rescan_kernel<<<blocks, 256, 0, st>>>(train, n, q, d, k, index_base, labels, redo_list, redo_count, nbr_idx, nbr_sqdist,
+                                              nbr_label, part_d, part_i);
+    const int mt = max_redo < workers ? max_redo : workers;
+    if (mt > 0)
+      knn_rescan_merge_kernel<<<(mt + 127) / 128, 128, 0, st>>>(workers, k, index_base, labels, redo_list, redo_count, part_d, part_i,
+                                                               nbr_idx, nbr_sqdist, nbr_label);
+  }
   return cudaGetLastError();
 }
 

@@ -11,12 +11,14 @@ constexpr int kKnnMaxK = 16;   // largest supported n_neighbors (certificate nee
 int knn_padded_dim(int d);     // 16 / 32 / 64, or 0 when d is too large for the tiled scan
 cudaError_t knn_pack(const double* train, int64_t n, int d, int dp, float* train32, float* tnorm_max,
                      cudaStream_t st);
+// gate (optional, device): the scan runs only when gate[1] != 0 -- the fp32 stand-in for a tensor-core filter call whose
+// queries left the filter's range (knn_tc16.cu), decided on the device without a host round trip
 cudaError_t knn_scan(int dp, const float* train32, int64_t n, const double* q, int64_t m, int d,
-                     int* cand_idx, float* cand_worst, float* qnorm, cudaStream_t st);
+                     int* cand_idx, float* cand_worst, float* qnorm, const int* gate, cudaStream_t st);
 cudaError_t knn_rerank(const double* train, const float* train32, int dp, int64_t n, const double* q,
                        int64_t m, int d, int k, int64_t index_base, const int32_t* labels,
                        const int* cand_idx, const float* cand_worst, const float* qnorm,
-                       float tnorm_max_host, double err_rel, int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label,
+                       float tnorm_max_host, double err_rel, double err_floor, int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label,
                        int32_t* redo_list, int32_t* redo_count, cudaStream_t st);
 cudaError_t knn_redo_all(int32_t* redo_list, int32_t* redo_count, int64_t m, cudaStream_t st);
 cudaError_t knn_rescan(const double* train, int64_t n, const double* q, int d, int k, int64_t index_base,
@@ -30,6 +32,16 @@ cudaError_t knn_vote(const int32_t* nbr_label, int64_t m, int k, int32_t* out, c
 cudaError_t knn_merge_vote(const double* cd, const int64_t* ci, const int32_t* cl, int r, int64_t m,
                            int k, int32_t* labels_out, int64_t* idx_out, double* dist_out,
                            cudaStream_t st);
+
+// knn_tc16.cu: tensor-core candidate filter for d <= 15 (one K = 16 MMA step, |t|^2 as the 16th feature)
+float knn_tc16_max_norm();                                   // largest |x|^2 the filter accepts (else: fp32 scan)
+int64_t knn_tc16_padded_rows(int64_t rows, bool query);
+size_t knn_tc16_packed_bytes(int64_t rows, bool query);
+// flags[0] = max |x|^2 (float bits), flags[1] = 1 when a row is outside the range; norms (optional): |x|^2 per row
+cudaError_t knn_tc16_pack(const double* x, int64_t rows, int d, bool query, void* packed, float* norms, int* flags, cudaStream_t st);
+// k: neighbours the caller will certify (the filter keeps k + 2 candidates for k <= 3, else 8); needs n >= 64
+cudaError_t knn_tc16_filter(const void* qpacked, const void* tpacked, int64_t m, int64_t n, int k, const int* qflags, int* cand_idx,
+                            float* cand_worst, int sm_count, cudaStream_t st);
 
 // knn_dense.cu: tensor-core candidate scan for feature dimensions beyond the tiled scan (sequence features, D = 2 * max_len)
 int knn_dense_kblocks(int d);

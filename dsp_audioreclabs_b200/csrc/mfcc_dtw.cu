@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cfloat>
 
+#include <climits>
 #include "kernels.cuh"
 #include "knn.cuh"
 #include "mfcc_dtw.cuh"
@@ -143,70 +144,88 @@ mfcc_kernel(const int16_t* __restrict__ samples, const int64_t* __restrict__ off
 // ---------------------------------------------------------------------------------------
 // DTW: one warp-sized CTA per (query, template) pair
 // ---------------------------------------------------------------------------------------
-constexpr int kDtwMaxDim = 16;
+// Lane L owns R consecutive query frames of a STRIP of 32 R rows (in registers) and runs one column behind lane L - 1:
+// D[i-1][j] crosses the lane boundary by one shfl_up per step.  Queries longer than a strip are processed strip by
+// strip: the strip's last row is kept in shared memory (one float per template frame, written in place -- lane 0 has
+// read column j long before the last lane overwrites it) and enters the next strip as its top boundary.  DMAX bounds
+// the feature dimension held in registers (R * DMAX <= 128 floats per lane): 16 for the 13 MFCCs, 32 / 64 / 128 for
+// stacked delta features or other embeddings.
+constexpr int kDtwMaxDim = 128;
 
-template <int R>
+template <int R, int DMAX>
 __global__ void __launch_bounds__(32)
 dtw_kernel(const float* __restrict__ qf, const int64_t* __restrict__ qoff, int64_t nq, const float* __restrict__ tf,
            const int64_t* __restrict__ toff, int64_t nt, int dim, int max_t_frames, float* __restrict__ cost) {
-  extern __shared__ float st[];                 // template frames [m][dim]
+  extern __shared__ float st[];                 // template frames [m][dim], then the boundary row [max_t_frames]
+  float* brow = st + (size_t)max_t_frames * dim;
   const int lane = threadIdx.x;
   const int64_t ti = blockIdx.x, qi = blockIdx.y;
   const int n = (int)(qoff[qi + 1] - qoff[qi]), m = (int)(toff[ti + 1] - toff[ti]);
   float* dst = cost + qi * nt + ti;
-  if (n == 0 || m == 0 || n > 32 * R) { if (lane == 0) *dst = INFINITY; return; }
+  if (n == 0 || m == 0) { if (lane == 0) *dst = INFINITY; return; }
   const float* tp = tf + toff[ti] * dim;
   for (int i = lane; i < m * dim; i += 32) st[i] = tp[i];
+  for (int j = lane; j < m; j += 32) brow[j] = INFINITY;      // "row -1"
   __syncwarp();
-  // this lane's strip of query frames in registers
-  float q[R][kDtwMaxDim];
   const float* qp = qf + qoff[qi] * dim;
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int i = lane * R + r;
-#pragma unroll
-    for (int c = 0; c < kDtwMaxDim; ++c) q[r][c] = (i < n && c < dim) ? qp[(size_t)i * dim + c] : 0.f;
-  }
-  float prev[R];                                // D[i][j-1] of the strip
-#pragma unroll
-  for (int r = 0; r < R; ++r) prev[r] = INFINITY;
-  float top_cur = INFINITY, top_prev = INFINITY;   // D[i0-1][j], D[i0-1][j-1] from the lane above
-  float bottom = INFINITY;                      // D[last row of the strip][j] of the previous step
-  const int last_lane = (n - 1) / R;
-  const int steps = m + last_lane;
   float result = INFINITY;
-  for (int s = 0; s < steps; ++s) {
-    // the lane above finished column j = s - lane in the previous step
-    const float from_above = __shfl_up_sync(0xffffffffu, bottom, 1);
-    top_prev = top_cur;
-    top_cur = lane == 0 ? INFINITY : from_above;
-    const int j = s - lane;
-    if (j >= 0 && j < m && lane <= last_lane) {
-      float t[kDtwMaxDim];
+  constexpr int kStrip = 32 * R;
+#pragma unroll 1
+  for (int i0 = 0; i0 < n; i0 += kStrip) {
+    const int ns = min(kStrip, n - i0);         // rows of this strip
+    // this lane's rows of the strip in registers
+    float q[R][DMAX];
 #pragma unroll
-      for (int c = 0; c < kDtwMaxDim; ++c) t[c] = c < dim ? st[j * dim + c] : 0.f;
-      float up = top_cur, diag = top_prev;
-      float cur_r = INFINITY;
+    for (int r = 0; r < R; ++r) {
+      const int i = i0 + lane * R + r;
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int i = lane * R + r;
-        float d2 = 0.f;
-#pragma unroll
-        for (int c = 0; c < kDtwMaxDim; ++c) { const float e = q[r][c] - t[c]; d2 = fmaf(e, e, d2); }
-        const float d = sqrtf(d2);
-        float best = fminf(fminf(up, prev[r]), diag);
-        if (i == 0 && j == 0) best = 0.f;
-        const float v = i < n ? d + best : INFINITY;
-        diag = prev[r];                         // D[i][j-1] is the diagonal of the row below
-        up = v;
-        prev[r] = v;
-        if (i == n - 1) cur_r = v;
-      }
-      bottom = prev[R - 1];
-      if (lane == last_lane && j == m - 1) result = cur_r;
+      for (int c = 0; c < DMAX; ++c) q[r][c] = (i < n && c < dim) ? qp[(size_t)i * dim + c] : 0.f;
     }
+    float prev[R];                              // D[i][j-1] of the lane's rows
+#pragma unroll
+    for (int r = 0; r < R; ++r) prev[r] = INFINITY;
+    float top_cur = INFINITY, top_prev = INFINITY;   // D[i-1][j], D[i-1][j-1] from the lane above (lane 0: the boundary row)
+    float bottom = INFINITY;                    // D[last row of the lane][j] of the previous step
+    const int last_lane = (ns - 1) / R;
+    const int steps = m + last_lane;
+#pragma unroll 1
+    for (int s = 0; s < steps; ++s) {
+      // the lane above finished column j = s - lane in the previous step
+      const float from_above = __shfl_up_sync(0xffffffffu, bottom, 1);
+      top_prev = top_cur;
+      top_cur = lane == 0 ? (s < m ? brow[s] : INFINITY) : from_above;
+      const int j = s - lane;
+      if (j >= 0 && j < m && lane <= last_lane) {
+        float t[DMAX];
+#pragma unroll
+        for (int c = 0; c < DMAX; ++c) t[c] = c < dim ? st[j * dim + c] : 0.f;
+        float up = top_cur, diag = top_prev;
+        float cur_r = INFINITY;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int i = i0 + lane * R + r;
+          float d2 = 0.f;
+#pragma unroll
+          for (int c = 0; c < DMAX; ++c) { const float e = q[r][c] - t[c]; d2 = fmaf(e, e, d2); }
+          const float d = sqrtf(d2);
+          float best = fminf(fminf(up, prev[r]), diag);
+          if (i == 0 && j == 0) best = 0.f;
+          const float v = i < n ? d + best : INFINITY;
+          diag = prev[r];                       // D[i][j-1] is the diagonal of the row below
+          up = v;
+          prev[r] = v;
+          if (i == i0 + ns - 1) cur_r = v;
+        }
+        bottom = prev[R - 1];
+        if (lane == last_lane) {
+          brow[j] = cur_r;                      // the strip's last row: top boundary of the next strip
+          if (i0 + ns == n && j == m - 1) result = cur_r;
+        }
+      }
+    }
+    __syncwarp();
   }
-  result = __shfl_sync(0xffffffffu, result, last_lane);
+  result = __shfl_sync(0xffffffffu, result, ((n - 1) % kStrip) / R);
   if (lane == 0) *dst = result;
 }
 
@@ -269,13 +288,15 @@ cudaError_t launch_mfcc(const int16_t* samples, const int64_t* offsets, const in
   return cudaGetLastError();
 }
 
-int dtw_max_query_frames() { return 32 * 8; }
+int dtw_max_query_frames() { return INT32_MAX; }      // any length: strips of 32 R rows
 int dtw_max_dim() { return kDtwMaxDim; }
+size_t dtw_smem_bytes(int max_t_frames, int dim) { return ((size_t)std::max(max_t_frames, 1) * dim + (size_t)std::max(max_t_frames, 1)) * sizeof(float); }
 
 cudaError_t launch_dtw(const float* qf, const int64_t* qoff, int64_t nq, int max_q_frames, const float* tf, const int64_t* toff,
                        int64_t nt, int max_t_frames, int dim, float* cost, cudaStream_t st) {
   if (nq == 0 || nt == 0) return cudaSuccess;
-  const size_t smem = (size_t)std::max(max_t_frames, 1) * dim * sizeof(float);
+  if (dim > kDtwMaxDim) return cudaErrorInvalidValue;
+  const size_t smem = dtw_smem_bytes(max_t_frames, dim);
   // grid.y is limited to 65535: queries are processed in slabs
   for (int64_t q0 = 0; q0 < nq; q0 += 65535) {
     const int64_t qc = std::min<int64_t>(65535, nq - q0);
@@ -284,14 +305,17 @@ cudaError_t launch_dtw(const float* qf, const int64_t* qoff, int64_t nq, int max
     auto run = [&](auto kern) -> cudaError_t {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      kern<<<grid, 32, smem, st>>>(cq, oq, qc, tf, toff, nt, dim, max_t_frames, cc);
+      kern<<<grid, 32, smem, st>>>(cq, oq, qc, tf, toff, nt, dim, std::max(max_t_frames, 1), cc);
       return cudaGetLastError();
     };
     cudaError_t e;
-    if (max_q_frames <= 32) e = run(dtw_kernel<1>);
-    else if (max_q_frames <= 64) e = run(dtw_kernel<2>);
-    else if (max_q_frames <= 128) e = run(dtw_kernel<4>);
-    else e = run(dtw_kernel<8>);
+    if (dim > 64) e = run(dtw_kernel<1, 128>);
+    else if (dim > 32) e = run(dtw_kernel<2, 64>);
+    else if (dim > 16) e = run(dtw_kernel<4, 32>);
+    else if (max_q_frames <= 32) e = run(dtw_kernel<1, 16>);
+    else if (max_q_frames <= 64) e = run(dtw_kernel<2, 16>);
+    else if (max_q_frames <= 128) e = run(dtw_kernel<4, 16>);
+    else e = run(dtw_kernel<8, 16>);
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;

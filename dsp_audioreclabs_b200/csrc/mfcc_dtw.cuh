@@ -18,6 +18,7 @@ cudaError_t launch_mfcc(const int16_t* samples, const int64_t* offsets, const in
                         int32_t* n_frames_out, unsigned int* work_counter, int sm_count, cudaStream_t st);
 int dtw_max_query_frames();
 int dtw_max_dim();
+size_t dtw_smem_bytes(int max_t_frames, int dim);     // template frames + one boundary row
 cudaError_t launch_dtw(const float* qf, const int64_t* qoff, int64_t nq, int max_q_frames, const float* tf, const int64_t* toff,
                        int64_t nt, int max_t_frames, int dim, float* cost, cudaStream_t st);
 cudaError_t launch_dtw_topk(const float* cost, int64_t nq, int64_t nt, int k, int64_t index_base, const int32_t* labels,

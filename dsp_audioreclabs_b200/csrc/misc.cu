@@ -50,6 +50,18 @@ __global__ void zscore_apply_kernel(const double* __restrict__ x, int64_t total,
   }
 }
 
+// the same on float32 statistics straight out of the fused front end (widened exactly, then the reference's arithmetic)
+__global__ void zscore_apply_f32_kernel(const float* __restrict__ x, int64_t total, int d,
+                                        const double* __restrict__ mean, const double* __restrict__ std,
+                                        double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % d);
+    const double s = std[j] == 0.0 ? 1.0 : std[j];
+    out[i] = ((double)x[i] - mean[j]) / s;
+  }
+}
+
 __global__ void f32_to_f64_kernel(const float* __restrict__ in, int64_t n, double* __restrict__ out) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     out[i] = (double)in[i];
@@ -70,6 +82,16 @@ cudaError_t zscore_apply(const double* x, int64_t n, int d, const double* mean, 
   if (total > 0) {
     const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
     zscore_apply_kernel<<<grid, 256, 0, st>>>(x, total, d, mean, std, out);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t zscore_apply_f32(const float* x, int64_t n, int d, const double* mean, const double* std, double* out,
+                             cudaStream_t st) {
+  const int64_t total = n * d;
+  if (total > 0) {
+    const int grid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    zscore_apply_f32_kernel<<<grid, 256, 0, st>>>(x, total, d, mean, std, out);
   }
   return cudaGetLastError();
 }

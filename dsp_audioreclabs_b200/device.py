@@ -62,6 +62,10 @@ class DeviceFrontend:
         self._out = FrontendOutputs(_dp(self.start), _dp(self.end), _dp(self.n_epd_frames), _dp(self.n_frames),
                                     _dp(self.status), _dp(self.energy), _dp(self.magnitude), _dp(self.zcr),
                                     _dp(self.stats), _dp(self.epd_energy), _dp(self.epd_zcr))
+        # the uploads and fills above were enqueued on torch's current stream; run() may use another one
+        self._ready = torch.cuda.Event()
+        self._ready.record(torch.cuda.current_stream(dev))
+        self._waited = set()
 
     def set_window(self, window_type):
         self.params.window = _capi.WINDOW_IDS[window_type]
@@ -84,6 +88,9 @@ class DeviceFrontend:
         self.params.aligned16 = int(samples.data_ptr() % 16 == 0 and
                                     bool(np.all(self.h_offsets[:-1] * samples.element_size() % 16 == 0)))
         st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        if st.cuda_stream not in self._waited:            # once per stream: order the launch after the construction work
+            st.wait_event(self._ready)
+            self._waited.add(st.cuda_stream)
         self.ctx.set_stream(st.cuda_stream)
         check(self.ctx.lib.dsp_frontend_batch_device(
             self.ctx.handle, _dp(samples), _TORCH_DTYPES[samples.dtype], _dp(self.offsets), _dp(self.lengths),
@@ -181,3 +188,16 @@ def zscore_device(x, mean=None, std=None, ctx=None):
     out = torch.empty_like(x)
     check(ctx.lib.dsp_zscore_device(ctx.handle, _dp(x), n, d, 0, _dp(m), _dp(s), _dp(out)))
     return out, m, s
+
+
+def zscore_apply_f32(stats, mean, std, out=None, ctx=None):
+    """(float32 [n, d] statistics of the fused front end) -> float64 z-scores with the given train mean / std:
+    one kernel between DeviceFrontend.stats and DeviceKNN.predict, no torch arithmetic on the path."""
+    assert stats.is_cuda and stats.dtype == torch.float32 and stats.is_contiguous() and stats.dim() == 2
+    ctx = ctx or default_context(stats.device.index or 0)
+    ctx.set_stream(torch.cuda.current_stream(stats.device).cuda_stream)
+    n, d = stats.shape
+    if out is None:
+        out = torch.empty(n, d, dtype=torch.float64, device=stats.device)
+    check(ctx.lib.dsp_zscore_apply_f32_device(ctx.handle, _dp(stats), n, d, _dp(mean), _dp(std), _dp(out)))
+    return out

@@ -4,9 +4,10 @@
   sample count, NO collective on the data path (`utterance_shards`).
 * KNN: the train set is sharded by row.  Every rank scores the (all-gathered) queries against
   its own rows, keeps its local top-k (distance, global row, label), and ONE all-gather of
-  those candidate lists over NCCL/NVLink lets each rank merge and vote for its own queries
-  (`ShardedKNN.predict`).  When the train matrix is small (D = 15) the cheaper equivalent is
-  to all-gather the train rows once and classify locally (`ShardedKNN.predict_replicated`).
+  those candidate lists -- packed into a single buffer -- over NCCL/NVLink lets each rank merge
+  and vote for its own queries (`ShardedKNN.predict_sharded`).  When the train matrix is small
+  (D = 15: 12 MB) the cheaper equivalent is to all-gather the train rows once per fit and
+  classify locally (`ShardedKNN.predict_replicated`); `ShardedKNN.predict` picks by size.
 
 * DTW template matching (the self-specified MFCC + DTW variant): templates sharded by row, queries replicated,
   the same single all-gather of top-k candidates (`ShardedDTW`).
@@ -39,18 +40,41 @@ def utterance_shards(offsets, world):
 
 
 def _all_gather_rows(x, group=None):
-    """all_gather of [n_r, ...] tensors with different n_r: returns (list of per-rank tensors)."""
+    """all-gather of [n_r, ...] tensors with different n_r: returns the list of per-rank tensors.  One tiny
+    all-gather of the row counts, one all_gather_into_tensor of the rows padded to the largest shard."""
     world = dist.get_world_size(group)
     n = torch.tensor([x.shape[0]], dtype=torch.int64, device=x.device)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    sizes = [int(s.item()) for s in sizes]
+    sizes = torch.empty(world, dtype=torch.int64, device=x.device)
+    dist.all_gather_into_tensor(sizes, n, group=group)
+    sizes = [int(v) for v in sizes.tolist()]
     mx = max(sizes)
     pad = torch.zeros((mx,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
     pad[: x.shape[0]] = x
-    out = [torch.empty_like(pad) for _ in range(world)]
-    dist.all_gather(out, pad, group=group)
-    return [o[:s] for o, s in zip(out, sizes)]
+    out = torch.empty((world * mx,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return [out[r * mx: r * mx + s] for r, s in enumerate(sizes)]
+
+
+def pack_candidates(d2, idx, lab):
+    """(sqdist f64 [m,k], global row i64 [m,k], label i32 [m,k]) -> ONE int64 buffer [m, k, 3] (the float64 bit
+    patterns travel as int64), so that the candidate exchange is a single collective."""
+    return torch.stack([d2.contiguous().view(torch.int64), idx.to(torch.int64), lab.to(torch.int64)], dim=2).contiguous()
+
+
+def unpack_candidates(packed):
+    """[..., k, 3] int64 -> (sqdist f64, idx i64, label i32) as contiguous tensors."""
+    return (packed[..., 0].contiguous().view(torch.float64), packed[..., 1].contiguous(),
+            packed[..., 2].to(torch.int32).contiguous())
+
+
+def all_gather_candidates(d2, idx, lab, group=None):
+    """The single candidate exchange of the row-sharded design: every rank contributes its local top-k of the SAME
+    m queries; returns [R, m, k] x 3."""
+    world = dist.get_world_size(group)
+    mine = pack_candidates(d2, idx, lab)
+    out = torch.empty((world,) + tuple(mine.shape), dtype=torch.int64, device=mine.device)
+    dist.all_gather_into_tensor(out.view(-1), mine.view(-1), group=group)
+    return unpack_candidates(out)
 
 
 class ShardedKNN:
@@ -58,64 +82,82 @@ class ShardedKNN:
 
     local_topk(train, labels, queries, k, index_base) -> (sqdist[m,k] f64, idx[m,k] i64, label[m,k] i32)
     merge_vote(cand_sqdist[R,m,k], cand_idx[R,m,k], cand_label[R,m,k]) -> labels[m] i32
-    Both default to the CUDA library (device tensors)."""
+    Both default to the CUDA library (device tensors).  Labels are class indices >= 0 (the kernels use negative
+    labels for empty candidate slots); encode other label sets to 0..C-1 first, as batch.KNN does.
 
-    def __init__(self, n_neighbors=3, group=None, local_topk=None, merge_vote=None):
+    replicate_below: `predict` classifies against an all-gathered copy of the train set, with NO per-call
+    candidate exchange, when the whole train set is at most this many bytes (the 15-dim statistical features:
+    100,000 rows are 12 MB); larger train sets (sequence features, DTW templates) take the row-sharded exchange.
+    Pass 0 to force the exchange."""
+
+    def __init__(self, n_neighbors=3, group=None, local_topk=None, merge_vote=None, replicate_below=64 << 20):
         self.k = int(n_neighbors)
         self.group = group
         self._topk = local_topk or self._cuda_topk
         self._merge = merge_vote or self._cuda_merge
-        self._knn = None
+        self.replicate_below = int(replicate_below)
+        self._knn = {}
+        self._full = None
 
     # -- CUDA callbacks ---------------------------------------------------------------------
     def _cuda_topk(self, train, labels, queries, k, index_base):
         from .device import DeviceKNN
-        if self._knn is None or self._knn_key != (train.data_ptr(), train.shape[0], index_base):
-            self._knn = DeviceKNN(k, device=train.device, index_base=index_base).fit(train, labels)
-            self._knn_key = (train.data_ptr(), train.shape[0], index_base)
-        return self._knn.topk(queries)
+        key = (train.data_ptr(), train.shape[0], index_base)
+        knn = self._knn.get(key)
+        if knn is None:
+            knn = self._knn[key] = DeviceKNN(k, device=train.device, index_base=index_base).fit(train, labels)
+        return knn.topk(queries)
 
     def _cuda_merge(self, cd, ci, cl):
         from .device import DeviceKNN
-        helper = self._knn or DeviceKNN(self.k, device=cd.device)
+        helper = next(iter(self._knn.values()), None) or DeviceKNN(self.k, device=cd.device)
         return helper.merge_vote(cd, ci, cl)[0]
 
     # -- API -------------------------------------------------------------------------------
     def fit(self, train_shard, labels_shard):
-        """Keep this rank's rows; the global row index of its first row comes from an
-        all-gather of the shard sizes."""
+        """Keep this rank's rows; the global row index of its first row and the size of the whole train set come
+        from one all-gather of the shard sizes.  A second fit() starts from scratch."""
         world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if labels_shard.numel() and int(labels_shard.min()) < 0:
+            raise ValueError("labels must be class indices >= 0 (encode them with np.unique(..., return_inverse=True))")
+        for knn in self._knn.values():
+            knn.free()
+        self._knn, self._full = {}, None
         n = torch.tensor([train_shard.shape[0]], dtype=torch.int64, device=train_shard.device)
-        sizes = [torch.zeros_like(n) for _ in range(world)]
-        dist.all_gather(sizes, n, group=self.group)
-        self.index_base = int(sum(int(s.item()) for s in sizes[:rank]))
+        sizes = torch.empty(world, dtype=torch.int64, device=train_shard.device)
+        dist.all_gather_into_tensor(sizes, n, group=self.group)
+        sizes = [int(v) for v in sizes.tolist()]
+        self.index_base = int(sum(sizes[:rank]))
+        self.n_total = int(sum(sizes))
         self.train, self.labels = train_shard.contiguous(), labels_shard.contiguous()
         return self
 
+    def train_bytes(self):
+        return self.n_total * int(self.train.shape[1]) * self.train.element_size()
+
     def predict(self, queries_local):
-        """Labels for this rank's queries.  Collectives: one all-gather of the query features, one
-        all-gather of the per-shard top-k candidates."""
+        """Labels for this rank's queries: the replicated-train path when the train set is small, else the
+        row-sharded exchange (every rank must take the same branch: the choice depends on global sizes only)."""
+        if self.train_bytes() <= self.replicate_below:
+            return self.predict_replicated(queries_local)
+        return self.predict_sharded(queries_local)
+
+    def predict_sharded(self, queries_local):
+        """The north-star exchange: all-gather the query features, score ALL queries against the local rows, ONE
+        all-gather of the packed per-shard top-k candidates, merge + vote for the rank's own queries."""
         rank = dist.get_rank(self.group)
         per_rank_q = _all_gather_rows(queries_local.contiguous(), self.group)
         q_all = torch.cat(per_rank_q, dim=0)
         d2, idx, lab = self._topk(self.train, self.labels, q_all, self.k, self.index_base)
-        world = dist.get_world_size(self.group)
-        cd = [torch.empty_like(d2) for _ in range(world)]
-        ci = [torch.empty_like(idx) for _ in range(world)]
-        cl = [torch.empty_like(lab) for _ in range(world)]
-        # the single candidate exchange (three dtypes -> three tensors of one logical all-gather)
-        dist.all_gather(cd, d2, group=self.group)
-        dist.all_gather(ci, idx, group=self.group)
-        dist.all_gather(cl, lab, group=self.group)
+        cd, ci, cl = all_gather_candidates(d2, idx, lab, self.group)
         lo = sum(t.shape[0] for t in per_rank_q[:rank])
         hi = lo + queries_local.shape[0]
-        return self._merge(torch.stack([c[lo:hi] for c in cd]), torch.stack([c[lo:hi] for c in ci]),
-                           torch.stack([c[lo:hi] for c in cl]))
+        return self._merge(cd[:, lo:hi].contiguous(), ci[:, lo:hi].contiguous(), cl[:, lo:hi].contiguous())
 
     def predict_replicated(self, queries_local):
-        """D = 15 fast path: all-gather the (small) train shards once, classify own queries with no
-        candidate exchange.  Same result as `predict`."""
-        if getattr(self, "_full", None) is None:
+        """All-gather the (small) train shards once per fit, classify own queries with no candidate exchange.
+        Same result as `predict_sharded`."""
+        if self._full is None:
             tr = torch.cat(_all_gather_rows(self.train, self.group), dim=0)
             lb = torch.cat(_all_gather_rows(self.labels, self.group), dim=0)
             self._full = (tr.contiguous(), lb.contiguous())
@@ -125,17 +167,18 @@ class ShardedKNN:
 
 class ShardedDTW:
     """Row-sharded DTW template matching (BASELINE config 5: templates sharded by row, queries replicated, ONE
-    all-gather of the per-shard top-k candidates).  Sequences are lists of [frames, dim] float32 arrays.
+    all-gather of the packed per-shard top-k candidates).  Sequences are lists of [frames, dim] float32 arrays.
 
     local_topk(templates, labels, queries, k, index_base) -> (cost[m,k] f64, idx[m,k] i64, label[m,k] i32), sorted by
-    (cost, index); defaults to the CUDA library (mfcc_dtw.DTWClassifier).  The merge is a k-way selection over the
-    R sorted lists by (cost, global index) and a vote with ties to the smallest label."""
+    (cost, index); defaults to the CUDA library (mfcc_dtw.DTWClassifier).  The merge is a k-way selection by
+    (cost, global index) with torch sorts on the device the group communicates on (CUDA under NCCL: pass `device`)."""
 
-    def __init__(self, n_neighbors=1, group=None, local_topk=None):
+    def __init__(self, n_neighbors=1, group=None, local_topk=None, device=None):
         self.k = int(n_neighbors)
         self.group = group
         self._topk = local_topk or self._cuda_topk
         self._clf = None
+        self.device = device          # torch.device for the exchange buffers; None = CPU (gloo)
 
     def _cuda_topk(self, templates, labels, queries, k, index_base):
         from .mfcc_dtw import DTWClassifier
@@ -146,29 +189,32 @@ class ShardedDTW:
 
     def fit(self, template_shard, labels_shard):
         world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-        n = torch.tensor([len(template_shard)], dtype=torch.int64)
-        sizes = [torch.zeros_like(n) for _ in range(world)]
-        dist.all_gather(sizes, n, group=self.group)
-        self.index_base = int(sum(int(s.item()) for s in sizes[:rank]))
+        self._clf = None                      # a second fit() must not answer from the old shard
+        n = torch.tensor([len(template_shard)], dtype=torch.int64, device=self.device)
+        sizes = torch.empty(world, dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(sizes, n, group=self.group)
+        self.index_base = int(sum(int(v) for v in sizes.tolist()[:rank]))
         self.templates, self.labels = list(template_shard), np.asarray(labels_shard)
         return self
 
     def kneighbors(self, queries):
         """(cost[m,k], global template index[m,k], label[m,k]) for the (replicated) queries."""
-        world = dist.get_world_size(self.group)
         c, i, l = self._topk(self.templates, self.labels, queries, self.k, self.index_base)
         c, i, l = (torch.from_numpy(np.ascontiguousarray(a)) for a in (c.astype(np.float64), i.astype(np.int64), l.astype(np.int32)))
-        cc = [torch.empty_like(c) for _ in range(world)]
-        ci = [torch.empty_like(i) for _ in range(world)]
-        cl = [torch.empty_like(l) for _ in range(world)]
-        dist.all_gather(cc, c, group=self.group)      # the single candidate exchange (three dtypes)
-        dist.all_gather(ci, i, group=self.group)
-        dist.all_gather(cl, l, group=self.group)
-        cost = torch.cat(cc, dim=1).numpy(); idx = torch.cat(ci, dim=1).numpy(); lab = torch.cat(cl, dim=1).numpy()
-        idx_key = np.where(idx < 0, np.iinfo(np.int64).max, idx)
-        order = np.lexsort((idx_key, cost), axis=1)[:, :self.k]
-        take = lambda a: np.take_along_axis(a, order, axis=1)
-        return take(cost), take(idx), take(lab)
+        if self.device is not None:
+            c, i, l = c.to(self.device), i.to(self.device), l.to(self.device)
+        cc, ci, cl = all_gather_candidates(c, i, l, self.group)            # the single candidate exchange
+        # k-way selection over the R sorted lists by (cost, global index), on whatever device the group runs on:
+        # a stable sort by index followed by a stable sort by cost
+        m = cc.shape[1]
+        cost = cc.permute(1, 0, 2).reshape(m, -1)
+        idx = ci.permute(1, 0, 2).reshape(m, -1)
+        lab = cl.permute(1, 0, 2).reshape(m, -1)
+        key = torch.where(idx < 0, torch.full_like(idx, torch.iinfo(torch.int64).max), idx)
+        o1 = torch.argsort(key, dim=1, stable=True)
+        o2 = torch.argsort(cost.gather(1, o1), dim=1, stable=True)
+        order = o1.gather(1, o2)[:, :self.k]
+        return tuple(a.gather(1, order).cpu().numpy() for a in (cost, idx, lab))
 
     def predict(self, queries):
         _, _, lab = self.kneighbors(queries)

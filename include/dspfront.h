@@ -67,10 +67,11 @@ typedef struct {
   double zcr_threshold_ratio;  /* config.ZCR_THRESHOLD_RATIO */
   int32_t channels;            /* 1, or 2 = interleaved stereo averaged per frame (:43-44) */
   int32_t force_exact;         /* 1: run every utterance through the float64 replay kernel */
-  int32_t aligned16;           /* device entry point only: 1 = the caller guarantees that every utterance
-                                * starts on a 16-byte boundary (offsets multiples of 8 samples, 16-byte
-                                * aligned buffer), which lets the streaming build of the fused kernel run;
-                                * 0 = unknown (shared-memory-resident build, any alignment) */
+  int32_t aligned16;           /* device entry point only, optional hint: 1 = every utterance starts on a 16-byte
+                                * boundary (offsets multiples of 8 samples, 16-byte aligned buffer).  Since ABI 2
+                                * nothing depends on it for the pipelined kernel -- packed CSR batches of any
+                                * length run at full speed, its producer realigns them on chip; the hint only
+                                * selects between two builds of the older resident kernel for other geometries */
 } dsp_frontend_params;
 
 /* Output pointers of one front-end batch.  Any pointer may be NULL to skip
@@ -190,6 +191,11 @@ int dsp_zscore_host(dsp_context* ctx, const double* x, int64_t n, int32_t d, int
                     double* std, double* out);
 int dsp_zscore_device(dsp_context* ctx, const double* x, int64_t n, int32_t d, int fit, double* mean,
                       double* std, double* out);
+/* Apply only, on the float32 [n,15] statistics the fused front end writes (dsp_frontend_outputs.stats): each value
+ * is widened exactly and normalised with the given float64 mean / std (std == 0 counts as 1) -- the step between
+ * the front end and dsp_knn_predict_device in the batched pipeline (train_model.py:147-148).  Device pointers. */
+int dsp_zscore_apply_f32_device(dsp_context* ctx, const float* x, int64_t n, int32_t d, const double* mean,
+                                const double* std, double* out);
 
 /* ---- KNN classify (src/models.py:33-35,52-58 -> sklearn KNeighborsClassifier) ---- */
 typedef struct dsp_knn dsp_knn;
@@ -211,7 +217,8 @@ int dsp_knn_topk_device(dsp_knn* knn, const double* queries, int64_t m, int64_t*
 int dsp_knn_predict_host(dsp_knn* knn, const double* queries, int64_t m, int32_t* labels_out);
 /* Diagnostics of the last topk / predict call on this handle (waits for it): how many queries the
  * float64 certificate sent to the exhaustive float64 rescan, and which candidate scan ran
- * (0 = none: float64 only, 1 = fp32 tiled scan, 2 = tensor-core scan).  Results never depend on it. */
+ * (0 = none: float64 only, 1 = fp32 tiled scan, 2 = tensor-core scan of wide features, 3 = tensor-core filter for
+ * d <= 15 with the fp32 scan standing in when a query leaves its range).  Results never depend on it. */
 int dsp_knn_last_stats(dsp_knn* knn, int64_t* rescanned, int32_t* scan_kind);
 int dsp_knn_predict_device(dsp_knn* knn, const double* queries, int64_t m, int32_t* labels_out);
 /* Merge R candidate lists (as gathered from R row shards, layout [R,m,k]) into the global

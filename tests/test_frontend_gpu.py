@@ -298,25 +298,66 @@ def test_batch_handoff_sizes(ctx, n_utts):
             assert np.allclose(e, r["energy"], rtol=1e-5, atol=0) and np.allclose(m, r["magnitude"], rtol=1e-5, atol=0), b
 
 
-def test_pipelined_kernel_replays_misaligned_utterances(ctx):
-    """A packed (CSR) batch whose utterances do not start on 16-byte boundaries, forced through the pipelined
-    kernel: aligned utterances take the fast path, the others are handed to the float64 replay inside the same
-    call (records still travel through the batch hand-off) -- every result equals the oracle's."""
+@pytest.mark.parametrize("lead", [0, 1, 2, 3, 4, 5, 6, 7])
+def test_pipelined_kernel_realigns_misaligned_utterances(ctx, lead):
+    """A packed (CSR) batch whose utterances start at ARBITRARY sample offsets (odd lengths, `lead` samples in front of
+    the first one): the pipelined kernel's producer realigns them on chip -- no utterance is handed to the float64
+    replay because of its address, and every result equals the oracle's.  Also without the pcm_variant
+    knob: the automatic choice for 256 / 128 is the pipelined kernel whatever the alignment."""
     from dsp_audioreclabs_b200 import batch
     from oracle import frontend_oracle as fo, synth
-    lens = [9001, 12347, 7777, 15003, 8192, 1000, 5000, 30001, 44100, 20011, 333, 25000, 26001, 40000, 12000, 13001]
-    utts = [synth.utterance_pcm(70 + i, n, seed0=3) for i, n in enumerate(lens)] * 3
+    lens = [9001, 12347, 7777, 15003, 8192, 1000, 5000, 30001, 44100, 20011, 333, 25000, 26001, 40000, 12000, 13001, 2049, 2047,
+            4096, 4097, 7, 15, 16, 17, 255, 256, 257, 0, 1, 6143, 6145]
+    utts = [synth.utterance_pcm(70 + i, n, seed0=3) for i, n in enumerate(lens)] * 2
     samples, off = pack(utts)
-    ctx.set_tuning("pcm_variant", PIPE)
-    try:
-        res = batch.frontend_batch(samples, off, 256, 128, "hamming", emit_epd_lists=True, ctx=ctx)
-    finally:
-        ctx.set_tuning("pcm_variant", -1)
-    replayed = int((res.status >= 0x100).sum())
-    assert 0 < replayed < len(utts)                      # 8192-, 1000-, 40000-, 12000-sample boundaries keep some starts aligned
+    refs = fo.frontend_batch(samples, off, 256, 128, "hamming")
+    samples = np.concatenate([np.full(lead, 12345, np.int16), samples, np.full(9, -4321, np.int16)])
+    off = off + lead
+    for forced in (True, False):
+        if forced:
+            ctx.set_tuning("pcm_variant", PIPE)
+        try:
+            res = batch.frontend_batch(samples, off, 256, 128, "hamming", emit_epd_lists=True, ctx=ctx)
+        finally:
+            ctx.set_tuning("pcm_variant", -1)
+        assert int((res.status >= 0x100).sum()) == 0             # nothing replayed: not for alignment, not for margins
+        for b, r in enumerate(refs):
+            if r is None:                                         # the reference raises (empty utterance): status says so
+                assert (int(res.status[b]) & 0xff) != 0, (lead, b)
+                continue
+            assert (int(res.status[b]) & 0xff) == 0, (lead, b)
+            assert (int(res.start[b]), int(res.end[b]), int(res.n_frames[b])) == (r["start"], r["end"], len(r["zcr"])), (lead, b)
+            e, m, z = res.frames(b)
+            assert np.array_equal(z.astype(np.float64), r["zcr"]), (lead, b)
+            assert np.allclose(e, r["energy"], rtol=1e-5, atol=0) and np.allclose(m, r["magnitude"], rtol=1e-5, atol=0), (lead, b)
+            el, zl = res.epd_lists(b)
+            assert np.array_equal(zl.astype(np.float64), r["zcr_list"]) and np.allclose(el, r["energy_list"], rtol=1e-12, atol=0), (lead, b)
+
+
+# BASELINE configs[3] / SURVEY.md 8(d) config 4: the power-of-two pairs and the REAL grids of ablation_study.py
+# (config.py:81,85 x train_model.py:45-46: frame lengths at shift 441, shifts at length 1102 -- up to fl = 2205 and
+# fs > fl), one launch per configuration, whichever kernel the library routes the geometry to
+CONFIG4 = ([(64, 32), (128, 64), (256, 128), (512, 256), (1024, 512), (2048, 1024)]
+           + [(int(44100 * ms / 1000), 441) for ms in (8, 10, 12, 15, 18, 20, 25, 30, 35, 40, 45, 50)]
+           + [(1102, int(44100 * ms / 1000)) for ms in (3, 5, 7, 8, 10, 12, 15, 18, 20, 25, 30)])
+
+
+@pytest.mark.parametrize("fl,fs", CONFIG4)
+def test_config4_geometries_match_the_oracle(ctx, fl, fs):
+    from dsp_audioreclabs_b200 import batch
+    from oracle import frontend_oracle as fo, synth
+    assert (1102, 441) in CONFIG4 and (2205, 441) in CONFIG4 and (1102, 1323) in CONFIG4 and (1102, 132) in CONFIG4
+    lens = [22050, 30011, 17000, 44100, 9001, 26000]
+    utts = [synth.utterance_pcm(300 + i, n, seed0=17) for i, n in enumerate(lens)]
+    samples, off = pack(utts)                                     # packed CSR: odd lengths, arbitrary alignment
+    win = ("rectangular", "hamming", "hanning")[(fl + fs) % 3]
+    res = batch.frontend_batch(samples, off, fl, fs, win, emit_epd_lists=True, ctx=ctx)
     for b, u in enumerate(utts):
-        r = fo.frontend_utterance(u, 256, 128, "hamming")
-        assert (int(res.start[b]), int(res.end[b]), int(res.n_frames[b])) == (r["start"], r["end"], len(r["zcr"])), b
+        r = fo.frontend_utterance(u, fl, fs, win)
+        assert (int(res.start[b]), int(res.end[b]), int(res.n_frames[b])) == (r["start"], r["end"], len(r["zcr"])), (fl, fs, b)
         e, m, z = res.frames(b)
-        assert np.array_equal(z.astype(np.float64), r["zcr"]), b
-        assert np.allclose(e, r["energy"], rtol=1e-5, atol=0) and np.allclose(m, r["magnitude"], rtol=1e-5, atol=0), b
+        assert np.array_equal(z.astype(np.float64), r["zcr"]), (fl, fs, b)
+        assert np.allclose(e, r["energy"], rtol=RTOL_F32, atol=0) and np.allclose(m, r["magnitude"], rtol=RTOL_F32, atol=0), (fl, fs, b)
+        el, zl = res.epd_lists(b)
+        assert np.array_equal(zl.astype(np.float64), r["zcr_list"]) and np.allclose(el, r["energy_list"], rtol=RTOL_EPD, atol=0)
+        assert_stats_close(res.stats[b], r["stats"], r)

@@ -98,3 +98,93 @@ def test_row_sharded_knn_merge_equals_single_shard(ctx, golden_knn):
         torch.cuda.synchronize()
         assert np.array_equal(idx.cpu().numpy(), k["d15/nbr_idx"])
         assert np.array_equal(labels.cpu().numpy(), k["d15/pred"])
+
+
+# ---- tensor-core candidate filter for d <= 15 (csrc/knn_tc16.cu) ---------------------------------------------
+SCAN_FP32, SCAN_TC16 = 1, 3
+
+
+def test_tc16_filter_serves_the_15_dim_path(ctx, golden_knn):
+    """The sklearn fixture goes through the tcgen05 filter (scan kind 3); the float64 certificate accepts (almost)
+    every query, and turning the filter off (fp32 tiled scan) gives the same neighbours."""
+    import os
+    from dsp_audioreclabs_b200 import batch
+    k = golden_knn
+    knn = batch.KNN(3, ctx=ctx).fit(k["d15/train_norm"], k["d15/train_labels"])
+    _, idx, _ = knn.kneighbors(k["d15/query_norm"])
+    rescanned, kind = knn.last_stats()
+    assert kind == SCAN_TC16 and rescanned <= 2
+    assert np.array_equal(idx, k["d15/nbr_idx"])
+    os.environ["DSP_KNN_NO_TC16"] = "1"
+    try:
+        ref = batch.KNN(3, ctx=ctx).fit(k["d15/train_norm"], k["d15/train_labels"])
+    finally:
+        del os.environ["DSP_KNN_NO_TC16"]
+    assert ref.last_stats()[1] == SCAN_FP32
+    assert np.array_equal(ref.kneighbors(k["d15/query_norm"])[1], idx)
+
+
+@pytest.mark.parametrize("d", [1, 2, 7, 15])
+@pytest.mark.parametrize("n", [5, 127, 128, 129, 1000, 4097])
+def test_tc16_filter_shapes(ctx, d, n):
+    """Tile edges: train rows around multiples of 128, query counts around the 256-query work unit, thin features."""
+    from dsp_audioreclabs_b200 import batch
+    from oracle import knn_oracle as ko
+    rng = np.random.default_rng(100 * d + n)
+    train = rng.standard_normal((n, d)) * rng.uniform(0.2, 3.0, d)
+    labels = rng.integers(0, 6, n)
+    knn = batch.KNN(3, ctx=ctx).fit(train, labels)
+    for m in (1, 255, 256, 257, 700):
+        q = rng.standard_normal((m, d)) * 1.5
+        _, idx, _ = knn.kneighbors(q)
+        assert knn.last_stats()[1] == SCAN_TC16
+        assert np.array_equal(idx, ko.knn_topk(train, q, 3)[0]), (d, n, m)
+
+
+def test_tc16_range_gates(ctx):
+    """Values the split-fp16 filter does not cover: a query with |q|^2 > 8192 opens the device-side gate and the
+    fp32 scan answers the call; a train row out of range switches the filter off at fit.  Exact either way."""
+    from dsp_audioreclabs_b200 import batch
+    from oracle import knn_oracle as ko
+    rng = np.random.default_rng(5)
+    train = rng.standard_normal((3000, 15))
+    labels = rng.integers(0, 4, 3000)
+    knn = batch.KNN(3, ctx=ctx).fit(train, labels)
+    q = rng.standard_normal((300, 15))
+    q[17] *= 400.0                                        # |q|^2 ~ 2.4e6
+    assert np.array_equal(knn.kneighbors(q)[1], ko.knn_topk(train, q, 3)[0])
+    assert knn.last_stats()[1] == SCAN_TC16                # the handle still owns a filter; this call was gated
+    big = train.copy()
+    big[5] *= 1000.0
+    knn2 = batch.KNN(3, ctx=ctx).fit(big, labels)
+    assert knn2.last_stats()[1] == SCAN_FP32
+    assert np.array_equal(knn2.kneighbors(q[:16])[1], ko.knn_topk(big, q[:16], 3)[0])
+    # tiny-scale features: the filter's absolute error floor makes the certificate reject, the float64 rescan answers
+    small = train * 1e-6
+    knn3 = batch.KNN(3, ctx=ctx).fit(small, labels)
+    assert np.array_equal(knn3.kneighbors(q[:16] * 1e-6)[1], ko.knn_topk(small, q[:16] * 1e-6, 3)[0])
+
+
+def test_knn_config3_scale_matches_sklearn_through_the_reference(ctx):
+    """10,240 queries against the 100,000-row train set, z-score + KNN, neighbour
+    indices and labels bit-exact against sklearn (kd_tree) driven by the reference's create_classifier('knn')
+    (fixture: oracle/gen_golden_knn3.py)."""
+    import os
+    from conftest import GOLDEN
+    from dsp_audioreclabs_b200 import batch
+    from oracle.gen_golden_knn3 import checksum, config3_data
+    g = np.load(os.path.join(GOLDEN, "knn_config3_golden.npz"))
+    xtr, ytr, xq, yq = config3_data()
+    if not np.array_equal(checksum(xtr, xq), g["checksum"]):
+        pytest.skip("numpy's random stream differs from the one the fixture was generated with")
+    tn, mu, sd = batch.zscore(xtr, ctx=ctx)
+    qn, _, _ = batch.zscore(xq, mu, sd, ctx=ctx)
+    knn = batch.KNN(3, ctx=ctx).fit(tn, ytr)
+    dist, idx, _ = knn.kneighbors(qn)
+    rescanned, kind = knn.last_stats()
+    assert kind == SCAN_TC16 and rescanned <= 10, rescanned
+    assert np.array_equal(idx, g["nbr_idx"])
+    assert np.allclose(dist, g["nbr_dist"], rtol=1e-12, atol=0)
+    pred = knn.predict(qn)
+    assert np.array_equal(pred, g["pred"])
+    assert float(np.mean(pred == yq)) == float(g["accuracy"])

@@ -29,14 +29,15 @@ def test_mfcc_matches_the_self_oracle(ctx):
         assert np.all(np.abs(got - ref) <= tol), (b, float((np.abs(got - ref) / tol).max()))
 
 
-@pytest.mark.parametrize("dim", [13, 1, 16])
+@pytest.mark.parametrize("dim", [13, 1, 16, 17, 39, 64, 100])
 def test_dtw_costs_and_neighbours(ctx, dim):
     from dsp_audioreclabs_b200 import mfcc_dtw
     from oracle import mfcc_dtw_oracle as mo
     rng = np.random.default_rng(dim)
     def seq(n, c): return (rng.standard_normal((n, dim)) * 0.3 + np.sin(np.arange(n)[:, None] * (0.1 + 0.05 * c)) * 2).astype(np.float32)
-    t_lens = [1, 2, 31, 32, 33, 64, 65, 100, 128, 129, 200, 256, 40, 57, 90, 7]
-    q_lens = [1, 5, 32, 33, 64, 97, 128, 130, 255, 256, 77]
+    t_lens = [1, 2, 31, 32, 33, 64, 65, 100, 128, 129, 200, 256, 40, 57, 90, 7, 300, 513]
+    # queries longer than one strip of 32 R rows (R = 8 / 4 / 2 / 1 for dim <= 16 / 32 / 64 / 128) cross strip boundaries
+    q_lens = [1, 5, 32, 33, 64, 97, 128, 130, 255, 256, 77, 257, 300, 511, 512, 513, 700]
     labels = np.array([i % 4 for i in range(len(t_lens))])
     temps = [seq(n, labels[i]) for i, n in enumerate(t_lens)]
     quers = [seq(n, i % 4) for i, n in enumerate(q_lens)]

@@ -117,3 +117,24 @@ def test_load_dataset_matrix_matches_the_reference(work):
     assert np.array_equal(y[order], g["y_sorted"])
     assert np.array_equal(X[order], g["X_sorted"])
     assert list(z["names"]) == list(g["names"])
+
+
+@needs_ref
+def test_compare_feature_methods_unchanged(work):
+    """compare_feature_methods.py (module-level script: statistical vs zero-padded sequence features, KNN / SVM /
+    decision tree on both, compare_feature_methods.py:43-176): every accuracy it prints is the reference's.  KNN runs
+    on the CUDA path (D = 15: tensor-core filter; D = 2 max_len: tensor-core scan); SVM / tree are delegated to the
+    reference's own src/models.py.  Both passes over the tree share ONE front-end launch."""
+    env = dict(os.environ, PYTHONPATH=STUBS, SPEECH_DATA_DIR=work["data"], OMP_NUM_THREADS="1")
+    ref_out = subprocess.run([sys.executable, "compare_feature_methods.py"], cwd=work["ref"], env=env, check=True,
+                             capture_output=True, text=True).stdout
+    report = str(work["base"] / "report_cmp.jsonl")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, STUBS]), SPEECH_DATA_DIR=work["data"],
+               DSP_RESULTS_DIR=str(work["base"] / "results_cmp"), DSP_RUN_REPORT=report, OMP_NUM_THREADS="1")
+    our_out = subprocess.run([sys.executable, "-m", "dsp_audioreclabs_b200.run", os.path.join(work["ref"], "compare_feature_methods.py")],
+                             cwd=work["ref"], env=env, check=True, capture_output=True, text=True).stdout
+    keep = lambda text: [ln for ln in text.splitlines() if any(ch.isdigit() for ch in ln)]
+    assert keep(our_out) == keep(ref_out)
+    assert len(keep(our_out)) > 15
+    rep = json.loads(open(report).read().strip().splitlines()[-1])
+    assert rep["gpu_launches"] > 0 and rep["frontend_launches"] == [["tree", 200]]
