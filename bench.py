@@ -38,7 +38,7 @@ SR = 44100
 FL, FS = 256, 128
 WINDOWS = ("rectangular", "hamming", "hanning")
 UTT_LEN = 44100        # samples per utterance: exactly 1 s, packed CSR (every other utterance starts 8 bytes off a
-                       # 16-byte boundary: the kernel's producer realigns those on chip)
+                       # 16-byte boundary: the kernel streams from the boundary below and carries the offset)
 
 
 def parse():

@@ -59,8 +59,13 @@ constexpr int kStreamThreads = 32 * kStreamWarps;
 constexpr int kDescRing = 64;              // > max ring slots: the producer can never lap a reader
 constexpr int kMaxRingSlots = 56;
 constexpr int kRecHdr = 128;
-constexpr int kKeyRegs = 11;               // EPD frames per lane whose float keys stay in registers
+constexpr int kKeyRegs = 13;               // EPD frames per lane whose float keys stay in registers (416 frames = 1.2 s at 256 / 128)
 constexpr int kLanesPerFrame = 8;          // generic windowed pass: lanes cooperating on one frame
+
+// per-group record of pass B (s_meta): bits 0-6 sign changes inside the group, then the sign bits of its samples
+// 0,2,4,6,8 (kMetaE), 1,3,5,7 (kMetaO), 62 (kMetaP) and 63 (kMetaL)
+constexpr int kMetaE = 8, kMetaO = 13, kMetaP = 17, kMetaL = 18;
+__host__ __device__ constexpr int meta_bit(int i) { return (i & 1) ? kMetaO + (i >> 1) : kMetaE + (i >> 1); }
 
 constexpr int kBarStream = 1;              // named barrier of the stream warps
 // record hand-offs use named barriers too (a warp parked on bar.sync costs no issue slots, a warp polling an
@@ -84,11 +89,8 @@ constexpr int kBatch = kMaxTailWarps;
 constexpr int kBarBatchFull = 2, kBarBatchEmpty = 4;
 constexpr int kBatchBarThreads = 32 * (kStreamWarps + kMaxTailWarps);
 
-constexpr int kStageSlots = 4;              // realigning producer: staging pieces of kChunkBytes in flight (power of two)
-constexpr int kStageBytes = kStageSlots * kChunkBytes;
-
 struct PipeLayout {
-  int ring, stage, gsum, bits, meta, rec, scratch, win, desc, part, consts, bars, total;
+  int ring, gsum, head, bits, meta, rec, scratch, win, desc, part, consts, bars, total;
   int rec_bytes, rec_e, rec_fe, rec_fm, rec_z, rec_zf;
 };
 
@@ -99,8 +101,8 @@ __host__ __device__ inline PipeLayout make_pipe_layout(int R, int capG, int capF
   PipeLayout L;
   int o = 0;
   L.ring = o;    o += R * kChunkBytes;
-  L.stage = o;   o += kStageBytes;
   L.gsum = o;    o += 2 * 8 * capG;
+  L.head = o;    o += 2 * 8 * capG;
   L.bits = o;    o += al16(8 * capG + 16);
   L.meta = o;    o += al16(4 * capG);
   L.rec_e = kRecHdr;
@@ -115,7 +117,7 @@ __host__ __device__ inline PipeLayout make_pipe_layout(int R, int capG, int capF
   L.desc = o;    o += kDescRing * 8;
   L.part = o;    o += 2 * kStreamWarps * 16;
   L.consts = o;  o += 2 * 64;
-  L.bars = o;    o += 8 * (2 * R + 2 * nrec + kStageSlots);
+  L.bars = o;    o += 8 * (2 * R + 2 * nrec);
   L.total = o;
   return L;
 }
@@ -405,8 +407,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
   double* s_consts = reinterpret_cast<double*>(smem + L.consts);                        // [2][8]
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* bar_empty = bar_full + R;
-  uint64_t* bar_stage = bar_empty + R + 2 * nrec;       // staging pieces of the realigning producer
-  unsigned char* s_stage = smem + L.stage;
+  unsigned long long* s_head = reinterpret_cast<unsigned long long*>(smem + L.head);   // [2][capG]
 
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   // kChain fixes frame 256 / shift 128 at compile time: divisions, edge handling and the generic loops fold away
@@ -419,7 +420,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
   for (int j = tid; j < fl; j += kPipeThreads) s_win[j] = a.win_f32[j];
   if (tid == 0) {
     for (int i = 0; i < R; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], edges ? kStreamWarps : 1); }
-    for (int i = 0; i < kStageSlots; ++i) mbar_init(&bar_stage[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -431,33 +431,31 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
   if (wid >= kStreamWarps) {
   if constexpr (kSplitRegs) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kTailRegs));
   if (wid == kPipeWarps - 1) {
-    // Lane 0 schedules and issues the bulk copies.  An utterance that starts on a 16-byte boundary goes straight into
-    // the ring.  Any other start (packed CSR batches of odd lengths, ragged data, sliced tensors) is fetched from the
-    // 16-byte boundary below it into a small staging area, and the WHOLE warp moves it into the ring shifted by the
-    // 1..7 samples in between (two 16-byte loads, a funnel shift per word for odd sample offsets, one 16-byte store):
-    // the stream warps always see sample 0 of the utterance at byte 0 of its first slot.  TMA cannot do this shift
-    // itself: bulk copies need 16-byte aligned addresses on both sides, and the tiled tensor-map form faults on an
-    // inner coordinate that is not a multiple of 16 bytes (tools/tma_probe.cu).
+    // Lane 0 schedules and issues the bulk copies.  Bulk copies need 16-byte aligned addresses on both sides (and the
+    // tiled tensor-map form faults on an inner coordinate that is not a multiple of 16 bytes, tools/tma_probe.cu), so an
+    // utterance that starts `shift` = 1..7 samples above a 16-byte boundary (packed CSR batches of odd lengths, ragged
+    // data, sliced tensors) is fetched FROM that boundary: the ring holds the aligned stream, sample i of the utterance at
+    // stream position i + shift, and the stream warps carry the offset through their group algebra (pass A / B / F) --
+    // nothing is moved twice on chip.  The descriptor hands them (utterance, length | shift << 20).
+    if (lane != 0) return;
     int slot = 0, lap = 0, useq = 0;
-    uint32_t stage_phase = 0;                      // bit s: parity the next completion of staging slot s will have
-    unsigned int u_next = 0;
-    if (lane == 0) u_next = atomicAdd(a.work_counter, 1u);
-    u_next = __shfl_sync(0xffffffffu, u_next, 0);
+    unsigned int u_next = atomicAdd(a.work_counter, 1u);
     for (;;) {
       const long long u = (long long)u_next;
       const bool done = u >= a.n_utts;
-      int n = 0;
-      const int16_t* src = nullptr;
+      int n = 0, shift = 0;
+      const unsigned char* gsrc = nullptr;
       if (!done) {
-        if (lane == 0) u_next = atomicAdd(a.work_counter, 1u);       // one index ahead: its latency hides behind the copies
-        u_next = __shfl_sync(0xffffffffu, u_next, 0);
+        u_next = atomicAdd(a.work_counter, 1u);       // one index ahead: its latency hides behind the copies
         const int64_t off = a.offsets[u];
         n = a.lengths ? a.lengths[u] : (int)(a.offsets[u + 1] - off);
-        src = a.samples + off;
+        const int16_t* src = a.samples + off;
+        shift = n > 0 ? (int)((reinterpret_cast<uintptr_t>(src) & 15) >> 1) : 0;     // samples above the 16-byte boundary
+        gsrc = reinterpret_cast<const unsigned char*>(src) - 2 * shift;
       }
-      if (lane == 0) s_desc[useq & (kDescRing - 1)] = make_int2(done ? -1 : (int)u, n);
-      const int nchunks = n > 0 ? (n + kChunkSamples - 1) / kChunkSamples : 1;
-      const int shift = (int)((reinterpret_cast<uintptr_t>(src) & 15) >> 1);     // samples above the 16-byte boundary
+      s_desc[useq & (kDescRing - 1)] = make_int2(done ? -1 : (int)u, n | (shift << 20));
+      const int np = n + shift;                       // samples of the aligned stream
+      const int nchunks = np > 0 ? (np + kChunkSamples - 1) / kChunkSamples : 1;
       uint32_t dst32 = smem_u32(s_ring) + (uint32_t)slot * kChunkBytes, full32 = smem_u32(&bar_full[slot]), empty32 = smem_u32(&bar_empty[slot]);
       auto next_slot = [&]() {
         dst32 += kChunkBytes; full32 += 8; empty32 += 8;
@@ -468,110 +466,34 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
           asm volatile("{\n\t.reg .pred p;\n\tWE_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t@p bra DE_%=;\n\tbra WE_%=;\n\tDE_%=:\n\t}"
                        ::"r"(empty32), "r"((uint32_t)((lap - 1) & 1)), "r"(0x989680u) : "memory");
       };
-      if (shift == 0 || n <= 0) {
-        if (lane == 0) {
-          // full 4 KB chunks first (running shared / global addresses, no per-chunk arithmetic), then the last,
-          // possibly partial one
-          const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(src);
+      // full 4 KB chunks first (running shared / global addresses, no per-chunk arithmetic), then the last,
+      // possibly partial one
 #pragma unroll 1
-          for (int c = 0; c + 1 < nchunks; ++c) {
-            wait_empty();
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full32), "r"((uint32_t)kChunkBytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst32), "l"(gsrc), "r"((uint32_t)kChunkBytes), "r"(full32) : "memory");
-            gsrc += kChunkBytes;
-            next_slot();
-          }
-          {
-            wait_empty();
-            const int s0 = (nchunks - 1) * kChunkSamples;
-            const int cnt = n > 0 ? n - s0 : 0;
-            const uint32_t bytes = ((uint32_t)cnt * 2u) & ~15u;
-            // tail of < 8 samples by plain loads; the release of the arrive below publishes them
-            int16_t* dst = reinterpret_cast<int16_t*>(s_ring + (size_t)slot * kChunkBytes);
-            for (int i = (int)(bytes >> 1); i < cnt; ++i) dst[i] = src[s0 + i];
-            if (bytes) {
-              asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full32), "r"(bytes) : "memory");
-              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                           ::"r"(dst32), "l"(gsrc), "r"(bytes), "r"(full32) : "memory");
-            } else {
-              asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full32) : "memory");
-            }
-            next_slot();
-          }
-        } else {
-          // keep the other lanes' view of the ring position in step with lane 0
-          for (int c = 0; c < nchunks; ++c) next_slot();
-        }
-        __syncwarp();
-      } else {
-        // ---- realigning path --------------------------------------------------------------------------------
-        const unsigned char* gal = reinterpret_cast<const unsigned char*>(src) - 2 * shift;     // 16-byte aligned
-        const uint32_t lb = (2u * (uint32_t)(n + shift)) & ~15u;      // bytes of the aligned stream the bulk copies fetch
-        const int pieces = (int)((lb + kChunkBytes - 1) / kChunkBytes);
-        const int nvec = lb >= 2u * shift ? (int)((lb - 2u * shift) >> 4) : 0;                  // whole output vectors they cover
-        auto issue_piece = [&](int p) {
-          const uint32_t bytes = min((uint32_t)kChunkBytes, lb - (uint32_t)p * kChunkBytes);
-          const uint32_t bar = smem_u32(&bar_stage[p & (kStageSlots - 1)]);
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      for (int c = 0; c + 1 < nchunks; ++c) {
+        wait_empty();
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full32), "r"((uint32_t)kChunkBytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst32), "l"(gsrc), "r"((uint32_t)kChunkBytes), "r"(full32) : "memory");
+        gsrc += kChunkBytes;
+        next_slot();
+      }
+      {
+        wait_empty();
+        const int s0 = (nchunks - 1) * kChunkSamples;
+        const int cnt = np > 0 ? np - s0 : 0;
+        const uint32_t bytes = ((uint32_t)cnt * 2u) & ~15u;
+        // tail of < 8 samples by plain loads; the release of the arrive below publishes them
+        int16_t* dst = reinterpret_cast<int16_t*>(s_ring + (size_t)slot * kChunkBytes);
+        const int16_t* gs = reinterpret_cast<const int16_t*>(gsrc);
+        for (int i = (int)(bytes >> 1); i < cnt; ++i) dst[i] = gs[i];
+        if (bytes) {
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full32), "r"(bytes) : "memory");
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(smem_u32(s_stage) + (uint32_t)(p & (kStageSlots - 1)) * kChunkBytes), "l"(gal + (size_t)p * kChunkBytes), "r"(bytes), "r"(bar)
-                       : "memory");
-        };
-        if (lane == 0)
-          for (int p = 0; p < min(pieces, kStageSlots); ++p) issue_piece(p);
-        int waited = 0;
-        const int ws = shift >> 1;                 // whole words of the shift
-        const uint32_t hs = (shift & 1) ? 16u : 0u;   // and the odd sample
-#pragma unroll 1
-        for (int c = 0; c < nchunks; ++c) {
-          // pieces c and c + 1 hold the bytes of output chunk c
-#pragma unroll 1
-          while (waited < min(c + 2, pieces)) {
-            const int ss = waited & (kStageSlots - 1);
-            mbar_wait(&bar_stage[ss], (stage_phase >> ss) & 1u);
-            stage_phase ^= 1u << ss;
-            ++waited;
-          }
-          wait_empty();
-          unsigned char* ring_slot = s_ring + (size_t)slot * kChunkBytes;
-          const int v_end = min(kChunkBytes / 16, nvec - c * (kChunkBytes / 16));    // output vectors of this chunk
-#pragma unroll 1
-          for (int v = lane; v < v_end; v += 32) {
-            const uint32_t so = ((uint32_t)c * kChunkBytes + 16u * (uint32_t)v) & (kStageBytes - 1);
-            const int4 q0 = *reinterpret_cast<const int4*>(s_stage + so);
-            const int4 q1 = *reinterpret_cast<const int4*>(s_stage + ((so + 16u) & (kStageBytes - 1)));
-            const uint32_t w[8] = {(uint32_t)q0.x, (uint32_t)q0.y, (uint32_t)q0.z, (uint32_t)q0.w, (uint32_t)q1.x, (uint32_t)q1.y, (uint32_t)q1.z, (uint32_t)q1.w};
-            int4 o;
-            switch (ws) {            // warp-uniform
-              case 0: o = make_int4(__funnelshift_r(w[0], w[1], hs), __funnelshift_r(w[1], w[2], hs), __funnelshift_r(w[2], w[3], hs), __funnelshift_r(w[3], w[4], hs)); break;
-              case 1: o = make_int4(__funnelshift_r(w[1], w[2], hs), __funnelshift_r(w[2], w[3], hs), __funnelshift_r(w[3], w[4], hs), __funnelshift_r(w[4], w[5], hs)); break;
-              case 2: o = make_int4(__funnelshift_r(w[2], w[3], hs), __funnelshift_r(w[3], w[4], hs), __funnelshift_r(w[4], w[5], hs), __funnelshift_r(w[5], w[6], hs)); break;
-              default: o = make_int4(__funnelshift_r(w[3], w[4], hs), __funnelshift_r(w[4], w[5], hs), __funnelshift_r(w[5], w[6], hs), __funnelshift_r(w[6], w[7], hs)); break;
-            }
-            *reinterpret_cast<int4*>(ring_slot + 16 * v) = o;
-          }
-          // samples of this chunk beyond the last whole vector (at most 15, at the end of the utterance): plain loads
-          {
-            const int lo = max(c * kChunkSamples, 8 * nvec), hi = min((c + 1) * kChunkSamples, n);
-            int16_t* dst = reinterpret_cast<int16_t*>(ring_slot);
-            for (int i = lo + lane; i < hi; i += 32) dst[i - c * kChunkSamples] = src[i];
-          }
-          __syncwarp();
-          if (lane == 0) {
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full32) : "memory");
-            if (c + kStageSlots < pieces) issue_piece(c + kStageSlots);      // piece c has been consumed: its slot is free
-          }
-          next_slot();
+                       ::"r"(dst32), "l"(gsrc), "r"(bytes), "r"(full32) : "memory");
+        } else {
+          asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(full32) : "memory");
         }
-        // pieces beyond the last chunk's needs (none by construction) would leave a phase open: drain to be safe
-#pragma unroll 1
-        while (waited < pieces) {
-          const int ss = waited & (kStageSlots - 1);
-          mbar_wait(&bar_stage[ss], (stage_phase >> ss) & 1u);
-          stage_phase ^= 1u << ss;
-          ++waited;
-        }
+        next_slot();
       }
       ++useq;
       if (done) break;
@@ -589,8 +511,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
     if (!kBatchMode && twid >= nrec) return;
     double* cand = reinterpret_cast<double*>(smem + L.scratch + (size_t)twid * 256);
 
-    // window coefficients of the hop-128 / length-256 chain: a lane owns samples 8*(lane&15) .. +8 of
-    // every hop block; c = 0 is the first half of a frame, c = 1 the second
+    // Window coefficients of the hop-128 / length-256 chain.  The chain reads 16-byte ALIGNED vectors whatever the
+    // utterance's address: with the trimmed segment starting m = 0..7 samples above a 16-byte boundary, a lane owns
+    // segment samples 8*(lane&15) - m .. +8 of every hop block and its coefficients are the window shifted by m
+    // (c = 0: first half of a frame, c = 1: the second; the m samples in front of a block's first frame get weight 0
+    // there -- they are the LAST m samples of the frame two blocks back, added by a small correction pass).  One code
+    // path and one LDG.128 per block for every alignment; the registers are loaded per utterance (tail_chain below).
+
+#ifdef DSP_EXP_HOIST
     float cw[2][8], cw2[2][8];
     if constexpr (kChain) {
 #pragma unroll
@@ -598,7 +526,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
 #pragma unroll
         for (int q8 = 0; q8 < 8; ++q8) { const float w = s_win[c * 128 + 8 * (lane & 15) + q8]; cw[c][q8] = w; cw2[c][q8] = w * w; }
     }
-
+#endif
     long long tp[5] = {0, 0, 0, 0, 0}, tprev = clock64();
     auto tick = [&](int i) { if (a.prof) { const long long t = clock64(); tp[i] += t - tprev; tprev = t; } };
     for (int it = 0;; ++it) {
@@ -825,10 +753,30 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
           const int last = max(nfr, 0);                      // last hop block this chain may touch
           const bool hi8 = (sub & 8) != 0, writer = (sub & 7) == 0;
           // block i at ptr[16 * i]; an idle chain re-reads the first block of the segment and stores nothing
-          const int4* ptr = reinterpret_cast<const int4*>(x + start + 8 * sub + (nfr > 0 ? fa : 0) * 128);
+#ifdef DSP_EXP_MAL0
+          const int mal = 0;
+#else
+          const int mal = (int)((reinterpret_cast<uintptr_t>(x + start) & 15) >> 1);       // = the utterance's shift: start is a multiple of 128
+#endif
+#ifndef DSP_EXP_HOIST
+          float cw[2][8], cw2[2][8];
+#endif
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int q8 = 0; q8 < 8; ++q8) {
+#ifdef DSP_EXP_HOIST
+              break;
+#endif
+              const int pos = c * 128 + 8 * sub + q8 - mal;
+              const float w = s_win[max(pos, 0)];
+              cw[c][q8] = pos >= 0 ? w : 0.f; cw2[c][q8] = pos >= 0 ? w * w : 0.f;
+            }
+          const int4* ptr = reinterpret_cast<const int4*>(x + start - mal + 8 * sub + (nfr > 0 ? fa : 0) * 128);
           const float c1f = -(8388608.f + 32768.f) - (float)thr;
           const float scale = hi8 ? (float)sc_m : (float)sc_e;
           float* dst = (hi8 ? s_fm : s_fe) + zbase + fa - 1;   // frame fa + i - 1 at dst[i]
+          float* dummy = reinterpret_cast<float*>(cand);
 #if DSP_CHAIN_PACKED
           // Packed fp32x2 arithmetic (sm_100 FFMA2 / FADD2 / FMUL2): the two samples of a 32-bit word travel as one
           // 64-bit register pair from the conversion on -- (x + c1f) - phi, d * d and the four multiply-adds of a word are
@@ -864,7 +812,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
             vv += __shfl_xor_sync(0xffffffffu, vv, 4);
             vv += __shfl_xor_sync(0xffffffffu, vv, 2);
             vv += __shfl_xor_sync(0xffffffffu, vv, 1);
-            if (writer && i >= 1 && i <= nfr) dst[i] = vv * scale;
+            // one unconditional store (a branch here makes the compiler give up the straight-line schedule of the loop:
+            // +50 % in this phase): lanes with nothing to write hit the warp's scratch word
+            *((writer && i >= 1 && i <= nfr) ? dst + i : dummy) = vv * scale;
           };
 #else
           float ce = 0.f, cm = 0.f;                          // first-half partials of the previous block
@@ -890,7 +840,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
             vv += __shfl_xor_sync(0xffffffffu, vv, 4);
             vv += __shfl_xor_sync(0xffffffffu, vv, 2);
             vv += __shfl_xor_sync(0xffffffffu, vv, 1);
-            if (writer && i >= 1 && i <= nfr) dst[i] = vv * scale;
+            // one unconditional store (a branch here makes the compiler give up the straight-line schedule of the loop:
+            // +50 % in this phase): lanes with nothing to write hit the warp's scratch word
+            *((writer && i >= 1 && i <= nfr) ? dst + i : dummy) = vv * scale;
           };
 #endif
           // kInFlight hop blocks in flight per lane (the tail warps run this phase together and wait on L2 / HBM together:
@@ -900,37 +852,56 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
           // its last use -- streaming loads keep the dead lines from displacing the ring's traffic (-4 % DRAM reads)
           constexpr int kInFlight = 6;
           int4 q[kInFlight];
-#pragma unroll
-          // The utterance may start anywhere (packed CSR): hop block i of the lane sits at ptr + 16 i, a 16-byte vector
-          // that is 16-, 8- or only 2-byte aligned in global memory -- one alignment per utterance, i.e. per warp.
-          // 16: one LDG.128; 8 (every other utterance of a packed batch of 1 s clips): two LDG.64; anything else: the
-          // two aligned vectors around it and a funnel shift per word (the loads hit L1 for the half the neighbour
-          // lane also reads).
-          const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(ptr) & 15u);
-          const uint32_t mws = mis >> 2, mhs = (mis & 2u) ? 16u : 0u;
-          auto load_block = [&](int bi) -> int4 {
-            const int4* p = ptr + 16 * bi;
-            if (mis == 0) return __ldcs(p);
-            if (mis == 8) {
-              const int2 lo = __ldcs(reinterpret_cast<const int2*>(p)), hi = __ldcs(reinterpret_cast<const int2*>(p) + 1);
-              return make_int4(lo.x, lo.y, hi.x, hi.y);
-            }
-            const int4* pa = reinterpret_cast<const int4*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)15);
-            const int4 q0 = __ldg(pa), q1 = __ldg(pa + 1);
-            const uint32_t w[8] = {(uint32_t)q0.x, (uint32_t)q0.y, (uint32_t)q0.z, (uint32_t)q0.w, (uint32_t)q1.x, (uint32_t)q1.y, (uint32_t)q1.z, (uint32_t)q1.w};
-            switch (mws) {
-              case 0: return make_int4(__funnelshift_r(w[0], w[1], mhs), __funnelshift_r(w[1], w[2], mhs), __funnelshift_r(w[2], w[3], mhs), __funnelshift_r(w[3], w[4], mhs));
-              case 1: return make_int4(__funnelshift_r(w[1], w[2], mhs), __funnelshift_r(w[2], w[3], mhs), __funnelshift_r(w[3], w[4], mhs), __funnelshift_r(w[4], w[5], mhs));
-              case 2: return make_int4(__funnelshift_r(w[2], w[3], mhs), __funnelshift_r(w[3], w[4], mhs), __funnelshift_r(w[4], w[5], mhs), __funnelshift_r(w[5], w[6], mhs));
-              default: return make_int4(__funnelshift_r(w[3], w[4], mhs), __funnelshift_r(w[4], w[5], mhs), __funnelshift_r(w[5], w[6], mhs), __funnelshift_r(w[6], w[7], mhs));
-            }
-          };
+          auto load_block = [&](int bi) -> int4 { return __ldcs(ptr + 16 * bi); };
 #pragma unroll
           for (int j = 0; j < kInFlight; ++j) q[j] = load_block(min(j, last));
 #pragma unroll 1
           for (int i = 0; i <= per; i += kInFlight) {       // uniform trip count: the shuffles are warp-wide
 #pragma unroll
             for (int j = 0; j < kInFlight; ++j) { step(q[j], i + j); q[j] = load_block(min(i + j + kInFlight, last)); }
+          }
+          if (mal) {
+            // the last mal samples of every chained frame t: segment samples 128 (t + 2) - mal .. 128 (t + 2), window
+            // positions 256 - mal .. 256 = the first mal samples of aligned block t + 2 (one lane per frame, two frames
+            // in flight per lane; the chain has just pulled these lines through L2).  The vector of the very last block
+            // may reach past the utterance: that one is read sample by sample.
+            __syncwarp();
+            const int16_t* xs = x + start - mal;
+            const int vec_frames = min(f2_chain, (n - start + mal - 8) / 128 - 1);      // frames whose whole vector lies inside the utterance
+            float wc[7];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) wc[j] = j < mal ? s_win[256 - mal + j] : 0.f;
+            auto corr = [&](const int4& q, int t) {
+              const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+              float ce = 0.f, cm = 0.f;
+#pragma unroll
+              for (int j = 0; j < 7; ++j) {
+                const int k = (j & 1) ? ((int)w[j >> 1] >> 16) : sext16(w[j >> 1]);
+                const float wd = wc[j] * ((float)(k - thr) - phi);
+                ce = fmaf(wd, wd, ce); cm += fabsf(wd);
+              }
+              s_fe[zbase + t] += ce * (float)sc_e;
+              s_fm[zbase + t] += cm * (float)sc_m;
+            };
+#pragma unroll 1
+            for (int t = lane; t < f2_chain; t += 64) {
+              const int t2 = t + 32;
+              const bool v1 = t < vec_frames, h2 = t2 < f2_chain, v2 = t2 < vec_frames;
+              int4 q1 = make_int4(0, 0, 0, 0), q2 = q1;
+              if (v1) q1 = __ldg(reinterpret_cast<const int4*>(xs + 128 * (t + 2)));
+              if (v2) q2 = __ldg(reinterpret_cast<const int4*>(xs + 128 * (t2 + 2)));
+              auto scalar = [&](int tt) {
+                const int16_t* pp = xs + 128 * (tt + 2);
+                uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int j = 0; j < 7; ++j) if (j < mal) w[j >> 1] |= (uint32_t)(unsigned short)__ldg(pp + j) << (16 * (j & 1));
+                return make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]);
+              };
+              if (!v1) q1 = scalar(t);
+              if (h2 && !v2) q2 = scalar(t2);
+              corr(q1, t);
+              if (h2) corr(q2, t2);
+            }
           }
         }
       }
@@ -1022,7 +993,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       if (a.out.stats && f2 > 0) {
         float* stats = a.out.stats + (int64_t)u * kStats;
         if (f2 <= 32 * 6) tail_stats_regs<6>(s_fe + zbase, s_fm + zbase, r_zf + zbase, f2, stats);
-        else if (f2 <= 32 * 11) tail_stats_regs<11>(s_fe + zbase, s_fm + zbase, r_zf + zbase, f2, stats);
+        else if (f2 <= 32 * 13) tail_stats_regs<13>(s_fe + zbase, s_fm + zbase, r_zf + zbase, f2, stats);
         else {
           float st[5];
           warp_stats([&](int i) { return s_fe[zbase + i]; }, f2, st);
@@ -1081,30 +1052,31 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       else bar_arrive(kBarRecFull + rec_id, kRecBarThreads);
       if (++rec_id == nrec) { rec_id = 0; ++rec_lap; }
     };
-    if (dsc.y < 0) {
-      // misaligned start: hand the utterance to the float64 replay, keep the pipeline's sequence numbers
-      rec_acquire();
-      if (stid == 0) { const int s = atomicAdd(a.flag_count, 1); a.flag_list[s] = u; r_int[0] = u; r_int[1] = 0; r_int[2] = 0; r_int[3] = 0;
-        r_int[4] = 0; r_int[5] = 0; r_int[6] = 0; double* rd = reinterpret_cast<double*>(rec + 64); rd[0] = 0.0; rd[1] = 1.0; rd[2] = 0.0; }
-      __syncwarp();
-      if (lane == 0 && (edges || swid == 0)) mbar_arrive(&bar_empty[cslot]);
-      __syncwarp();
-      rec_publish();
-      if (++cslot == R) { cslot = 0; ++clap; }
-      ++useq;
-      continue;
-    }
-    const int n = dsc.y;
-    const int nchunks = n > 0 ? (n + kChunkSamples - 1) / kChunkSamples : 1;
-    const int ng = (n + kGroup - 1) / kGroup;
+    // The ring holds the 16-byte aligned stream around the utterance: sample i sits at stream position i + sh
+    // (sh = 0..7, per utterance).  Groups, chunks and bit strings are indexed by STREAM position; a frame that starts at
+    // sample p is the run of whole groups from p / 64 minus the first sh samples of its first group plus the first sh
+    // samples of the group behind its last one -- the "head" sums / head bits every group records next to its totals.
+#ifdef DSP_EXP_NOSHIFT
+    const int n = dsc.y & 0xfffff, sh = 0;
+#else
+    const int n = dsc.y & 0xfffff, sh = dsc.y >> 20;
+#endif
+    const int np = n + sh;
+    const int nchunks = np > 0 ? (np + kChunkSamples - 1) / kChunkSamples : 1;
+    const int ng = (np + kGroup - 1) / kGroup;
     unsigned long long* gsum = s_gsum + (size_t)par * a.cap_groups;
+    unsigned long long* head = s_head + (size_t)par * a.cap_groups;
     auto chunk_ptr = [&](int c) -> const unsigned char* {
       int s = cslot + c; if (s >= R) s -= R;
       return s_ring + (size_t)s * kChunkBytes;
     };
-    auto sample_at = [&](int i) -> int {
+    auto at_pos = [&](int i) -> int {       // sample at stream position i
       return (int)reinterpret_cast<const int16_t*>(chunk_ptr(i >> 11))[i & (kChunkSamples - 1)];
     };
+    // head masks: word w of a group's first vector keeps its samples below sh
+    uint32_t hmask[4];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) hmask[w] = (2 * w + 1 < sh) ? 0xffffffffu : ((2 * w < sh) ? 0x0000ffffu : 0u);
 
     // =========================== pass A: group sums, min, max =========================
     int S = 0;
@@ -1116,9 +1088,32 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       if (c) mbar_wait(&bar_full[s], (uint32_t)(lp & 1));
       const int g = kGroupsPerChunk * c + lane;
       const int base = g * kGroup;
-      if (base + kGroup <= n) {
-        const unsigned char* gp = s_ring + (size_t)s * kChunkBytes + lane * (2 * kGroup);
-        int hh = 0, hl = 0, sh = 0;
+      if (base + kGroup <= np) {
+        unsigned char* gp = s_ring + (size_t)s * kChunkBytes + lane * (2 * kGroup);
+        if (sh) {
+          if (g == 0) {
+            // the sh samples in front of the utterance belong to its neighbour: overwrite them with copies of sample 0
+            // (min / max unaffected, the sum corrected below, the head sums / bits of group 0 consistent with it)
+            volatile int16_t* fp = reinterpret_cast<volatile int16_t*>(gp);
+            const int16_t k0 = fp[sh];
+            for (int i = 0; i < sh; ++i) fp[i] = k0;
+            S -= sh * (int)k0;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slot is refilled by a bulk copy later
+          }
+          asm volatile("" ::: "memory");
+          // head of the group: sums over its first sh samples (one masked vector)
+          const int4 q = *reinterpret_cast<const int4*>(gp);
+          const uint32_t x0 = (uint32_t)q.x & hmask[0], x1 = (uint32_t)q.y & hmask[1], x2 = (uint32_t)q.z & hmask[2], x3 = (uint32_t)q.w & hmask[3];
+          const uint32_t h0 = __byte_perm(x0, x1, 0x7531), l0 = __byte_perm(x0, x1, 0x6420);
+          const uint32_t h1 = __byte_perm(x2, x3, 0x7531), l1 = __byte_perm(x2, x3, 0x6420);
+          const int hhh = dp4a_ss((int)h1, (int)h1, dp4a_ss((int)h0, (int)h0, 0));
+          const int hhl = dp4a_su((int)h1, l1, dp4a_su((int)h0, l0, 0));
+          const uint32_t hll = dp4a_uu(l1, l1, dp4a_uu(l0, l0, 0u));
+          const int hs1 = 256 * dp4a_ss((int)h1, 0x01010101, dp4a_ss((int)h0, 0x01010101, 0)) + (int)dp4a_uu(l1, 0x01010101u, dp4a_uu(l0, 0x01010101u, 0u));
+          const long long hs2 = (long long)hhh * 65536 + (long long)hhl * 512 + (long long)hll;
+          head[g] = ((unsigned long long)hs2 << 24) | (unsigned long long)((uint32_t)hs1 & 0xffffffu);
+        }
+        int hh = 0, hl = 0, sumh = 0;
         uint32_t ll = 0, sl = 0;
         // fully unrolled on purpose: a compact 2-unit loop (L0-resident, measured) made pass A 8 % faster and the
         // kernel no faster -- the phases share the SM's issue slots, see DESIGN.md
@@ -1130,21 +1125,27 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
           hh = dp4a_ss((int)h0, (int)h0, hh); hh = dp4a_ss((int)h1, (int)h1, hh);
           hl = dp4a_su((int)h0, l0, hl);      hl = dp4a_su((int)h1, l1, hl);
           ll = dp4a_uu(l0, l0, ll);           ll = dp4a_uu(l1, l1, ll);
-          sh = dp4a_ss((int)h0, 0x01010101, sh); sh = dp4a_ss((int)h1, 0x01010101, sh);
+          sumh = dp4a_ss((int)h0, 0x01010101, sumh); sumh = dp4a_ss((int)h1, 0x01010101, sumh);
           sl = dp4a_uu(l0, 0x01010101u, sl);  sl = dp4a_uu(l1, 0x01010101u, sl);
           mn2 = __vimin3_s16x2(mn2, (uint32_t)q.x, (uint32_t)q.y); mn2 = __vimin3_s16x2(mn2, (uint32_t)q.z, (uint32_t)q.w);
           mx2 = __vimax3_s16x2(mx2, (uint32_t)q.x, (uint32_t)q.y); mx2 = __vimax3_s16x2(mx2, (uint32_t)q.z, (uint32_t)q.w);
         }
-        const int s1 = 256 * sh + (int)sl;
+        const int s1 = 256 * sumh + (int)sl;
         const long long s2 = (long long)hh * 65536 + (long long)hl * 512 + (long long)ll;
         S += s1;
         gsum[g] = ((unsigned long long)s2 << 24) | (unsigned long long)((uint32_t)s1 & 0xffffffu);
-      } else if (base < n) {
-        int s1 = 0; long long s2 = 0;
+      } else if (base < np) {
+        // the partial last group, one sample at a time (valid stream positions only)
+        int s1 = 0, h1s = 0; long long s2 = 0, h2s = 0;
+        const int lo = max(base, sh);
 #pragma unroll 1
-        for (int i = base; i < n; ++i) { const int k = sample_at(i); s1 += k; s2 += (long long)k * k; mn = min(mn, k); mx = max(mx, k); }
+        for (int i = lo; i < np; ++i) {
+          const int k = at_pos(i); s1 += k; s2 += (long long)k * k; mn = min(mn, k); mx = max(mx, k);
+          if (i < base + sh) { h1s += k; h2s += (long long)k * k; }
+        }
         S += s1;
         gsum[g] = ((unsigned long long)s2 << 24) | (unsigned long long)((uint32_t)s1 & 0xffffffu);
+        head[g] = ((unsigned long long)h2s << 24) | (unsigned long long)((uint32_t)h1s & 0xffffffu);
       }
     }
     mn = min(mn, min(sext16(mn2), (int)mn2 >> 16));
@@ -1192,7 +1193,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       for (int c = swid; c < nchunks; c += kStreamWarps) {
         int s = cslot + c; if (s >= R) s -= R;
         const int g = kGroupsPerChunk * c + lane;
-        if (g * kGroup + kGroup <= n) {
+        if (g * kGroup + kGroup <= np) {
           const unsigned char* gp = s_ring + (size_t)s * kChunkBytes + lane * (2 * kGroup);
           const int rot = lane & 7;
           // r = the two bits of a word at positions 0 and 16; r << c drops them into bit c of both planes at once, so a
@@ -1215,7 +1216,14 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
           const uint32_t ep = __byte_perm(acc0, acc1, 0x5410), op = __byte_perm(acc0, acc1, 0x7632);
           const uint32_t E = __funnelshift_l(ep, ep, 4 * rot), O = __funnelshift_l(op, op, 4 * rot);
           const uint32_t x1 = E ^ O, x2 = (O ^ (E >> 1)) & 0x7fffffffu;
-          s_meta[g] = (uint32_t)(__popc(x1) + __popc(x2)) | ((E & 1u) << 8) | ((O & 1u) << 9) | ((E >> 31) << 10) | ((O >> 31) << 11);
+          // group record: crossings inside the group | samples 0,2,4,6,8 | samples 1,3,5,7 | sample 62 | sample 63
+          s_meta[g] = (uint32_t)(__popc(x1) + __popc(x2)) | ((E & 0x1fu) << kMetaE) | ((O & 0xfu) << kMetaO) | ((E >> 31) << kMetaP) | ((O >> 31) << kMetaL);
+        } else if (sh && g * kGroup < np) {
+          // partial last group of a shifted stream: the last whole frame may end inside its head -- first 9 bits only
+          uint32_t m = 0;
+          for (int i = 0; i < 9 && g * kGroup + i < np; ++i)
+            if (at_pos(g * kGroup + i) - thr >= 0) m |= 1u << ((i & 1) ? kMetaO + (i >> 1) : kMetaE + (i >> 1));
+          s_meta[g] = m;
         }
         // this chunk's last read: hand the slot back now, not after the warp's other chunks (the producer refills
         // the ring in order, and the next utterance's last chunks are the ones pass A ends up waiting for)
@@ -1229,7 +1237,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       const int g = kGroupsPerChunk * c + lane;
       const int base = g * kGroup;
       uint32_t b0 = 0, b1 = 0;
-      if (base + kGroup <= n) {
+      if (base + kGroup <= np) {
         const unsigned char* gp = s_ring + (size_t)s * kChunkBytes + lane * (2 * kGroup);
         const int rot = lane & 7;
         uint32_t nlo = 0, nhi = 0;         // "below the mean" bits, MSB-first, in processing order
@@ -1267,17 +1275,22 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
         const int sh = 8 * rot;
         const unsigned long long z = sh ? ((y << sh) | (y >> (64 - sh))) : y;
         b0 = ~(uint32_t)z; b1 = ~(uint32_t)(z >> 32);
-      } else if (base < n) {
+      } else if (base < np) {
 #pragma unroll 1
-        for (int i = 0; i < kGroup && base + i < n; ++i) {
-          const uint32_t bit = (sample_at(base + i) - thr >= 0);
+        for (int i = 0; i < kGroup && base + i < np; ++i) {
+          const uint32_t bit = (at_pos(base + i) - thr >= 0);
           if (i < 32) b0 |= bit << i; else b1 |= bit << (i - 32);
         }
       }
-      if (base < n) {
+      if (base < np) {
         s_bits[2 * g] = b0; s_bits[2 * g + 1] = b1;
-        const uint32_t x0 = b0 ^ __funnelshift_r(b0, b1, 1), x1 = (b1 ^ (b1 >> 1)) & 0x7fffffffu;
-        s_meta[g] = (uint32_t)(__popc(x0) + __popc(x1)) | ((b0 & 3u) << 8) | ((b1 >> 30) << 10);
+        if (!edges) {      // whole-group frames read the group records (same layout as the fast form writes)
+          const uint32_t x0 = b0 ^ __funnelshift_r(b0, b1, 1), x1 = (b1 ^ (b1 >> 1)) & 0x7fffffffu;
+          uint32_t m = (uint32_t)(__popc(x0) + __popc(x1)) | (((b1 >> 30) & 1u) << kMetaP) | ((b1 >> 31) << kMetaL);
+#pragma unroll
+          for (int i = 0; i < 9; ++i) m |= ((b0 >> i) & 1u) << ((i & 1) ? kMetaO + (i >> 1) : kMetaE + (i >> 1));
+          s_meta[g] = m;
+        }
       }
     }
     if (stid < 4) s_bits[2 * ng + stid] = 0;
@@ -1309,52 +1322,76 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       const long long thr2 = (long long)thr * thr;
       const int nfull = n >= fl ? (n - fl) / fs + 1 : 0;        // frames without zero padding
       const int fmax = max(nfull, f2full);
+      // shifted stream (sh = 1..7): head corrections of a whole-group frame.  Sign changes at pairs (i, i+1):
+      // even i pairs are bits of E ^ O, odd i pairs bits of O ^ (E >> 1) (E / O = the even / odd samples of the record).
+      // Leaving the frame in front: the sh pairs i < sh of its first group; entering behind: the pair across the last
+      // group boundary and the sh - 1 pairs i < sh - 1 of the next group.
+      const uint32_t mA1 = (1u << ((sh + 1) >> 1)) - 1u, mA2 = (1u << (sh >> 1)) - 1u;
+      const uint32_t mB1 = mA2, mB2 = sh ? (1u << ((sh - 1) >> 1)) - 1u : 0u;
+      auto head_changes = [](uint32_t m, uint32_t m1, uint32_t m2) {
+        const uint32_t E = (m >> kMetaE) & 0x1fu, O = (m >> kMetaO) & 0xfu;
+        return __popc((E ^ O) & m1) + __popc((O ^ (E >> 1)) & m2);
+      };
+      auto unpack1 = [](unsigned long long pk) { return ((int)((uint32_t)pk << 8)) >> 8; };
 #pragma unroll 1
       for (int f = stid; f < fmax; f += kStreamThreads) {
         const int p = f * fs;
         int zc = 0;
-        uint32_t m_first = 0, m_last = 0;
+        int hb0 = 0, hb1 = 0, hbp = 0, hbl = 0;     // sign bits of the frame's samples 0, 1, fl-2, fl-1
         if (f < nfull) {
-          const int q = p + fl;
           long long s1, s2;
           if (!edges) {
             // whole groups only: sum k, sum k^2, crossings from the per-group records
             const int g0 = p / kGroup, gpf = fl / kGroup;
             int k1 = 0; long long k2 = 0;
-            uint32_t prev = 0;
+            uint32_t prev = 0, m_first = 0, m_last = 0;
 #pragma unroll 2
             for (int j = 0; j < gpf; ++j) {
               const unsigned long long pk = gsum[g0 + j];
               const uint32_t m = s_meta[g0 + j];
               k2 += (long long)(pk >> 24);
-              k1 += ((int)((uint32_t)pk << 8)) >> 8;
-              zc += (int)(m & 0x7fu) + (int)(((m >> 8) ^ prev) & (j ? 1u : 0u));
-              prev = m >> 11;
+              k1 += unpack1(pk);
+              zc += (int)(m & 0x7fu) + (int)(((m >> kMetaE) ^ prev) & (j ? 1u : 0u));
+              prev = m >> kMetaL;
               if (j == 0) m_first = m;
               m_last = m;
+            }
+            if (sh) {
+              const unsigned long long ha = head[g0], hb = head[g0 + gpf];
+              const uint32_t mb = s_meta[g0 + gpf];
+              k1 += unpack1(hb) - unpack1(ha);
+              k2 += (long long)(hb >> 24) - (long long)(ha >> 24);
+              zc += (int)(((mb >> kMetaE) ^ (m_last >> kMetaL)) & 1u) + head_changes(mb, mB1, mB2) - head_changes(m_first, mA1, mA2);
+              hb0 = (m_first >> meta_bit(sh)) & 1; hb1 = (m_first >> meta_bit(sh + 1)) & 1;
+              hbl = (mb >> meta_bit(sh - 1)) & 1;
+              hbp = sh >= 2 ? (mb >> meta_bit(sh - 2)) & 1 : (m_last >> kMetaL) & 1;
+            } else {
+              hb0 = (m_first >> kMetaE) & 1; hb1 = (m_first >> kMetaO) & 1; hbp = (m_last >> kMetaP) & 1; hbl = (m_last >> kMetaL) & 1;
             }
             s1 = (long long)(k1 - fl * thr);
             s2 = k2 - 2ll * thr * (long long)k1 + (long long)fl * thr2;
           } else {
-            long long k1 = 0, k2 = 0;           // sum k, sum k^2 over the frame
-            const int ga = (p + kGroup - 1) / kGroup, gb = q / kGroup;
+            long long k1 = 0, k2 = 0;           // sum k, sum k^2 over the frame (stream positions ps .. qs)
+            const int ps = p + sh, qs = ps + fl;
+            const int ga = (ps + kGroup - 1) / kGroup, gb = qs / kGroup;
             auto direct = [&](int i0, int i1) {
 #pragma unroll 1
-              for (int i = i0; i < i1; ++i) { const int k = sample_at(i); k1 += k; k2 += (long long)k * k; }
+              for (int i = i0; i < i1; ++i) { const int k = at_pos(i); k1 += k; k2 += (long long)k * k; }
             };
-            if (ga > gb) direct(p, q);
+            if (ga > gb) direct(ps, qs);
             else {
               for (int g = ga; g < gb; ++g) {
                 const unsigned long long pk = gsum[g];
                 k2 += (long long)(pk >> 24);
-                k1 += (long long)(((int)((uint32_t)pk << 8)) >> 8);
+                k1 += (long long)unpack1(pk);
               }
-              direct(p, ga * kGroup);
-              direct(gb * kGroup, q);
+              direct(ps, ga * kGroup);
+              direct(gb * kGroup, qs);
             }
             s1 = k1 - (long long)fl * thr;
             s2 = k2 - 2ll * thr * k1 + (long long)fl * thr2;
-            zc = count_changes(s_bits, p, q);
+            zc = count_changes(s_bits, ps, qs);
+            hb0 = bit_at(s_bits, ps); hb1 = bit_at(s_bits, ps + 1); hbl = bit_at(s_bits, qs - 1); hbp = bit_at(s_bits, qs - 2);
           }
           if (f < f1) {
             // exact integer sums of d = k - thr, then sum (d - phi)^2 in three roundings
@@ -1372,16 +1409,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
           int zf;
           if (f < nfull && !(hann && fl <= 2)) {
             zf = zc;
-            if (hann) {
-              int s0, s1b, sp, sl;
-              if (!edges) { s0 = (m_first >> 8) & 1; s1b = (m_first >> 9) & 1; sp = (m_last >> 10) & 1; sl = (m_last >> 11) & 1; }
-              else { s0 = bit_at(s_bits, p); s1b = bit_at(s_bits, p + 1); sl = bit_at(s_bits, p + fl - 1); sp = bit_at(s_bits, p + fl - 2); }
-              zf += (s1b - (s0 ^ s1b)) + (sp - (sp ^ sl));
-            }
+            if (hann) zf += (hb1 - (hb0 ^ hb1)) + (hbp - (hbp ^ hbl));
           } else if (fastb) {
             zf = 0xffff;                     // zero-padded frame, no bit string in this mode: the tail counts it from L2
           } else {
-            zf = frame_zcr(s_bits, p, valid, fl, hann);
+            zf = frame_zcr(s_bits, p + sh, valid, fl, hann);
           }
           r_zf[f] = (unsigned short)zf;
         }
@@ -1432,16 +1464,16 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
 // ---------------------------------------------------------------------------------------
 bool pipe_kernel_plan(int64_t max_len, int cap_frames, int fl, size_t smem_limit, PipePlan* plan) {
   if (max_len > 65535 || cap_frames > 65535 || fl > 65535) return false;      // 16-bit crossing counts, int32 sums
-  const int chunks = (int)std::max<int64_t>((max_len + kChunkSamples - 1) / kChunkSamples, 1);
+  const int chunks = (int)std::max<int64_t>((max_len + 7 + kChunkSamples - 1) / kChunkSamples, 1);   // + the <= 7 samples below a misaligned start
   const int capG = chunks * kGroupsPerChunk;
   if (kBatchMode) {
-    // two batches of records; the ring keeps the utterance in flight plus at least a quarter of the next one
+    // two batches of records; the ring keeps the utterance in flight plus at least two chunks of the next one
     const int nrec = 2 * kBatch;
     const PipeLayout fixed = make_pipe_layout(0, capG, cap_frames, fl, nrec);
     const long long room = (long long)smem_limit - fixed.total - 1024;
     int R = (int)(room / (kChunkBytes + 16));
     if (R > kMaxRingSlots) R = kMaxRingSlots;
-    if (R < chunks + std::max(2, chunks / 4)) return false;
+    if (R < chunks + 2) return false;     // (a quarter of the next utterance in flight is typical: 1 s clips get 39 slots for 22 chunks)
     plan->ring_slots = R; plan->n_rec = nrec; plan->cap_groups = capG;
     plan->smem = (size_t)make_pipe_layout(R, capG, cap_frames, fl, nrec).total;
     return true;

@@ -174,11 +174,15 @@ def test_misaligned_and_odd_offsets(ctx):
     for i in range(len(utts)):
         j = len(utts) - 1 - i
         assert (ra.start[i], ra.end[i], ra.n_frames[i]) == (rb.start[j], rb.end[j], rb.n_frames[j])
-        for x, y in zip(ra.frames(i), rb.frames(j)):
-            assert np.array_equal(x, y)
+        (ea, ma, za), (eb, mb, zb) = ra.frames(i), rb.frames(j)
+        assert np.array_equal(za, zb)
+        # fp32 windowed sums: the window pass reads 16-byte aligned vectors, so the association of its partial sums
+        # follows the utterance's address modulo 16 bytes -- a few ulp between placements, never an integer result
+        assert np.allclose(ea, eb, rtol=2e-6, atol=0) and np.allclose(ma, mb, rtol=2e-6, atol=0)
         for x, y in zip(ra.epd_lists(i), rb.epd_lists(j)):
             assert np.array_equal(x, y)
-        assert np.array_equal(ra.stats[i], rb.stats[j])
+        assert np.array_equal(ra.stats[i][10:], rb.stats[j][10:])
+        assert np.allclose(ra.stats[i][:10], rb.stats[j][:10], rtol=0, atol=2e-6 * float(np.abs(ra.stats[i][:10]).max()))
 
 
 def test_padded_layout_with_explicit_lengths_equals_packed(ctx):
@@ -299,11 +303,13 @@ def test_batch_handoff_sizes(ctx, n_utts):
 
 
 @pytest.mark.parametrize("lead", [0, 1, 2, 3, 4, 5, 6, 7])
-def test_pipelined_kernel_realigns_misaligned_utterances(ctx, lead):
+def test_pipelined_kernel_takes_misaligned_utterances(ctx, lead):
     """A packed (CSR) batch whose utterances start at ARBITRARY sample offsets (odd lengths, `lead` samples in front of
-    the first one): the pipelined kernel's producer realigns them on chip -- no utterance is handed to the float64
-    replay because of its address, and every result equals the oracle's.  Also without the pcm_variant
-    knob: the automatic choice for 256 / 128 is the pipelined kernel whatever the alignment."""
+    the first one): the pipelined kernel streams each utterance from the 16-byte boundary below its start and carries
+    the 0..7-sample offset through its group sums -- no utterance is handed to the float64 replay because of its address
+    (the replayed set equals that of the 16-byte aligned packing, i.e. the degenerate one-frame
+    utterances whose only frame sits ON its own thresholds), and every result equals the oracle's.  Also without the
+    pcm_variant knob: the automatic choice for 256 / 128 is the pipelined kernel whatever the alignment."""
     from dsp_audioreclabs_b200 import batch
     from oracle import frontend_oracle as fo, synth
     lens = [9001, 12347, 7777, 15003, 8192, 1000, 5000, 30001, 44100, 20011, 333, 25000, 26001, 40000, 12000, 13001, 2049, 2047,
@@ -311,6 +317,14 @@ def test_pipelined_kernel_realigns_misaligned_utterances(ctx, lead):
     utts = [synth.utterance_pcm(70 + i, n, seed0=3) for i, n in enumerate(lens)] * 2
     samples, off = pack(utts)
     refs = fo.frontend_batch(samples, off, 256, 128, "hamming")
+    s_al, o_al, l_al = batch.pack_aligned(utts)
+    ctx.set_tuning("pcm_variant", PIPE)
+    try:
+        aligned = batch.frontend_batch(s_al, o_al, 256, 128, "hamming", lengths=l_al, ctx=ctx)
+    finally:
+        ctx.set_tuning("pcm_variant", -1)
+    replayed_when_aligned = aligned.status >= 0x100
+    assert all(len(u) < 2 * 256 for u, r in zip(utts, replayed_when_aligned) if r)
     samples = np.concatenate([np.full(lead, 12345, np.int16), samples, np.full(9, -4321, np.int16)])
     off = off + lead
     for forced in (True, False):
@@ -320,7 +334,7 @@ def test_pipelined_kernel_realigns_misaligned_utterances(ctx, lead):
             res = batch.frontend_batch(samples, off, 256, 128, "hamming", emit_epd_lists=True, ctx=ctx)
         finally:
             ctx.set_tuning("pcm_variant", -1)
-        assert int((res.status >= 0x100).sum()) == 0             # nothing replayed: not for alignment, not for margins
+        assert np.array_equal(res.status >= 0x100, replayed_when_aligned)      # nothing replayed because of its address
         for b, r in enumerate(refs):
             if r is None:                                         # the reference raises (empty utterance): status says so
                 assert (int(res.status[b]) & 0xff) != 0, (lead, b)

@@ -61,16 +61,33 @@ def test_invariants_determinism_permutation(ctx, big, window):
     b = run(devapi, ctx, dev, samples, offsets, window)
     for name in ("start", "end", "n_frames", "status", "energy", "magnitude", "zcr", "stats"):
         assert torch.equal(getattr(a, name), getattr(b, name)), name
-    # permutation: results do not depend on which CTA / in which order an utterance is processed
-    perm = torch.randperm(N_UTTS, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
-    shuffled = torch.zeros_like(samples)
-    shuffled[: N_UTTS * L] = samples[: N_UTTS * L].view(N_UTTS, L)[perm].reshape(-1)
-    c = run(devapi, ctx, dev, shuffled, offsets, window)
-    assert torch.equal(c.start, a.start[perm]) and torch.equal(c.end, a.end[perm])
-    assert torch.equal(c.stats, a.stats[perm])
+    # permutation: results do not depend on which CTA / in which order an utterance is processed.  Integer results
+    # (endpoints, frame counts, crossing counts) never depend on where an utterance sits; the fp32 windowed sums are
+    # bit-identical for utterances that keep their address modulo 16 bytes (the window pass reads 16-byte aligned
+    # vectors, so the association of its partial sums follows the alignment) and agree to a few ulp otherwise.
     cap = int(a.h_feat_offsets[1] - a.h_feat_offsets[0])
-    assert torch.equal(c.zcr[: N_UTTS * cap].view(N_UTTS, cap), a.zcr[: N_UTTS * cap].view(N_UTTS, cap)[perm])
-    assert torch.equal(c.energy[: N_UTTS * cap].view(N_UTTS, cap), a.energy[: N_UTTS * cap].view(N_UTTS, cap)[perm])
+    step16 = 8 // int(np.gcd(L, 8))                       # utterances i and i + step16 share their alignment class
+    g = torch.Generator(device=dev).manual_seed(1)
+    for keep_alignment in (True, False):
+        if keep_alignment:
+            assert N_UTTS % step16 == 0
+            perm = (torch.randperm(N_UTTS // step16, device=dev, generator=g)[:, None] * step16
+                    + torch.arange(step16, device=dev)[None, :]).reshape(-1)
+        else:
+            perm = torch.randperm(N_UTTS, device=dev, generator=g)
+        shuffled = torch.zeros_like(samples)
+        shuffled[: N_UTTS * L] = samples[: N_UTTS * L].view(N_UTTS, L)[perm].reshape(-1)
+        c = run(devapi, ctx, dev, shuffled, offsets, window)
+        assert torch.equal(c.start, a.start[perm]) and torch.equal(c.end, a.end[perm]) and torch.equal(c.n_frames, a.n_frames[perm])
+        assert torch.equal(c.zcr[: N_UTTS * cap].view(N_UTTS, cap), a.zcr[: N_UTTS * cap].view(N_UTTS, cap)[perm])
+        assert torch.equal(c.stats[:, 10:], a.stats[perm][:, 10:])
+        ce, ae = c.energy[: N_UTTS * cap].view(N_UTTS, cap), a.energy[: N_UTTS * cap].view(N_UTTS, cap)[perm]
+        if keep_alignment:
+            assert torch.equal(c.stats, a.stats[perm]) and torch.equal(ce, ae)
+        else:
+            assert bool(((ce - ae).abs() <= 2e-6 * ae.abs()).all())
+            sc = a.stats[perm][:, [2, 2, 2, 2, 2, 7, 7, 7, 7, 7]].abs()          # scale of a sequence: its maximum
+            assert bool(((c.stats[:, :10] - a.stats[perm][:, :10]).abs() <= 2e-6 * sc).all())
 
 
 def test_fast_kernel_equals_float64_replay_and_oracle_on_subsamples(ctx, big):

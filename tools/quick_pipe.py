@@ -28,8 +28,8 @@ print("parity mismatches:", bad, flush=True)
 dev = torch.device("cuda", 0)
 samples, row_offsets = bench.synth_batch_device(n, dev, seed=7)
 stream = torch.cuda.Stream(device=dev)
-for fl, fs in ((256, 128),):
-    fe = devapi.DeviceFrontend(row_offsets, fl, fs, "hamming", ctx=ctx, device=dev)
+def timed(tag, offsets, lengths=None, fl=256, fs=128):
+    fe = devapi.DeviceFrontend(offsets, fl, fs, "hamming", ctx=ctx, device=dev, lengths=lengths)
     with torch.cuda.stream(stream):
         for _ in range(3): fe.run(samples, stream=stream)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -37,4 +37,27 @@ for fl, fs in ((256, 128),):
         for _ in range(5): fe.run(samples, stream=stream)
         e1.record(stream)
     stream.synchronize()
-    print(f"fl={fl} fs={fs} pipelined {e0.elapsed_time(e1) / 5:.3f} ms  {n} utterances  replayed {int((fe.status >= 0x100).sum().item())}", flush=True)
+    ms = e0.elapsed_time(e1) / 5
+    gbs = fe.algorithmic_bytes() / ms / 1e6
+    print(f"{tag}: fl={fl} fs={fs} pipelined {ms:.3f} ms  {len(offsets) - 1} utterances  {gbs:.0f} GB/s = {gbs / 6554.2:.3f} of peak  "
+          f"replayed {int((fe.status >= 0x100).sum().item())}", flush=True)
+
+
+L = bench.UTT_LEN
+LAYOUTS = os.environ.get("QUICK_LAYOUTS", "packed,aligned,ragged").split(",")
+if "packed" in LAYOUTS:
+    timed("packed CSR L=44100 (every other start 8 bytes off)", row_offsets)
+if "aligned" in LAYOUTS:      # round 1's layout: every utterance padded to 44,104 samples (16-byte aligned starts)
+    keep = samples
+    bench.UTT_LEN = 44104
+    samples, pad_off = bench.synth_batch_device(n, dev, seed=7)
+    bench.UTT_LEN = L
+    timed("16-byte aligned starts (L=44104)", pad_off)
+    samples = keep
+if "ragged" not in LAYOUTS:
+    sys.exit(0)
+rng = np.random.default_rng(99)
+lens = (rng.uniform(0.8, 1.2, int(n * 1.05)) * 44100).astype(np.int64)
+r_off = np.concatenate([[0], np.cumsum(lens)])
+r_off = r_off[: int(np.searchsorted(r_off, n * L, side="right"))]
+timed("ragged U(0.8,1.2) s packed CSR (any alignment)", r_off)
