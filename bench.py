@@ -6,7 +6,8 @@ Workload per GPU and step (BASELINE.json configs[1] batch through the pipeline o
 1 s utterances (44.1 kHz int16 PCM, SURVEY.md 8(d) recipe generated on the device), frame 256 / shift 128, the three
 window types cycled across steps -> fused front end (DC removal, peak normalisation, endpoint detection, framing +
 window, energy / magnitude / ZCR, 15 statistics) -> z-score with the train set's mean / std -> KNN (k = 3) against a
-100,000-utterance train set whose features were extracted by the same front end before the timed region.
+100,000-utterance train set whose features were extracted by the same front end, with the same window type (one fitted
+classifier per window, as a reference run uses one --window-type for train and test), before the timed region.
 N = 1: the whole train set lives on the GPU.  N > 1 (one rank per GPU, weak scaling: 100,000 query utterances per
 GPU): the train rows are sharded over the ranks; every step all-gathers the ranks' query features, scores ALL of them
 against the local rows, exchanges the packed top-k candidates in ONE NCCL all-gather and merges + votes
@@ -289,7 +290,7 @@ def run_reference(args):
 
 METRIC = "audio-seconds processed/sec (features+endpoints+KNN)"
 WORKLOAD = ("configs[1] batch through the configs[2] pipeline: 100k synthetic 1 s utterances per GPU, frame 256 / shift 128, three windows "
-            "cycled over steps -> fused front end -> z-score -> KNN(3) vs a 100k-utterance train set")
+            "cycled over steps -> fused front end -> z-score -> KNN(3) vs a 100k-utterance train set framed with the same window")
 
 
 def knn_section(dev, ctx):
@@ -371,26 +372,29 @@ def run_ours(args):
     # ---- train set (outside the timed region, like model weights): rank r owns rows [tb[r], tb[r+1]) -----------------
     tb = ddist.balanced_bounds(args.train_utts, world)
     n_tr = int(tb[rank + 1] - tb[rank])
+    # one classifier per window type, as in the reference (a run extracts train AND test features with the same
+    # --window-type, run.py:84-130): the step that frames its queries with window w classifies them against models[w]
+    models = {}
     with torch.cuda.stream(stream):
         tr_samples, tr_offsets = synth_batch_device(n_tr, dev, seed=990000 + rank, first_index=int(tb[rank]))
-        tr_fe = devapi.DeviceFrontend(tr_offsets, FL, FS, "hamming", ctx=ctx, device=dev)
-        tr_fe.run(tr_samples, stream=stream)
-        x_tr = tr_fe.stats.double().contiguous()
         y_tr = (torch.arange(int(tb[rank]), int(tb[rank + 1]), device=dev) % 10).to(torch.int32)
-        if world > 1:
-            mean, std = ddist.zscore_stats_allreduce(x_tr)          # one tiny all-reduce (fit time)
-            std = torch.where(std == 0, torch.ones_like(std), std)
-            x_tr_n, _, _ = devapi.zscore_device(x_tr, mean, std, ctx=ctx)
-        else:
-            x_tr_n, mean, std = devapi.zscore_device(x_tr, ctx=ctx)
-        if world > 1:
-            knn = ddist.ShardedKNN(3, replicate_below=(0 if args.knn_path == "sharded" else 1 << 62)).fit(x_tr_n.contiguous(), y_tr)
-            predict = knn.predict
-        else:
-            knn = devapi.DeviceKNN(3, ctx=ctx, device=dev).fit(x_tr_n.contiguous(), y_tr)
-            predict = knn.predict
+        for w in WINDOWS:
+            tr_fe = devapi.DeviceFrontend(tr_offsets, FL, FS, w, ctx=ctx, device=dev)
+            tr_fe.run(tr_samples, stream=stream)
+            x_tr = tr_fe.stats.double().contiguous()
+            if world > 1:
+                mean, std = ddist.zscore_stats_allreduce(x_tr)          # one tiny all-reduce (fit time)
+                std = torch.where(std == 0, torch.ones_like(std), std)
+                x_tr_n, _, _ = devapi.zscore_device(x_tr, mean, std, ctx=ctx)
+                knn = ddist.ShardedKNN(3, replicate_below=(0 if args.knn_path == "sharded" else 1 << 62)).fit(x_tr_n.contiguous(), y_tr)
+            else:
+                x_tr_n, mean, std = devapi.zscore_device(x_tr, ctx=ctx)
+                knn = devapi.DeviceKNN(3, ctx=ctx, device=dev).fit(x_tr_n.contiguous(), y_tr)
+            models[w] = (mean, std, knn, x_tr_n)
+            stream.synchronize()
+            del tr_fe
     stream.synchronize()
-    del tr_samples, tr_fe
+    del tr_samples
     torch.cuda.empty_cache()
 
     # ---- query utterances: rank r owns utterances [r*n_utts, (r+1)*n_utts) of the global batch ------------------------
@@ -409,8 +413,9 @@ def run_ours(args):
         fe.run(samples, stream=stream)
         if timed is not None:
             ev_fe[timed][1].record(stream)
+        mean, std, knn, _ = models[WINDOWS[i % 3]]
         devapi.zscore_apply_f32(fe.stats, mean, std, out=qn, ctx=ctx)
-        labels[0] = predict(qn)
+        labels[0] = knn.predict(qn)
 
     with torch.cuda.stream(stream):
         for i in range(max(args.warmup, 3)):
@@ -528,26 +533,29 @@ def run_ours(args):
             # KNN labels of the first queries against the float64 oracle on the SAME z-scored features
             from oracle import knn_oracle as ko
             nq = 64
-            ref = ko.knn_predict(x_tr_n.cpu().numpy(), y_tr.cpu().numpy(), qn[:nq].cpu().numpy(), 3)
+            ref = ko.knn_predict(models["hamming"][3].cpu().numpy(), y_tr.cpu().numpy(), qn[:nq].cpu().numpy(), 3)
             parity["knn_label_mismatches_vs_oracle"] = int((ref != labels[0][:nq].cpu().numpy()).sum())
-            parity["knn_rescanned_in_float64,scan_kind"] = list(knn.last_stats())
+            parity["knn_not_certified_by_first_pass,scan_kind"] = list(models["hamming"][2].last_stats())
 
     # ---- e2e: the same pipeline through the host-buffer API (H2D + D2H inside) --------------------------------------------
     e2e = None
     if not args.no_e2e:
-        if world > 1:
-            xt = torch.cat(ddist._all_gather_rows(x_tr_n.contiguous()), dim=0).cpu().numpy()
-            yt = torch.cat(ddist._all_gather_rows(y_tr.contiguous()), dim=0).cpu().numpy()
-        else:
-            xt, yt = x_tr_n.cpu().numpy(), y_tr.cpu().numpy()
-        mu_h, sd_h = mean.cpu().numpy(), std.cpu().numpy()
-        hknn = batch.KNN(3, ctx=ctx).fit(xt, yt)
+        host_models = {}
+        for w in WINDOWS:
+            mean, std, _, x_tr_n = models[w]
+            if world > 1:
+                xt = torch.cat(ddist._all_gather_rows(x_tr_n.contiguous()), dim=0).cpu().numpy()
+                yt = torch.cat(ddist._all_gather_rows(y_tr.contiguous()), dim=0).cpu().numpy()
+            else:
+                xt, yt = x_tr_n.cpu().numpy(), y_tr.cpu().numpy()
+            host_models[w] = (mean.cpu().numpy(), std.cpu().numpy(), batch.KNN(3, ctx=ctx).fit(xt, yt))
         h_samples = torch.empty(samples.numel(), dtype=torch.int16, pin_memory=True)
         h_samples.copy_(samples)
         torch.cuda.synchronize()
         hs = h_samples.numpy()
 
         def e2e_step(i):
+            mu_h, sd_h, hknn = host_models[WINDOWS[i % 3]]
             res = batch.frontend_batch(hs, row_offsets, FL, FS, WINDOWS[i % 3], emit_frames=False, ctx=ctx)
             q = batch.zscore(res.stats.astype(np.float64), mu_h, sd_h, ctx=ctx)[0]
             return res, q, hknn.predict(q)

@@ -132,6 +132,7 @@ struct dsp_knn {
   bool tc16 = false;           // d <= 15: tensor-core candidate filter (knn_tc16.cu); the fp32 tiled scan stands in when a value leaves its range
   DevBuf tc_train, tc_q, tc_flags;
   DevBuf train64, train32, labels, tnorm, cand_idx, cand_worst, qnorm, redo_list, redo_count, nbr_label, q, o_idx, o_dist, o_lab;
+  DevBuf refine_list, refine_thr, surv_count, surv_rows;     // second pass of the D <= 15 path (knn_refine)
   DevBuf tpacked, tnorm_dense, qpacked, qnorm_chunk, dense_flags, part_d, part_i;
 };
 
@@ -837,7 +838,7 @@ static void knn_release(dsp_knn* k) {
   DevBuf* all[] = {&k->train64, &k->train32, &k->labels, &k->tnorm, &k->cand_idx, &k->cand_worst, &k->qnorm,
                    &k->redo_list, &k->redo_count, &k->nbr_label, &k->q, &k->o_idx, &k->o_dist, &k->o_lab,
                    &k->tpacked, &k->tnorm_dense, &k->qpacked, &k->qnorm_chunk, &k->dense_flags, &k->part_d, &k->part_i,
-                   &k->tc_train, &k->tc_q, &k->tc_flags};
+                   &k->tc_train, &k->tc_q, &k->tc_flags, &k->refine_list, &k->refine_thr, &k->surv_count, &k->surv_rows};
   for (DevBuf* b : all) b->release();
 }
 
@@ -929,28 +930,47 @@ int dsp_knn_topk_device(dsp_knn* h, const double* q, int64_t m, int64_t* nbr_idx
     CU(h->cand_idx.ensure(sizeof(int) * (size_t)m * kKnnCand));
     CU(h->cand_worst.ensure(sizeof(float) * (size_t)m));
     CU(h->qnorm.ensure(sizeof(float) * (size_t)m));
-    const int* gate = nullptr;
     double err_rel = (double)(h->d + 4) * 1.1920929e-7, err_floor = 0.0;
+    float qnorm_limit = 0.f;
     if (h->tc16) {
-      // tensor-core filter; the fp32 scan below is launched behind a device-side gate and runs only when a query
-      // left the filter's range (no host round trip either way)
+      // tensor-core filter; a query outside its range (|q|^2 above knn_tc16_max_norm(), NaN / inf) is scored as the zero
+      // vector there and handed to the exhaustive float64 scan by the rerank kernel -- per query, on the device
       CU(h->tc_q.ensure(knn_tc16_packed_bytes(m, true)));
       int* qflags = h->tc_flags.as<int>() + 4;
       CU(knn_tc16_pack(q, m, h->d, true, h->tc_q.p, h->qnorm.as<float>(), qflags, c->stream));
       CU(knn_tc16_filter(h->tc_q.p, h->tc_train.p, m, h->n, h->k, qflags, h->cand_idx.as<int>(), h->cand_worst.as<float>(),
                          c->sm_count, c->stream));
       c->launches += 2;
-      gate = qflags;
-      err_rel = std::max(err_rel, knn_dense_err_rel(16));      // covers whichever of the two scans produced the candidates
+      err_rel = knn_dense_err_rel(16);
       err_floor = 1.0;
+      qnorm_limit = knn_tc16_max_norm();
+    } else {
+      CU(knn_scan(h->dp, h->train32.as<float>(), h->n, q, m, h->d, h->cand_idx.as<int>(), h->cand_worst.as<float>(),
+                  h->qnorm.as<float>(), nullptr, c->stream));
+      c->launches += 1;
     }
-    CU(knn_scan(h->dp, h->train32.as<float>(), h->n, q, m, h->d, h->cand_idx.as<int>(), h->cand_worst.as<float>(),
-                h->qnorm.as<float>(), gate, c->stream));
+    // rejected queries: fp32 threshold scan + float64 ranking of the survivors (knn_refine) for up to refine_cap of them,
+    // the exhaustive float64 scan for the rest
+    const int refine_cap = (h->dp == 16 && h->k < kKnnCand) ? (int)std::min<int64_t>(m, 65536) : 0;
+    if (refine_cap) {
+      CU(h->refine_list.ensure(sizeof(int32_t) * (size_t)refine_cap));
+      CU(h->refine_thr.ensure(sizeof(float) * (size_t)refine_cap));
+      CU(h->surv_count.ensure(sizeof(int32_t) * (size_t)refine_cap));
+      CU(h->surv_rows.ensure(sizeof(int32_t) * (size_t)refine_cap * knn_refine_survivor_cap()));
+    }
     CU(knn_rerank(h->train64.as<double>(), h->train32.as<float>(), h->dp, h->n, q, m, h->d, h->k, h->index_base,
                   h->labels.as<int32_t>(), h->cand_idx.as<int>(), h->cand_worst.as<float>(), h->qnorm.as<float>(),
                   h->tnorm_max, err_rel, err_floor, nbr_idx, nbr_sqdist, nbr_label, h->redo_list.as<int32_t>(),
-                  h->redo_count.as<int32_t>(), c->stream));
-    c->launches += 2;
+                  h->redo_count.as<int32_t>(), c->stream, refine_cap ? h->refine_list.as<int32_t>() : nullptr,
+                  h->refine_thr.as<float>(), refine_cap, qnorm_limit));
+    c->launches += 1;
+    if (refine_cap) {
+      CU(knn_refine(h->train64.as<double>(), h->train32.as<float>(), h->dp, h->n, q, h->d, h->k, h->index_base,
+                    h->labels.as<int32_t>(), h->refine_list.as<int32_t>(), h->refine_thr.as<float>(), refine_cap,
+                    h->surv_count.as<int32_t>(), h->surv_rows.as<int32_t>(), h->redo_count.as<int32_t>(),
+                    h->redo_list.as<int32_t>(), nbr_idx, nbr_sqdist, nbr_label, c->sm_count, c->stream));
+      c->launches += 2;
+    }
   } else if (h->dense) {
     // tensor-core candidate scan in chunks of queries (bounded staging), float64 rerank + certificate per chunk;
     // the rejected queries of every chunk accumulate in one redo list
@@ -996,6 +1016,12 @@ int dsp_knn_topk_device(dsp_knn* h, const double* q, int64_t m, int64_t* nbr_idx
                 h->redo_list.as<int32_t>(), h->redo_count.as<int32_t>(), nbr_idx, nbr_sqdist, nbr_label,
                 c->sm_count, h->part_d.as<double>(), h->part_i.as<long long>(), (int)std::min<int64_t>(m, INT32_MAX), c->stream));
   c->launches++;
+  if (std::getenv("DSP_KNN_DEBUG")) {
+    int32_t cnt[4];
+    cudaMemcpyAsync(cnt, h->redo_count.p, sizeof cnt, cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    fprintf(stderr, "[knn] m=%lld n=%lld exhaustive=%d refined=%d refined->exhaustive=%d\n", (long long)m, (long long)h->n, cnt[0], cnt[1], cnt[2]);
+  }
   return DSP_OK;
 }
 
@@ -1119,12 +1145,14 @@ int dsp_dtw_topk_host(dsp_context* c, const float* q_feats, const int64_t* q_off
 int dsp_knn_last_stats(dsp_knn* h, int64_t* rescanned, int32_t* scan_kind) {
   if (!h) return fail(DSP_ERR_INVALID, "bad argument");
   CU(cudaSetDevice(h->ctx->device));
-  int32_t cnt = 0;
+  // queries the first certificate rejected: refined ([1]) + sent straight to the exhaustive scan ([0] minus those the
+  // refinement passed on, [2])
+  int32_t cnt[4] = {0, 0, 0, 0};
   if (h->redo_count.p) {
-    CU(cudaMemcpyAsync(&cnt, h->redo_count.p, sizeof cnt, cudaMemcpyDeviceToHost, h->ctx->stream));
+    CU(cudaMemcpyAsync(cnt, h->redo_count.p, sizeof cnt, cudaMemcpyDeviceToHost, h->ctx->stream));
     CU(cudaStreamSynchronize(h->ctx->stream));
   }
-  if (rescanned) *rescanned = cnt;
+  if (rescanned) *rescanned = (int64_t)cnt[0] + cnt[1] - cnt[2];
   if (scan_kind) *scan_kind = h->dp ? (h->tc16 ? 3 : 1) : (h->dense ? 2 : 0);
   return DSP_OK;
 }

@@ -209,7 +209,8 @@ __global__ void knn_rerank_kernel(const double* __restrict__ train, const float*
                                   const float* __restrict__ qnorm, float tnorm_max, double err_rel, double err_floor,
                                   int64_t* __restrict__ nbr_idx, double* __restrict__ nbr_sqdist,
                                   int32_t* __restrict__ nbr_label, int32_t* __restrict__ redo_list,
-                                  int32_t* __restrict__ redo_count) {
+                                  int32_t* __restrict__ redo_count, int32_t* __restrict__ refine_list,
+                                  float* __restrict__ refine_thr, int refine_cap, float qnorm_limit) {
   const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (qi >= m) return;
   const double* q = queries + qi * d;
@@ -218,7 +219,7 @@ __global__ void knn_rerank_kernel(const double* __restrict__ train, const float*
   int nc = 0;
   for (int c = 0; c < kKnnCand; ++c) {
     const int i = cand_idx[qi * kKnnCand + c];
-    if (i < 0) continue;
+    if (i < 0 || i >= n) continue;
     const double dd = sqdist64(q, train + (int64_t)i * d, d);
     int s = nc++;
     while (s > 0 && less_di(dd, i, cd[s - 1], cidx[s - 1])) { cd[s] = cd[s - 1]; cidx[s] = cidx[s - 1]; --s; }
@@ -226,19 +227,41 @@ __global__ void knn_rerank_kernel(const double* __restrict__ train, const float*
   }
   const int kk = (int)min((int64_t)k, n);
   bool ok = (nc >= kk);
+  // a query outside the tensor-core filter's range was scored as the zero vector (knn_tc16_pack_kernel): its candidates
+  // mean nothing -- exhaustive float64 scan
+  const bool in_range = !(qnorm_limit > 0.f) || qnorm[qi] <= qnorm_limit;
+  if (!in_range) { ok = false; nc = 0; }
   if (ok && n > kKnnCand) {
-    // every row that is NOT a candidate has fp32 score >= worst kept score; its exact squared
-    // distance is at least (score + |q|^2) - err.  err bounds the fp32 evaluation of
-    // |t|^2 - 2 q.t + |q|^2: (d+2) roundings on terms bounded by (|q| + |t|)^2.
+    // Every row that is NOT a candidate has score >= the worst kept score W, and the scan's score of row t is within
+    // err_rel * (|q| + |t|)^2 of |t|^2 - 2 q.t (the roundings act on terms bounded by (|q| + |t|)^2).  A row that
+    // could displace a candidate has exact distance <= D_k (the k-th exact candidate distance), hence |t| <= |q| +
+    // sqrt(D_k) by the triangle inequality, hence score error <= err_rel * (2 |q| + sqrt(D_k))^2 -- the norm of the
+    // rows that matter, not of the largest row of the train set (which made outliers in the train set reject 3 % of
+    // the queries of real feature sets).  So: D_k < W + |q|^2 - err certifies the candidates.
     const float qn = qnorm[qi];
-    const double bound = (double)(sqrtf(qn) + sqrtf(tnorm_max));
+    const double bound = 2.0 * (double)sqrtf(qn) * 1.0000002 + sqrt(cd[kk - 1]);
     // err_floor: the split-fp16 filter also has an ABSOLUTE error (fp16 subnormal spacing of the lo planes), covered
-    // by evaluating the relative bound at (|q| + |t|max)^2 >= err_floor
+    // by evaluating the relative bound at no less than err_floor
     const double err = err_rel * fmax(bound * bound, err_floor);
     const double lower = (double)cand_worst[qi] + (double)qn - err;
     ok = cd[kk - 1] < lower;
   }
   if (!ok) {
+    // Not certified.  With k candidates in hand their k-th exact distance D bounds the true k-th distance from above:
+    // every row that can still matter has exact distance <= D, i.e. fp32 score <= D - |q|^2 + err32 -- the threshold of
+    // the second pass (knn_refine_collect_kernel); without a refine list, or past its capacity: exhaustive float64 scan
+    if (refine_list && nc >= kk && train32) {
+      const int slot = atomicAdd(redo_count + 1, 1);
+      if (slot < refine_cap) {
+        // rows that matter have |t| <= |q| + sqrt(D_k) (above): the fp32 scan's error on them
+        const float qn = qnorm[qi];
+        const double bound = 2.0 * (double)sqrtf(qn) * 1.0000002 + sqrt(cd[kk - 1]);
+        const double err32 = (double)(d + 4) * 1.1920929e-7 * bound * bound;
+        refine_list[slot] = (int)qi;
+        refine_thr[slot] = __double2float_ru(cd[kk - 1] - (double)qn + err32);
+        return;
+      }
+    }
     const int slot = atomicAdd(redo_count, 1);
     redo_list[slot] = (int)qi;
     return;
@@ -358,8 +381,19 @@ __global__ void knn_rescan_kernel(const double* __restrict__ train, int64_t n,
     double bd[kKnnMaxK];
     int64_t bi[kKnnMaxK];
     for (int c = 0; c < k; ++c) { bd[c] = INFINITY; bi[c] = INT64_MAX; }
-    for (int64_t i = row_lo + lane; i < row_hi; i += 32) {
-      const double dd = sqdist64(q, train + i * d, d);
+    // 32 rows at a time: the warp copies their 32 * d contiguous doubles into shared memory with coalesced loads (a
+    // lane walking its own row touches 32 different sectors per load: 6 ms for 100 rejected queries x 10^5 rows), then
+    // every lane sums its row in feature order -- the very sum sqdist64 computes
+    extern __shared__ double rescan_stage[];
+    double* stage = rescan_stage + (size_t)(threadIdx.x >> 5) * 32 * d;
+    for (int64_t i0 = row_lo; i0 < row_hi; i0 += 32) {
+      const int rows = (int)min((int64_t)32, row_hi - i0);
+      __syncwarp();
+      for (int e = lane; e < rows * d; e += 32) stage[e] = train[i0 * d + e];
+      __syncwarp();
+      if (lane >= rows) continue;
+      const int64_t i = i0 + lane;
+      const double dd = sqdist64(q, stage + lane * d, d);
       if (less_di(dd, i, bd[k - 1], bi[k - 1])) {
         int s = k - 1;
         while (s > 0 && less_di(dd, i, bd[s - 1], bi[s - 1])) { bd[s] = bd[s - 1]; bi[s] = bi[s - 1]; --s; }
@@ -583,7 +617,134 @@ __global__ void knn_merge_vote_kernel(const double* __restrict__ cd, const int64
 __global__ void knn_iota_kernel(int32_t* list, int32_t* count, int64_t m) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < m) list[i] = (int32_t)i;
-  if (i == 0) *count = (int32_t)m;
+  if (i == 0) { count[0] = (int32_t)m; count[1] = 0; count[2] = 0; }
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Second pass for the queries the certificate rejected (D <= 15 path): instead of an exhaustive float64 scan per query
+// (the 12 MB train matrix through L2 once per rejected query), score every row again in fp32 against the query's OWN
+// threshold -- rows whose score is above it cannot be among the k nearest (rerank kernel) -- and keep the survivors
+// (typically a dozen); knn_refine_finish_kernel ranks those in float64 exactly as the rescan would.  A query with
+// more than kRefineCap survivors goes to the exhaustive scan.  Work items = (block of 128 rejected queries) x (part of
+// the train rows), persistent grid, everything sized on the device: no host round trip.
+// ---------------------------------------------------------------------------------------
+constexpr int kRefineCap = 64;
+constexpr int kRefineThreads = 128;
+
+template <int DP>
+__global__ void __launch_bounds__(kRefineThreads)
+knn_refine_collect_kernel(const float* __restrict__ train32, int64_t n, const double* __restrict__ queries, int d,
+                          const int32_t* __restrict__ refine_list, const float* __restrict__ refine_thr,
+                          const int32_t* __restrict__ counts, int refine_cap, int32_t* __restrict__ surv_count,
+                          int32_t* __restrict__ surv_rows) {
+  __shared__ __align__(16) float tile[kTileRows * DP];
+  const int total = min(counts[1], refine_cap);
+  if (total == 0) return;
+  const int qblocks = (total + kRefineThreads - 1) / kRefineThreads;
+  int parts = (int)gridDim.x / qblocks;
+  if (parts < 1) parts = 1;
+  const int64_t tiles = (n + kTileRows - 1) / kTileRows;
+  if (parts > tiles) parts = (int)tiles;
+  const int64_t tiles_per = (tiles + parts - 1) / parts;
+  for (int work = blockIdx.x; work < qblocks * parts; work += gridDim.x) {
+    const int qb = work / parts, part = work % parts;
+    const int slot = qb * kRefineThreads + threadIdx.x;
+    const bool live = slot < total;
+    float q[DP - 1];
+    float thr = -INFINITY;
+    if (live) {
+      const int64_t qi = refine_list[slot];
+      thr = refine_thr[slot];
+#pragma unroll
+      for (int j = 0; j < DP - 1; ++j) q[j] = j < d ? -2.f * (float)queries[qi * d + j] : 0.f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < DP - 1; ++j) q[j] = 0.f;
+    }
+    const int64_t row_lo = (int64_t)part * tiles_per * kTileRows, row_hi = min(n, row_lo + tiles_per * kTileRows);
+    for (int64_t base = row_lo; base < row_hi; base += kTileRows) {
+      const int rows = (int)min((int64_t)kTileRows, row_hi - base);
+      __syncthreads();
+      {
+        const float4* src = reinterpret_cast<const float4*>(train32 + base * DP);
+        float4* dst = reinterpret_cast<float4*>(tile);
+        for (int i = threadIdx.x; i < rows * (DP / 4); i += kRefineThreads) dst[i] = src[i];
+      }
+      __syncthreads();
+      for (int j = 0; j < rows; ++j) {
+        const float4* row = reinterpret_cast<const float4*>(tile + j * DP);
+        float acc = tile[j * DP + DP - 1];
+#pragma unroll
+        for (int v = 0; v < DP / 4; ++v) {
+          const float4 x = row[v];
+          acc = fmaf(q[4 * v], x.x, acc);
+          acc = fmaf(q[4 * v + 1], x.y, acc);
+          acc = fmaf(q[4 * v + 2], x.z, acc);
+          if (4 * v + 3 < DP - 1) acc = fmaf(q[4 * v + 3], x.w, acc);
+        }
+        if (acc <= thr) {
+          const int s = atomicAdd(surv_count + slot, 1);
+          if (s < kRefineCap) surv_rows[(int64_t)slot * kRefineCap + s] = (int)(base + j);
+        }
+      }
+    }
+  }
+}
+
+// one warp per rejected query: float64 distances of its survivors, the k smallest by (distance, index)
+__global__ void knn_refine_finish_kernel(const double* __restrict__ train, const double* __restrict__ queries, int d, int k,
+                                         int64_t index_base, const int32_t* __restrict__ labels,
+                                         const int32_t* __restrict__ refine_list, int32_t* __restrict__ counts, int refine_cap,
+                                         const int32_t* __restrict__ surv_count, const int32_t* __restrict__ surv_rows,
+                                         int64_t* __restrict__ nbr_idx, double* __restrict__ nbr_sqdist,
+                                         int32_t* __restrict__ nbr_label, int32_t* __restrict__ redo_list) {
+  const int lane = threadIdx.x & 31;
+  const int total = min(counts[1], refine_cap);
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < total; slot += warps) {
+    const int64_t qi = refine_list[slot];
+    const int cnt = surv_count[slot];
+    if (cnt > kRefineCap || cnt < k) {       // too many survivors (or, defensively, too few): exhaustive float64 scan
+      if (lane == 0) { const int s = atomicAdd(counts, 1); redo_list[s] = (int)qi; atomicAdd(counts + 2, 1); }
+      continue;
+    }
+    const double* q = queries + qi * d;
+    double dd[kRefineCap / 32];
+    int64_t ii[kRefineCap / 32];
+#pragma unroll
+    for (int r = 0; r < kRefineCap / 32; ++r) {
+      const int e = lane + 32 * r;
+      dd[r] = INFINITY; ii[r] = INT64_MAX;
+      if (e < cnt) { ii[r] = surv_rows[(int64_t)slot * kRefineCap + e]; dd[r] = sqdist64(q, train + ii[r] * d, d); }
+    }
+    for (int c = 0; c < k; ++c) {
+      // the lane's smallest remaining entry, then the warp's
+      int br = 0;
+#pragma unroll
+      for (int r = 1; r < kRefineCap / 32; ++r) if (less_di(dd[r], ii[r], dd[br], ii[br])) br = r;
+      double md = dd[0]; int64_t mi = ii[0];
+#pragma unroll
+      for (int r = 1; r < kRefineCap / 32; ++r) if (br == r) { md = dd[r]; mi = ii[r]; }
+      int owner = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, md, o);
+        const int64_t oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        const int oo = __shfl_xor_sync(0xffffffffu, owner, o);
+        if (less_di(od, oi, md, mi)) { md = od; mi = oi; owner = oo; }
+      }
+      if (owner == lane) {
+#pragma unroll
+        for (int r = 0; r < kRefineCap / 32; ++r) if (br == r) { dd[r] = INFINITY; ii[r] = INT64_MAX; }
+      }
+      if (lane == 0) {
+        if (nbr_idx) nbr_idx[qi * k + c] = index_base + mi;
+        if (nbr_sqdist) nbr_sqdist[qi * k + c] = md;
+        if (nbr_label) nbr_label[qi * k + c] = labels[mi];
+      }
+    }
+  }
 }
 
 }  // namespace
@@ -627,9 +788,10 @@ cudaError_t knn_rerank(const double* train, const float* train32, int dp, int64_
                        int64_t m, int d, int k, int64_t index_base, const int32_t* labels,
                        const int* cand_idx, const float* cand_worst, const float* qnorm,
                        float tnorm_max_host, double err_rel, double err_floor, int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label,
-                       int32_t* redo_list, int32_t* redo_count, cudaStream_t st) {
+                       int32_t* redo_list, int32_t* redo_count, cudaStream_t st, int32_t* refine_list, float* refine_thr,
+                       int refine_cap, float qnorm_limit) {
   if (m == 0) return cudaSuccess;
-  cudaMemsetAsync(redo_count, 0, sizeof(int32_t), st);
+  cudaMemsetAsync(redo_count, 0, 4 * sizeof(int32_t), st);
   if (d > 64) {
     const unsigned grid = (unsigned)std::min<int64_t>((m + kRerankWarps - 1) / kRerankWarps, 148 * 32);
     knn_rerank_wide_kernel<<<grid, 32 * kRerankWarps, 0, st>>>(train, n, q, m, d, k, index_base, labels, cand_idx, cand_worst, qnorm,
@@ -639,7 +801,22 @@ cudaError_t knn_rerank(const double* train, const float* train32, int dp, int64_
   }
   knn_rerank_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(
       train, train32, dp, n, q, m, d, k, index_base, labels, cand_idx, cand_worst, qnorm, tnorm_max_host, err_rel, err_floor,
-      nbr_idx, nbr_sqdist, nbr_label, redo_list, redo_count);
+      nbr_idx, nbr_sqdist, nbr_label, redo_list, redo_count, refine_list, refine_thr, refine_cap, qnorm_limit);
+  return cudaGetLastError();
+}
+
+int knn_refine_survivor_cap() { return kRefineCap; }
+
+cudaError_t knn_refine(const double* train, const float* train32, int dp, int64_t n, const double* q, int d, int k,
+                       int64_t index_base, const int32_t* labels, const int32_t* refine_list, const float* refine_thr,
+                       int refine_cap, int32_t* surv_count, int32_t* surv_rows, int32_t* counts, int32_t* redo_list,
+                       int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label, int sm_count, cudaStream_t st) {
+  if (dp != 16 || refine_cap <= 0) return cudaSuccess;
+  cudaMemsetAsync(surv_count, 0, sizeof(int32_t) * (size_t)refine_cap, st);
+  knn_refine_collect_kernel<16><<<sm_count * 4, kRefineThreads, 0, st>>>(train32, n, q, d, refine_list, refine_thr, counts, refine_cap,
+                                                                          surv_count, surv_rows);
+  knn_refine_finish_kernel<<<sm_count * 2, 256, 0, st>>>(train, q, d, k, index_base, labels, refine_list, counts, refine_cap,
+                                                          surv_count, surv_rows, nbr_idx, nbr_sqdist, nbr_label, redo_list);
   return cudaGetLastError();
 }
 
@@ -664,8 +841,11 @@ cudaError_t knn_rescan(const double* train, int64_t n, const double* q, int d, i
                                                                nbr_idx, nbr_sqdist, nbr_label);
   } else {
     const int blocks = sm_count * 2, workers = blocks * 8;          // knn_rescan_grid(sm_count) >= workers: the partial lists fit
-    knn_rescan_kernel<<<blocks, 256, 0, st>>>(train, n, q, d, k, index_base, labels, redo_list, redo_count, nbr_idx, nbr_sqdist,
-                                              nbr_label, part_d, part_i);
+    const size_t stage_bytes = (size_t)8 * 32 * d * sizeof(double);      // d <= 64: at most 128 KB
+    cudaError_t ea = cudaFuncSetAttribute(knn_rescan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage_bytes);
+    if (ea != cudaSuccess) return ea;
+    knn_rescan_kernel<<<blocks, 256, stage_bytes, st>>>(train, n, q, d, k, index_base, labels, redo_list, redo_count, nbr_idx, nbr_sqdist,
+                                                        nbr_label, part_d, part_i);
     const int mt = max_redo < workers ? max_redo : workers;
     if (mt > 0)
       knn_rescan_merge_kernel<<<(mt + 127) / 128, 128, 0, st>>>(workers, k, index_base, labels, redo_list, redo_count, part_d, part_i,

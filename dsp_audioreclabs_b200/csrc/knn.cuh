@@ -19,7 +19,15 @@ cudaError_t knn_rerank(const double* train, const float* train32, int dp, int64_
                        int64_t m, int d, int k, int64_t index_base, const int32_t* labels,
                        const int* cand_idx, const float* cand_worst, const float* qnorm,
                        float tnorm_max_host, double err_rel, double err_floor, int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label,
-                       int32_t* redo_list, int32_t* redo_count, cudaStream_t st);
+                       int32_t* redo_list, int32_t* redo_count, cudaStream_t st, int32_t* refine_list = nullptr,
+                       float* refine_thr = nullptr, int refine_cap = 0, float qnorm_limit = 0.f);
+// D <= 15: second pass for the queries the certificate rejected (fp32 threshold scan + float64 ranking of the survivors);
+// counts = redo_count: [0] exhaustive rescans, [1] refined queries, [2] refined queries passed on to the exhaustive scan
+int knn_refine_survivor_cap();
+cudaError_t knn_refine(const double* train, const float* train32, int dp, int64_t n, const double* q, int d, int k,
+                       int64_t index_base, const int32_t* labels, const int32_t* refine_list, const float* refine_thr,
+                       int refine_cap, int32_t* surv_count, int32_t* surv_rows, int32_t* counts, int32_t* redo_list,
+                       int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label, int sm_count, cudaStream_t st);
 cudaError_t knn_redo_all(int32_t* redo_list, int32_t* redo_count, int64_t m, cudaStream_t st);
 cudaError_t knn_rescan(const double* train, int64_t n, const double* q, int d, int k, int64_t index_base,
                        const int32_t* labels, const int32_t* redo_list, const int32_t* redo_count,

@@ -260,7 +260,8 @@ knn_tc16_filter_kernel(const unsigned char* __restrict__ qpacked, const unsigned
                        int units, int t_tiles, const int* __restrict__ qflags, int* __restrict__ cand_idx,
                        float* __restrict__ cand_worst) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  if (qflags[1]) return;                                    // a query outside the filter's range: the fp32 scan takes the call
+  // (a query outside the filter's range was packed as the zero vector: it gets candidates like any other and the rerank
+  //  kernel sends it to the exhaustive float64 scan -- qflags is informational)
   unsigned char* s_q = smem;                                // [2][2 blocks][hi | lo]
   unsigned char* s_t = smem + 2 * kQBufBytes;               // [kTStages][hi | lo]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kQBufBytes + (size_t)kTStages * kTileBytes);
