@@ -345,8 +345,11 @@ def traffic_of_record(kernel_src):
 
 # --------------------------------------------------------------------------------------------
 def run_ours(args):
+    import faulthandler
     import torch
     import torch.distributed as dist
+    # a rank that waits forever (a collective its peers never enter) must end the run with a stack trace, not hang the box
+    faulthandler.dump_traceback_later(int(os.environ.get("BENCH_WATCHDOG_S", "420")), exit=True)
     from dsp_audioreclabs_b200 import batch, device as devapi, dist as ddist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -474,8 +477,30 @@ def run_ours(args):
                 "knn": {"queries_per_gpu_per_step": n_utts, "train_rows": args.train_utts, "dim": 15, "k": 3,
                         "train_layout": "whole train set on the GPU" if world == 1 else
                         (f"rows sharded x{world}; per step: all-gather of the query features, ONE NCCL all-gather of the packed top-k candidates "
-                         f"({world * n_utts} queries x 3 x 24 B per rank), merge + vote" if args.knn_path == "sharded" else
+                         f"({world * n_utts} queries x 3 x 16 B per rank), merge + vote" if args.knn_path == "sharded" else
                          f"rows all-gathered once at fit (replicated), no per-step exchange")}}
+    if world > 1 and args.knn_path == "sharded":
+        # the same steps with the train rows all-gathered once at fit (the D = 15 fast path: no per-step exchange)
+        try:
+            with torch.cuda.stream(stream):
+                for i in range(3):
+                    models[WINDOWS[i]][2].predict_replicated(qn)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for i in range(6):
+                    fe = frontends[WINDOWS[i % 3]]
+                    fe.run(samples, stream=stream)
+                    mean, std, knn, _ = models[WINDOWS[i % 3]]
+                    devapi.zscore_apply_f32(fe.stats, mean, std, out=qn, ctx=ctx)
+                    knn.predict_replicated(qn)
+                e1.record(stream)
+            stream.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / 6], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pipeline["replicated_train_rows"] = {"ms_per_step_max_over_ranks": float(t.item()),
+                                                 "audio_s_per_s": world * audio_s_per_step / (float(t.item()) / 1e3)}
+        except Exception as exc:
+            pipeline["replicated_train_rows"] = {"error": repr(exc)}
     frontend_only = {"workload": "configs[1]: batched front end only", "value": world * audio_s_per_step / (fe_ms_max / 1e3),
                      "unit": "audio-s/s", "ms_per_launch_max_over_ranks": fe_ms_max}
 
@@ -510,11 +535,11 @@ def run_ours(args):
 
     # ---- parity spot check against the oracle on a few of the benchmarked utterances -------------------------------------
     parity = None
+    with torch.cuda.stream(stream):
+        step(1)                                   # hamming; on EVERY rank: the sharded classify step is a collective
+    stream.synchronize()
     if rank == 0:
         from oracle import frontend_oracle as fo
-        with torch.cuda.stream(stream):
-            step(1)                               # hamming
-        stream.synchronize()
         f = frontends["hamming"]
         nchk = 24
         host = samples[: nchk * UTT_LEN].cpu().numpy()
@@ -599,6 +624,7 @@ def run_ours(args):
         if world == 1 and not args.no_knn:
             line["knn"] = knn_section(dev, ctx)
         print(json.dumps(line), flush=True)
+    faulthandler.cancel_dump_traceback_later()
     if world > 1:
         dist.destroy_process_group()
 

@@ -144,15 +144,26 @@ class ShardedKNN:
 
     def predict_sharded(self, queries_local):
         """The north-star exchange: all-gather the query features, score ALL queries against the local rows, ONE
-        all-gather of the packed per-shard top-k candidates, merge + vote for the rank's own queries."""
+        all-gather of the packed per-shard top-k candidates (16 bytes per candidate: the float64 distance, and the
+        global row with the label in one int64), merge + vote for the rank's own queries (only their slice of the
+        gathered buffer is unpacked)."""
         rank = dist.get_rank(self.group)
+        world = dist.get_world_size(self.group)
         per_rank_q = _all_gather_rows(queries_local.contiguous(), self.group)
         q_all = torch.cat(per_rank_q, dim=0)
         d2, idx, lab = self._topk(self.train, self.labels, q_all, self.k, self.index_base)
-        cd, ci, cl = all_gather_candidates(d2, idx, lab, self.group)
+        if self.n_total >= (1 << 31):
+            raise ValueError("row-sharded KNN packs the global row index into 32 bits: at most 2^31 train rows")
+        mine = torch.stack([d2.contiguous().view(torch.int64),
+                            (idx.to(torch.int64) << 32) | (lab.to(torch.int64) & 0xFFFFFFFF)], dim=2).contiguous()
+        out = torch.empty((world,) + tuple(mine.shape), dtype=torch.int64, device=mine.device)
+        dist.all_gather_into_tensor(out.view(-1), mine.view(-1), group=self.group)      # the single candidate exchange
         lo = sum(t.shape[0] for t in per_rank_q[:rank])
-        hi = lo + queries_local.shape[0]
-        return self._merge(cd[:, lo:hi].contiguous(), ci[:, lo:hi].contiguous(), cl[:, lo:hi].contiguous())
+        own = out[:, lo:lo + queries_local.shape[0]]
+        cd = own[..., 0].contiguous().view(torch.float64)
+        ci = (own[..., 1] >> 32).contiguous()
+        cl = ((own[..., 1] << 32) >> 32).to(torch.int32).contiguous()       # sign-extended low word (-1 = empty slot)
+        return self._merge(cd, ci, cl)
 
     def predict_replicated(self, queries_local):
         """All-gather the (small) train shards once per fit, classify own queries with no candidate exchange.
