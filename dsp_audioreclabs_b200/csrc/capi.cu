@@ -261,17 +261,13 @@ int frontend_device(dsp_context* c, const void* samples, int dtype, const int64_
   // tuning knob (pcm_variant == pcm_num_variants())
   const int kPipeVariant = pcm_num_variants();
   PipePlan plan{};
-  // automatic choice (tools/config_sweep.py, ms per 20k utterances, resident vs pipelined): the pipelined kernel when
-  // frames are whole 64-sample groups and the hop is at least 128 -- 256/128 1.25 vs 0.83 (BASELINE configs[1], its
-  // specialised instantiation), 512/256 1.20 vs 0.97, 1024/512 1.28 vs 1.00, 2048/1024 2.35 vs 0.99, 1024/256 1.44 vs 1.25;
-  // shorter hops (128/64 2.44 vs 3.29) and frames with ragged edges (1102/441 2.1 vs 6.0) stay on frontend_pcm_kernel,
-  // whose window pass reads the trimmed segment from shared memory
-  const bool pipe_geometry = (fl % 64 == 0 && fs % 64 == 0 && fs >= 128 && fl <= 16384);
-  // (any alignment: its producer realigns utterances that do not start on a 16-byte boundary, csrc/frontend_pipe.cu)
-  // frame 256 / shift 128 (its specialised instantiation) takes any alignment at full speed; the other whole-group
-  // geometries read the trimmed segment with 16-byte loads and are routed here only for aligned layouts
-  const bool chain_geometry = (fl == 256 && fs == 128);
-  bool pipe = fast && (c->pcm_variant == kPipeVariant || (c->pcm_variant < 0 && pipe_geometry && (chain_geometry || p->aligned16))) &&
+  // automatic choice: the pipelined kernel (frontend_pipe.cu) for every geometry its shared-memory plan fits -- any
+  // frame length / shift (frames that are not whole 64-sample groups take its ragged-edge forms), any utterance
+  // alignment.  tools/config_sweep.py, ms per 20k packed 1 s utterances, resident vs pipelined: 256/128 2.85 vs 0.71,
+  // 1102/441 (the reference's default) 3.73 vs 1.41, 512/256 2.79 vs 0.99, 2048/1024 5.71 vs 1.03, 2205/441 8.55 vs 1.83,
+  // 1102/1323 3.32 vs 1.18.  Geometries with very many frames per utterance (hops under ~100 samples at 1 s) do not fit
+  // its per-utterance records and stay on frontend_pcm_kernel.
+  bool pipe = fast && (c->pcm_variant == kPipeVariant || c->pcm_variant < 0) &&
               pipe_kernel_plan(max_len, (int)cap_frames64, fl, kMaxSmemPerCta, &plan);
   if (fast && !pipe && c->pcm_variant == kPipeVariant) variant = kAutoResident;
   if (pipe) {

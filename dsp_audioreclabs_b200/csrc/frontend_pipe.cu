@@ -909,7 +909,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
         const int sub = lane & (kLanesPerFrame - 1);
         const int slot = lane / kLanesPerFrame;
         constexpr int kSlots = 32 / kLanesPerFrame;
-        const bool vec_ok = ((start & 7) == 0) && ((fs & 7) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+        // Generic windowed pass: kLanesPerFrame lanes per frame.  Whatever the frame's address (odd hops, packed CSR
+        // batches), a lane reads 16-byte ALIGNED vectors: the frame starts mm = 0..7 samples into its first vector, the
+        // window is indexed per sample (scalar shared-memory loads at j = 8 v - mm + i), and the samples outside
+        // [0, valid) -- in front of the frame in its first vector, behind it in the last -- get weight 0.
 #pragma unroll 1
         for (int t0 = f2_chain; t0 < f2; t0 += kSlots) {
           const int t = t0 + slot;
@@ -917,42 +920,39 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
           if (t < f2) {
             const int p = start + t * fs;
             const int valid = min(fl, end - p);
-            int jdone = 0;
-            if (vec_ok) {
-              const int nv = valid >> 3;
-              const int4* xv = reinterpret_cast<const int4*>(x + p);
-              const float4* wv = reinterpret_cast<const float4*>(s_win);
-              // four 16-byte loads in flight per lane (the samples come from L2)
-              auto acc8 = [&](const int4& q, int vq) {
-                const float4 wa = wv[2 * vq], wb = wv[2 * vq + 1];
-                const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
-                const float ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+            const int mm = (int)((reinterpret_cast<uintptr_t>(x + p) & 15) >> 1);
+            const int4* xv = reinterpret_cast<const int4*>(x + p - mm);
+            const int nv = (mm + valid + 7) >> 3;
+            auto acc8 = [&](const int4& q, int v) {
+              const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+              const int j0 = 8 * v - mm;
+              float ww[8];
+              if (j0 >= 0 && j0 + 8 <= valid) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const float dlo = (float)(sext16(w[k]) - thr) - phi;
-                  const float dhi = (float)(((int)w[k] >> 16) - thr) - phi;
-                  const float alo = ww[2 * k] * dlo, ahi = ww[2 * k + 1] * dhi;
-                  e = fmaf(alo, alo, e); m += fabsf(alo);
-                  e = fmaf(ahi, ahi, e); m += fabsf(ahi);
-                }
-              };
-              int vq = sub;
-#pragma unroll 1
-              for (; vq + 3 * kLanesPerFrame < nv; vq += 4 * kLanesPerFrame) {
-                const int4 q0 = __ldg(xv + vq), q1 = __ldg(xv + vq + kLanesPerFrame);
-                const int4 q2 = __ldg(xv + vq + 2 * kLanesPerFrame), q3 = __ldg(xv + vq + 3 * kLanesPerFrame);
-                acc8(q0, vq); acc8(q1, vq + kLanesPerFrame); acc8(q2, vq + 2 * kLanesPerFrame); acc8(q3, vq + 3 * kLanesPerFrame);
+                for (int i = 0; i < 8; ++i) ww[i] = s_win[j0 + i];
+              } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const int j = j0 + i; const bool in = (unsigned)j < (unsigned)valid; const float wv = s_win[in ? j : 0]; ww[i] = in ? wv : 0.f; }
               }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float dlo = (float)(sext16(w[k]) - thr) - phi;
+                const float dhi = (float)(((int)w[k] >> 16) - thr) - phi;
+                const float alo = ww[2 * k] * dlo, ahi = ww[2 * k + 1] * dhi;
+                e = fmaf(alo, alo, e); m += fabsf(alo);
+                e = fmaf(ahi, ahi, e); m += fabsf(ahi);
+              }
+            };
+            // four 16-byte loads in flight per lane (the samples come from L2)
+            int vq = sub;
 #pragma unroll 1
-              for (; vq < nv; vq += kLanesPerFrame) { const int4 q = __ldg(xv + vq); acc8(q, vq); }
-              jdone = nv << 3;
+            for (; vq + 3 * kLanesPerFrame < nv; vq += 4 * kLanesPerFrame) {
+              const int4 q0 = __ldg(xv + vq), q1 = __ldg(xv + vq + kLanesPerFrame);
+              const int4 q2 = __ldg(xv + vq + 2 * kLanesPerFrame), q3 = __ldg(xv + vq + 3 * kLanesPerFrame);
+              acc8(q0, vq); acc8(q1, vq + kLanesPerFrame); acc8(q2, vq + 2 * kLanesPerFrame); acc8(q3, vq + 3 * kLanesPerFrame);
             }
 #pragma unroll 1
-            for (int j = jdone + sub; j < valid; j += kLanesPerFrame) {
-              const float d = (float)((int)__ldg(x + p + j) - thr) - phi;
-              const float av = s_win[j] * d;
-              e = fmaf(av, av, e); m += fabsf(av);
-            }
+            for (; vq < nv; vq += kLanesPerFrame) { const int4 q = __ldg(xv + vq); acc8(q, vq); }
           }
 #pragma unroll
           for (int o = kLanesPerFrame / 2; o > 0; o >>= 1) {
@@ -1088,19 +1088,19 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       if (c) mbar_wait(&bar_full[s], (uint32_t)(lp & 1));
       const int g = kGroupsPerChunk * c + lane;
       const int base = g * kGroup;
+      if (sh && g == 0 && n > 0) {
+        // the sh samples in front of the utterance belong to its neighbour: overwrite them with copies of sample 0
+        // (min / max unaffected, the sum corrected here, the head sums / bits of group 0 consistent with it)
+        volatile int16_t* fp = reinterpret_cast<volatile int16_t*>(s_ring + (size_t)s * kChunkBytes);
+        const int16_t k0 = fp[sh];
+        for (int i = 0; i < sh; ++i) fp[i] = k0;
+        S -= sh * (int)k0;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slot is refilled by a bulk copy later
+      }
+      asm volatile("" ::: "memory");
       if (base + kGroup <= np) {
         unsigned char* gp = s_ring + (size_t)s * kChunkBytes + lane * (2 * kGroup);
         if (sh) {
-          if (g == 0) {
-            // the sh samples in front of the utterance belong to its neighbour: overwrite them with copies of sample 0
-            // (min / max unaffected, the sum corrected below, the head sums / bits of group 0 consistent with it)
-            volatile int16_t* fp = reinterpret_cast<volatile int16_t*>(gp);
-            const int16_t k0 = fp[sh];
-            for (int i = 0; i < sh; ++i) fp[i] = k0;
-            S -= sh * (int)k0;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slot is refilled by a bulk copy later
-          }
-          asm volatile("" ::: "memory");
           // head of the group: sums over its first sh samples (one masked vector)
           const int4 q = *reinterpret_cast<const int4*>(gp);
           const uint32_t x0 = (uint32_t)q.x & hmask[0], x1 = (uint32_t)q.y & hmask[1], x2 = (uint32_t)q.z & hmask[2], x3 = (uint32_t)q.w & hmask[3];
@@ -1137,9 +1137,8 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       } else if (base < np) {
         // the partial last group, one sample at a time (valid stream positions only)
         int s1 = 0, h1s = 0; long long s2 = 0, h2s = 0;
-        const int lo = max(base, sh);
 #pragma unroll 1
-        for (int i = lo; i < np; ++i) {
+        for (int i = base; i < np; ++i) {
           const int k = at_pos(i); s1 += k; s2 += (long long)k * k; mn = min(mn, k); mx = max(mx, k);
           if (i < base + sh) { h1s += k; h2s += (long long)k * k; }
         }
@@ -1371,23 +1370,47 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
             s1 = (long long)(k1 - fl * thr);
             s2 = k2 - 2ll * thr * (long long)k1 + (long long)fl * thr2;
           } else {
-            long long k1 = 0, k2 = 0;           // sum k, sum k^2 over the frame (stream positions ps .. qs)
+            // sum k, sum k^2 over stream positions [ps, qs): whole groups from their records, the two ragged ends as
+            // "head" sums -- the first r samples of a group, straight from the ring with the byte-plane dot products
+            // of pass A on whole vectors and one masked vector (a frame edge costs <= 8 vector steps, not <= 63 samples)
+            long long k1 = 0, k2 = 0;
             const int ps = p + sh, qs = ps + fl;
-            const int ga = (ps + kGroup - 1) / kGroup, gb = qs / kGroup;
-            auto direct = [&](int i0, int i1) {
+            const int ga = ps / kGroup, gb = qs / kGroup;
 #pragma unroll 1
-              for (int i = i0; i < i1; ++i) { const int k = at_pos(i); k1 += k; k2 += (long long)k * k; }
-            };
-            if (ga > gb) direct(ps, qs);
-            else {
-              for (int g = ga; g < gb; ++g) {
-                const unsigned long long pk = gsum[g];
-                k2 += (long long)(pk >> 24);
-                k1 += (long long)unpack1(pk);
-              }
-              direct(ps, ga * kGroup);
-              direct(gb * kGroup, qs);
+            for (int g = ga; g < gb; ++g) {
+              const unsigned long long pk = gsum[g];
+              k2 += (long long)(pk >> 24);
+              k1 += (long long)unpack1(pk);
             }
+            auto head = [&](int g, int r, long long sign) {
+              const unsigned char* gp = chunk_ptr(g >> 5) + (g & 31) * (2 * kGroup);
+              int hh = 0, hl = 0, sumh = 0;
+              uint32_t ll = 0, sl = 0;
+              const int nv = r >> 3, rem = r & 7;
+#pragma unroll 1
+              for (int v = 0; v <= nv; ++v) {
+                if (v == nv && rem == 0) break;
+                int4 q = *reinterpret_cast<const int4*>(gp + 16 * v);
+                if (v == nv) {          // the ragged vector: keep its first rem samples
+                  const uint32_t m0 = rem >= 2 ? 0xffffffffu : 0x0000ffffu;
+                  const uint32_t m1 = rem >= 4 ? 0xffffffffu : (rem == 3 ? 0x0000ffffu : 0u);
+                  const uint32_t m2 = rem >= 6 ? 0xffffffffu : (rem == 5 ? 0x0000ffffu : 0u);
+                  const uint32_t m3 = rem == 7 ? 0x0000ffffu : 0u;
+                  q.x &= m0; q.y &= m1; q.z &= m2; q.w &= m3;
+                }
+                const uint32_t h0 = __byte_perm((uint32_t)q.x, (uint32_t)q.y, 0x7531), l0 = __byte_perm((uint32_t)q.x, (uint32_t)q.y, 0x6420);
+                const uint32_t h1 = __byte_perm((uint32_t)q.z, (uint32_t)q.w, 0x7531), l1 = __byte_perm((uint32_t)q.z, (uint32_t)q.w, 0x6420);
+                hh = dp4a_ss((int)h0, (int)h0, hh); hh = dp4a_ss((int)h1, (int)h1, hh);
+                hl = dp4a_su((int)h0, l0, hl);      hl = dp4a_su((int)h1, l1, hl);
+                ll = dp4a_uu(l0, l0, ll);           ll = dp4a_uu(l1, l1, ll);
+                sumh = dp4a_ss((int)h0, 0x01010101, sumh); sumh = dp4a_ss((int)h1, 0x01010101, sumh);
+                sl = dp4a_uu(l0, 0x01010101u, sl);  sl = dp4a_uu(l1, 0x01010101u, sl);
+              }
+              k1 += sign * (long long)(256 * sumh + (int)sl);
+              k2 += sign * ((long long)hh * 65536 + (long long)hl * 512 + (long long)ll);
+            };
+            if (qs & (kGroup - 1)) head(gb, qs & (kGroup - 1), 1);
+            if (ps & (kGroup - 1)) head(ga, ps & (kGroup - 1), -1);
             s1 = k1 - (long long)fl * thr;
             s2 = k2 - 2ll * thr * k1 + (long long)fl * thr2;
             zc = count_changes(s_bits, ps, qs);

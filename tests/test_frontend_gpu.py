@@ -365,13 +365,18 @@ def test_config4_geometries_match_the_oracle(ctx, fl, fs):
     utts = [synth.utterance_pcm(300 + i, n, seed0=17) for i, n in enumerate(lens)]
     samples, off = pack(utts)                                     # packed CSR: odd lengths, arbitrary alignment
     win = ("rectangular", "hamming", "hanning")[(fl + fs) % 3]
-    res = batch.frontend_batch(samples, off, fl, fs, win, emit_epd_lists=True, ctx=ctx)
-    for b, u in enumerate(utts):
-        r = fo.frontend_utterance(u, fl, fs, win)
-        assert (int(res.start[b]), int(res.end[b]), int(res.n_frames[b])) == (r["start"], r["end"], len(r["zcr"])), (fl, fs, b)
-        e, m, z = res.frames(b)
-        assert np.array_equal(z.astype(np.float64), r["zcr"]), (fl, fs, b)
-        assert np.allclose(e, r["energy"], rtol=RTOL_F32, atol=0) and np.allclose(m, r["magnitude"], rtol=RTOL_F32, atol=0), (fl, fs, b)
-        el, zl = res.epd_lists(b)
-        assert np.array_equal(zl.astype(np.float64), r["zcr_list"]) and np.allclose(el, r["energy_list"], rtol=RTOL_EPD, atol=0)
-        assert_stats_close(res.stats[b], r["stats"], r)
+    refs = [fo.frontend_utterance(u, fl, fs, win) for u in utts]
+    for variant in (-1, PIPE, RESIDENT):          # the automatic route, and both kernels forced (PIPE falls back where it does not fit)
+        ctx.set_tuning("pcm_variant", variant)
+        try:
+            res = batch.frontend_batch(samples, off, fl, fs, win, emit_epd_lists=True, ctx=ctx)
+        finally:
+            ctx.set_tuning("pcm_variant", -1)
+        for b, r in enumerate(refs):
+            assert (int(res.start[b]), int(res.end[b]), int(res.n_frames[b])) == (r["start"], r["end"], len(r["zcr"])), (fl, fs, b, variant)
+            e, m, z = res.frames(b)
+            assert np.array_equal(z.astype(np.float64), r["zcr"]), (fl, fs, b, variant)
+            assert np.allclose(e, r["energy"], rtol=RTOL_F32, atol=0) and np.allclose(m, r["magnitude"], rtol=RTOL_F32, atol=0), (fl, fs, b, variant)
+            el, zl = res.epd_lists(b)
+            assert np.array_equal(zl.astype(np.float64), r["zcr_list"]) and np.allclose(el, r["energy_list"], rtol=RTOL_EPD, atol=0)
+            assert_stats_close(res.stats[b], r["stats"], r)
