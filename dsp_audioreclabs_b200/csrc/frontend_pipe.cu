@@ -59,7 +59,9 @@ constexpr int kStreamThreads = 32 * kStreamWarps;
 constexpr int kDescRing = 64;              // > max ring slots: the producer can never lap a reader
 constexpr int kMaxRingSlots = 56;
 constexpr int kRecHdr = 128;
-constexpr int kKeyRegs = 13;               // EPD frames per lane whose float keys stay in registers (416 frames = 1.2 s at 256 / 128)
+// EPD frames per lane whose float keys stay in registers: 416 frames = 1.2 s at 256 / 128 for the specialised instantiation
+// (its code size is what its speed hangs on), 704 frames for the general one (1 s at a hop of 64)
+template <bool kChain> constexpr int key_regs() { return kChain ? 13 : 22; }
 constexpr int kLanesPerFrame = 8;          // generic windowed pass: lanes cooperating on one frame
 
 // per-group record of pass B (s_meta): bits 0-6 sign changes inside the group, then the sign bits of its samples
@@ -193,16 +195,22 @@ __device__ __forceinline__ int count_changes(const uint32_t* bits, int p, int q)
     c += __popc((cur ^ (cur >> 1)) & 0x7fffffffu);
     return c;
   }
+  // pairs (i, i + 1) for i in [p, q - 2]: bit i of cur ^ (the string shifted down by one); the two end words masked,
+  // the words in between whole, each word loaded once
   const int last = q - 2;
   const int w0 = p >> 5, w1 = last >> 5;
+  const uint32_t mfirst = 0xffffffffu << (p & 31), mlast = 0xffffffffu >> (31 - (last & 31));
+  uint32_t cur = bits[w0], nxt = bits[w0 + 1];
+  uint32_t x = cur ^ __funnelshift_r(cur, nxt, 1);
+  if (w0 == w1) return __popc(x & mfirst & mlast);
+  c = __popc(x & mfirst);
 #pragma unroll 1
-  for (int w = w0; w <= w1; ++w) {
-    const uint32_t cur = bits[w], nxt = bits[w + 1];
-    uint32_t x = cur ^ __funnelshift_r(cur, nxt, 1);
-    if (w == w0) x &= 0xffffffffu << (p & 31);
-    if (w == w1) x &= 0xffffffffu >> (31 - (last & 31));
-    c += __popc(x);
+  for (int w = w0 + 1; w < w1; ++w) {
+    cur = nxt; nxt = bits[w + 1];
+    c += __popc(cur ^ __funnelshift_r(cur, nxt, 1));
   }
+  cur = nxt; nxt = bits[w1 + 1];
+  c += __popc((cur ^ __funnelshift_r(cur, nxt, 1)) & mlast);
   return c;
 }
 
@@ -531,7 +539,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
     auto tick = [&](int i) { if (a.prof) { const long long t = clock64(); tp[i] += t - tprev; tprev = t; } };
     for (int it = 0;; ++it) {
       const int batch = kBatchMode ? (it & 1) : 0;
-      unsigned char* rec = smem + L.rec + (size_t)(kBatchMode ? batch * kBatch + twid : twid) * L.rec_bytes;
+      // nb = records per batch = tail warps at work (7 unless the per-utterance records of a many-frame geometry leave
+      // room for fewer: pipe_kernel_plan); the other tail warps only keep the batch barriers' head counts
+      const int nb = kBatchMode ? (nrec >> 1) : nrec;
+      unsigned char* rec = smem + L.rec + (size_t)(kBatchMode ? batch * nb + min(twid, nb - 1) : twid) * L.rec_bytes;
       int* r_int = reinterpret_cast<int*>(rec);
       double* r_dbl = reinterpret_cast<double*>(rec + 64);
       double* r_e = reinterpret_cast<double*>(rec + L.rec_e);
@@ -541,9 +552,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       float* s_fm = reinterpret_cast<float*>(rec + L.rec_fm);
       if constexpr (kBatchMode) bar_sync(kBarBatchFull + batch, kBatchBarThreads);
       else bar_sync(kBarRecFull + twid, kRecBarThreads);
-      const int u = r_int[0];
+      int u = r_int[0];
       if constexpr (kBatchMode) {
         if (u == -2) break;                                   // the closing batch: every tail warp leaves
+        if (twid >= nb) u = -1;                               // a tail warp without a record slot
         if (u < 0) { __syncwarp(); bar_arrive(kBarBatchEmpty + batch, kBatchBarThreads); continue; }   // padding of the last batch
       } else {
         if (u < 0) break;
@@ -561,6 +573,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
         const bool top = v >= (double)(f1 - 1);
         int rank = top ? f1 - 1 : (int)floor(v);
         // float projections of the energies (monotone); kept in registers for the usual sizes
+        constexpr int kKeyRegs = key_regs<kChain>();
         const bool in_regs = f1 <= 32 * kKeyRegs;
         uint32_t key[kKeyRegs];
         uint32_t kmin = 0xffffffffu, kmax = 0u;
@@ -993,7 +1006,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
       if (a.out.stats && f2 > 0) {
         float* stats = a.out.stats + (int64_t)u * kStats;
         if (f2 <= 32 * 6) tail_stats_regs<6>(s_fe + zbase, s_fm + zbase, r_zf + zbase, f2, stats);
-        else if (f2 <= 32 * 13) tail_stats_regs<13>(s_fe + zbase, s_fm + zbase, r_zf + zbase, f2, stats);
+        else if (f2 <= 32 * key_regs<kChain>()) tail_stats_regs<key_regs<kChain>()>(s_fe + zbase, s_fm + zbase, r_zf + zbase, f2, stats);
         else {
           float st[5];
           warp_stats([&](int i) { return s_fe[zbase + i]; }, f2, st);
@@ -1030,6 +1043,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
   // STREAM WARPS
   // =========================================================================================
   const int swid = wid, stid = tid;
+  const int nbs = kBatchMode ? (nrec >> 1) : nrec;       // records per batch (pipe_kernel_plan)
   int useq = 0, cslot = 0, clap = 0, rec_id = 0, rec_lap = 0;
   long long sp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sprev = clock64();
   auto stick = [&](int i) { if (a.prof) { const long long t = clock64(); sp[i] += t - sprev; sprev = t; } };
@@ -1044,11 +1058,11 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
     int* r_int = reinterpret_cast<int*>(rec);
     // record slot hand-off with the tail warps: per record, or (batch mode) per batch of kBatch records
     auto rec_acquire = [&]() {
-      if constexpr (kBatchMode) { if (rec_lap > 0 && rec_id % kBatch == 0) bar_sync(kBarBatchEmpty + rec_id / kBatch, kBatchBarThreads); }
+      if constexpr (kBatchMode) { if (rec_lap > 0 && rec_id % nbs == 0) bar_sync(kBarBatchEmpty + rec_id / nbs, kBatchBarThreads); }
       else { if (rec_lap > 0) bar_sync(kBarRecEmpty + rec_id, kRecBarThreads); }
     };
     auto rec_publish = [&]() {
-      if constexpr (kBatchMode) { if (rec_id % kBatch == kBatch - 1) bar_arrive(kBarBatchFull + rec_id / kBatch, kBatchBarThreads); }
+      if constexpr (kBatchMode) { if (rec_id % nbs == nbs - 1) bar_arrive(kBarBatchFull + rec_id / nbs, kBatchBarThreads); }
       else bar_arrive(kBarRecFull + rec_id, kRecBarThreads);
       if (++rec_id == nrec) { rec_id = 0; ++rec_lap; }
     };
@@ -1332,8 +1346,16 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
         return __popc((E ^ O) & m1) + __popc((O ^ (E >> 1)) & m2);
       };
       auto unpack1 = [](unsigned long long pk) { return ((int)((uint32_t)pk << 8)) >> 8; };
+      // ragged-edge geometries have few, long frames (98 of 1,102 samples at the reference's default): TWO threads per
+      // frame there, each taking one edge, half of the whole groups and half of the bit string; one exchange per frame
+      const bool pair = !kChain && edges;
+      const int fstep = pair ? kStreamThreads / 2 : kStreamThreads;
 #pragma unroll 1
-      for (int f = stid; f < fmax; f += kStreamThreads) {
+      for (int f0 = 0; f0 < fmax; f0 += fstep) {
+        const int f = f0 + (pair ? (stid >> 1) : stid);
+        const int half = pair ? (stid & 1) : 0;
+        const unsigned act = __ballot_sync(0xffffffffu, f < nfull);     // the lanes that reach the pair exchange below
+        if (f >= fmax) continue;
         const int p = f * fs;
         int zc = 0;
         int hb0 = 0, hb1 = 0, hbp = 0, hbl = 0;     // sign bits of the frame's samples 0, 1, fl-2, fl-1
@@ -1376,8 +1398,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
             long long k1 = 0, k2 = 0;
             const int ps = p + sh, qs = ps + fl;
             const int ga = ps / kGroup, gb = qs / kGroup;
+            const int gmid = pair ? (ga + gb + 1) >> 1 : gb;
 #pragma unroll 1
-            for (int g = ga; g < gb; ++g) {
+            for (int g = half ? gmid : ga; g < (half ? gb : gmid); ++g) {
               const unsigned long long pk = gsum[g];
               k2 += (long long)(pk >> 24);
               k1 += (long long)unpack1(pk);
@@ -1409,14 +1432,20 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
               k1 += sign * (long long)(256 * sumh + (int)sl);
               k2 += sign * ((long long)hh * 65536 + (long long)hl * 512 + (long long)ll);
             };
-            if (qs & (kGroup - 1)) head(gb, qs & (kGroup - 1), 1);
-            if (ps & (kGroup - 1)) head(ga, ps & (kGroup - 1), -1);
+            // (this branch always runs paired; both halves execute the same instructions on their own edge / range)
+            {
+              const int hr = (half ? qs : ps) & (kGroup - 1);
+              if (hr) head(half ? gb : ga, hr, half ? 1 : -1);
+              // sign changes at the pairs (i, i + 1), i in [ps, qs - 1): split at the middle sample
+              const int pmid = (ps + qs) >> 1;
+              zc = count_changes(s_bits, half ? pmid : ps, half ? qs : pmid + 1);
+              k1 += __shfl_xor_sync(act, k1, 1); k2 += __shfl_xor_sync(act, k2, 1); zc += __shfl_xor_sync(act, zc, 1);
+            }
             s1 = k1 - (long long)fl * thr;
             s2 = k2 - 2ll * thr * k1 + (long long)fl * thr2;
-            zc = count_changes(s_bits, ps, qs);
             hb0 = bit_at(s_bits, ps); hb1 = bit_at(s_bits, ps + 1); hbl = bit_at(s_bits, qs - 1); hbp = bit_at(s_bits, qs - 2);
           }
-          if (f < f1) {
+          if (f < f1 && half == 0) {
             // exact integer sums of d = k - thr, then sum (d - phi)^2 in three roundings
             const double t1 = 2.0 * phi_d * (double)s1, t2 = (double)fl * phi_d * phi_d;
             const double ep = ((double)s2 - t1) + t2;
@@ -1427,7 +1456,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
             if (a.out.epd_zcr) a.out.epd_zcr[eo + f] = (float)zc;
           }
         }
-        if (f < f2full) {
+        if (f < f2full && half == 0) {
           const int valid = min(fl, n - p);
           int zf;
           if (f < nfull && !(hann && fl <= 2)) {
@@ -1458,16 +1487,16 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
   if constexpr (kBatchMode) {
     // pad the open batch with "skip" records, then one closing batch that makes every tail warp leave
     auto mark = [&](int code) {
-      if (rec_lap > 0 && rec_id % kBatch == 0) bar_sync(kBarBatchEmpty + rec_id / kBatch, kBatchBarThreads);
+      if (rec_lap > 0 && rec_id % nbs == 0) bar_sync(kBarBatchEmpty + rec_id / nbs, kBatchBarThreads);
       if (stid == 0) *reinterpret_cast<int*>(smem + L.rec + (size_t)rec_id * L.rec_bytes) = code;
       __syncwarp();
-      if (rec_id % kBatch == kBatch - 1) bar_arrive(kBarBatchFull + rec_id / kBatch, kBatchBarThreads);
+      if (rec_id % nbs == nbs - 1) bar_arrive(kBarBatchFull + rec_id / nbs, kBatchBarThreads);
       if (++rec_id == nrec) { rec_id = 0; ++rec_lap; }
     };
 #pragma unroll 1
-    while (rec_id % kBatch != 0) mark(-1);
+    while (rec_id % nbs != 0) mark(-1);
 #pragma unroll 1
-    for (int k = 0; k < kBatch; ++k) mark(-2);
+    for (int k = 0; k < nbs; ++k) mark(-2);
     return;
   }
   // tell the tail warps to stop: one terminator record each
@@ -1490,16 +1519,21 @@ bool pipe_kernel_plan(int64_t max_len, int cap_frames, int fl, size_t smem_limit
   const int chunks = (int)std::max<int64_t>((max_len + 7 + kChunkSamples - 1) / kChunkSamples, 1);   // + the <= 7 samples below a misaligned start
   const int capG = chunks * kGroupsPerChunk;
   if (kBatchMode) {
-    // two batches of records; the ring keeps the utterance in flight plus at least two chunks of the next one
-    const int nrec = 2 * kBatch;
-    const PipeLayout fixed = make_pipe_layout(0, capG, cap_frames, fl, nrec);
-    const long long room = (long long)smem_limit - fixed.total - 1024;
-    int R = (int)(room / (kChunkBytes + 16));
-    if (R > kMaxRingSlots) R = kMaxRingSlots;
-    if (R < chunks + 2) return false;     // (a quarter of the next utterance in flight is typical: 1 s clips get 39 slots for 22 chunks)
-    plan->ring_slots = R; plan->n_rec = nrec; plan->cap_groups = capG;
-    plan->smem = (size_t)make_pipe_layout(R, capG, cap_frames, fl, nrec).total;
-    return true;
+    // two batches of records, as many per batch (= tail warps at work) as leave the ring the utterance in flight plus
+    // at least two chunks of the next one: 7 for the usual geometries, fewer when hops under ~100 samples make the
+    // per-utterance records large (64/32 at 1 s: 1,377 frames, 16.6 KB per record -> 2 per batch)
+    for (int nb = kBatch; nb >= 1; --nb) {
+      const int nrec = 2 * nb;
+      const PipeLayout fixed = make_pipe_layout(0, capG, cap_frames, fl, nrec);
+      const long long room = (long long)smem_limit - fixed.total - 1024;
+      int R = (int)(room / (kChunkBytes + 16));
+      if (R > kMaxRingSlots) R = kMaxRingSlots;
+      if (R < chunks + 2) continue;
+      plan->ring_slots = R; plan->n_rec = nrec; plan->cap_groups = capG;
+      plan->smem = (size_t)make_pipe_layout(R, capG, cap_frames, fl, nrec).total;
+      return true;
+    }
+    return false;
   }
   for (int nrec = kMaxTailWarps; nrec >= 2; --nrec) {
     const PipeLayout fixed = make_pipe_layout(0, capG, cap_frames, fl, nrec);
