@@ -359,6 +359,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = ddist.bind_to_gpu_numa(local)         # before any pinned allocation: first touch places the staging buffers
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -617,7 +618,7 @@ def run_ours(args):
                        "l2_policy": f"input {samples.numel() * 2 / 1e9:.2f} GB per pass >> 126 MB L2 (no flush needed)"},
             "roofline": roofline, "pipeline": pipeline, "frontend_only": frontend_only, "per_window": per_window,
             "per_config": per_config, "clocks": clocks,
-            "e2e": e2e, "gpu_launches": int(launches), "parity": parity,
+            "e2e": e2e, "gpu_launches": int(launches), "parity": parity, "numa": numa,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single(args.cpu_utts)

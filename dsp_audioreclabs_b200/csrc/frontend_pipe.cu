@@ -956,10 +956,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
                 e = fmaf(ahi, ahi, e); m += fabsf(ahi);
               }
             };
-            // four 16-byte loads in flight per lane (the samples come from L2)
+            // four 16-byte loads in flight per lane (the samples come from L2); the specialised 256 / 128 instantiation
+            // comes here for the one or two zero-padded frames behind its chain only: one compact loop there, its
+            // hot code has to stay inside the instruction cache
             int vq = sub;
 #pragma unroll 1
-            for (; vq + 3 * kLanesPerFrame < nv; vq += 4 * kLanesPerFrame) {
+            for (; !kChain && vq + 3 * kLanesPerFrame < nv; vq += 4 * kLanesPerFrame) {
               const int4 q0 = __ldg(xv + vq), q1 = __ldg(xv + vq + kLanesPerFrame);
               const int4 q2 = __ldg(xv + vq + 2 * kLanesPerFrame), q3 = __ldg(xv + vq + 3 * kLanesPerFrame);
               acc8(q0, vq); acc8(q1, vq + kLanesPerFrame); acc8(q2, vq + 2 * kLanesPerFrame); acc8(q3, vq + 3 * kLanesPerFrame);

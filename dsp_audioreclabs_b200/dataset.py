@@ -43,6 +43,12 @@ def decode_tree_packed(data_dir, threads=None):
     return groups, readable, paths, labels, class_names
 
 
+def effective_channels(n_channels):
+    """load_wav only down-mixes TWO channels (src/audio_processing.py:43-44); a file with any other channel count is
+    processed as the flat interleaved array it is stored as, i.e. as one channel."""
+    return 2 if int(n_channels) == 2 else 1
+
+
 def decode_tree(data_dir):
     """-> (clips [(pcm, channels)], labels, class_names, paths) of the readable files, as views into the
     packed staging buffers."""
@@ -65,7 +71,7 @@ def features_for_groups(groups, n_files, frame_length, frame_shift, window_type=
         if not len(g.index):
             continue
         res = batch.frontend_batch(g.samples, g.offsets, frame_length, frame_shift, window_type, do_endpoint_detection,
-                                   energy_high_ratio, energy_low_ratio, zcr_threshold_ratio, channels=g.channels,
+                                   energy_high_ratio, energy_low_ratio, zcr_threshold_ratio, channels=effective_channels(g.channels),
                                    emit_frames=False, lengths=g.lengths, ctx=ctx)
         X[g.index] = res.stats
         ok[g.index] = (res.status & 0xff) == 0
@@ -84,7 +90,7 @@ def features_for_clips(clips, frame_length, frame_shift, window_type="hamming", 
     for (_, ch), idx in groups.items():
         samples, offsets, lengths = batch.pack_aligned([clips[i][0] for i in idx])
         res = batch.frontend_batch(samples, offsets, frame_length, frame_shift, window_type, do_endpoint_detection,
-                                   energy_high_ratio, energy_low_ratio, zcr_threshold_ratio, channels=ch,
+                                   energy_high_ratio, energy_low_ratio, zcr_threshold_ratio, channels=effective_channels(ch),
                                    emit_frames=False, lengths=lengths, ctx=ctx)
         X[idx] = res.stats
         ok[idx] = (res.status & 0xff) == 0

@@ -20,6 +20,37 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin this process (its threads and, by first touch, the pinned staging buffers it allocates afterwards) to the
+    CPUs of the NUMA node the GPU hangs off: with one process per GPU, eight ranks left on node 0 push all their
+    host->device traffic through one socket's memory controllers (round 1: 0.44 end-to-end efficiency at 8 GPUs).
+    Reads the PCI bus id from the CUDA runtime and the node / cpu list from sysfs.  Returns a dict describing what was
+    done (for the bench line); never raises -- a box without the sysfs entries is left as it is."""
+    import os
+    info = {"gpu": int(device_index), "numa_node": None, "cpus": None, "bound": False}
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"] = len(allowed)
+            info["bound"] = True
+    except Exception as exc:          # noqa: BLE001 -- best effort by design
+        info["error"] = repr(exc)
+    return info
+
+
 def balanced_bounds(n, world):
     """Contiguous ranges [b[r], b[r+1]) of n items, sizes differing by at most one."""
     base, rem = divmod(int(n), int(world))

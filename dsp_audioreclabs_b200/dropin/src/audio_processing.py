@@ -191,11 +191,12 @@ def _tree_pass(tree, cfg):
     results = []
     for g in tree['groups']:
         # dense frame matrices only while they fit the budget (capacity = untrimmed frame counts)
-        n_el = g.lengths.astype(np.int64) // g.channels
+        ch_eff = 2 if g.channels == 2 else 1          # load_wav down-mixes two channels only (:43-44)
+        n_el = g.lengths.astype(np.int64) // ch_eff
         cap = int(np.where(n_el > 0, np.minimum(-(-n_el // fs), -(-np.maximum(n_el - fl, 0) // fs) + 1), 0).sum())
         dense = cap * int(fl) * 8 <= _FRAMES_BUDGET
         results.append(_b.frontend_batch(g.samples, g.offsets, fl, fs, window_type, do_epd, hr, lr, zr,
-                                         channels=g.channels, emit_epd_lists=True, lengths=g.lengths,
+                                         channels=ch_eff, emit_epd_lists=True, lengths=g.lengths,
                                          float64_outputs=True, emit_dense_frames=dense))
         launch_log.append(('tree', len(g.index)))
     while len(_passes) >= _MAX_PASSES:
@@ -252,7 +253,7 @@ def process_audio_file(filepath, frame_length, frame_shift,
         gi, j = tree['slot'][apath]
         g = tree['groups'][gi]
         res = _tree_pass(tree, cfg)[gi]
-        n = int(g.lengths[j]) // g.channels
+        n = int(g.lengths[j]) // (2 if g.channels == 2 else 1)
         if n == 0:
             raise ValueError("zero-size array to reduction operation maximum which has no identity")
         rate = tree['rates'][tree['order'][apath]]
