@@ -419,7 +419,7 @@ def run_ours(args):
             ev_fe[timed][1].record(stream)
         mean, std, knn, _ = models[WINDOWS[i % 3]]
         devapi.zscore_apply_f32(fe.stats, mean, std, out=qn, ctx=ctx)
-        labels[0] = knn.predict(qn)
+        labels[0] = knn.predict(qn, [n_utts] * world) if world > 1 else knn.predict(qn)
 
     with torch.cuda.stream(stream):
         for i in range(max(args.warmup, 3)):

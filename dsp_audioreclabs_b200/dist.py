@@ -166,22 +166,31 @@ class ShardedKNN:
     def train_bytes(self):
         return self.n_total * int(self.train.shape[1]) * self.train.element_size()
 
-    def predict(self, queries_local):
+    def predict(self, queries_local, counts=None):
         """Labels for this rank's queries: the replicated-train path when the train set is small, else the
-        row-sharded exchange (every rank must take the same branch: the choice depends on global sizes only)."""
+        row-sharded exchange (every rank must take the same branch: the choice depends on global sizes only).
+        counts: the per-rank query counts when the caller knows them (see predict_sharded)."""
         if self.train_bytes() <= self.replicate_below:
             return self.predict_replicated(queries_local)
-        return self.predict_sharded(queries_local)
+        return self.predict_sharded(queries_local, counts)
 
-    def predict_sharded(self, queries_local):
+    def predict_sharded(self, queries_local, counts=None):
         """The north-star exchange: all-gather the query features, score ALL queries against the local rows, ONE
         all-gather of the packed per-shard top-k candidates (16 bytes per candidate: the float64 distance, and the
         global row with the label in one int64), merge + vote for the rank's own queries (only their slice of the
         gathered buffer is unpacked)."""
         rank = dist.get_rank(self.group)
         world = dist.get_world_size(self.group)
-        per_rank_q = _all_gather_rows(queries_local.contiguous(), self.group)
-        q_all = torch.cat(per_rank_q, dim=0)
+        if counts is not None and len(set(int(c) for c in counts)) == 1 and int(counts[rank]) == queries_local.shape[0]:
+            # equal, known query counts (a batch sharded evenly): no size exchange, no padding and -- what matters --
+            # no host synchronisation on the step: the whole classify step stays enqueued behind the front end
+            q_all = torch.empty((world * queries_local.shape[0],) + tuple(queries_local.shape[1:]),
+                                dtype=queries_local.dtype, device=queries_local.device)
+            dist.all_gather_into_tensor(q_all, queries_local.contiguous(), group=self.group)
+            per_rank_q = [q_all[r * queries_local.shape[0]:(r + 1) * queries_local.shape[0]] for r in range(world)]
+        else:
+            per_rank_q = _all_gather_rows(queries_local.contiguous(), self.group)
+            q_all = torch.cat(per_rank_q, dim=0)
         d2, idx, lab = self._topk(self.train, self.labels, q_all, self.k, self.index_base)
         if self.n_total >= (1 << 31):
             raise ValueError("row-sharded KNN packs the global row index into 32 bits: at most 2^31 train rows")

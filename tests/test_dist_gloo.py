@@ -49,7 +49,10 @@ def _worker(rank, world, port, out_dir):
     knn.fit(torch.from_numpy(xn[tb[rank]:tb[rank + 1]]), torch.from_numpy(y[tb[rank]:tb[rank + 1]]))
     assert knn.index_base == tb[rank]
     q_local = torch.from_numpy(qn[qb[rank]:qb[rank + 1]])
-    a = knn.predict(q_local).numpy()
+    a = knn.predict_sharded(q_local).numpy()                # the candidate all-gather (sizes exchanged)
+    a2 = knn.predict_sharded(q_local, [len(q_local)] * world).numpy()      # equal counts known to the caller: no size exchange
+    assert np.array_equal(a, a2)
+    assert np.array_equal(knn.predict(q_local).numpy(), a)  # automatic choice (replicated here: the train set is tiny)
     b = knn.predict_replicated(q_local).numpy()
     mean, std = ddist.zscore_stats_allreduce(torch.from_numpy(k["d15/train"][tb[rank]:tb[rank + 1]]))
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), a=a, b=b, lo=qb[rank], hi=qb[rank + 1],
