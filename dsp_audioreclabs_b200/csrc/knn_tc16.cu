@@ -43,12 +43,16 @@ constexpr int kPlaneBytes = kRows * kK * 2;      // one fp16 plane of a tile: 4 
 constexpr int kTileBytes = 2 * kPlaneBytes;      // {hi, lo}: 8 KB
 constexpr int kUnitQ = 2 * kRows;                // queries per work unit
 constexpr int kQBufBytes = 2 * kTileBytes;       // two query blocks
-constexpr int kTStages = 18;                     // 144 KB of train tiles in flight; with the query buffers and the candidate lists the CTA owns its SM (all of TMEM is allocated)
+#ifndef DSP_TC16_SPLIT
+#define DSP_TC16_SPLIT 2            // epilogue warps per (TMEM lane group, query block): 1 = one warp on all 128 columns of a tile, 2 = two on 64 each
+#endif
+constexpr int kSplit = DSP_TC16_SPLIT;
+constexpr int kTStages = kSplit == 1 ? 18 : 16;                     // 144 KB of train tiles in flight; with the query buffers and the candidate lists the CTA owns its SM (all of TMEM is allocated)
 constexpr int kAccStages = 2;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 8 * kSplit;
 constexpr int kTcThreads = 32 * (2 + kEpiWarps);
 constexpr int kTmemCols = 512;
-constexpr int kEpiThreads = 32 * 8;
+constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kListBytes = 2 * kKnnCand * kEpiThreads * 4;     // per-thread candidate lists: scores and indices, [entry][thread]
 constexpr size_t kTcSmem = 2 * kQBufBytes + (size_t)kTStages * kTileBytes + kListBytes + 1024;   // + mbarriers and the TMEM address slot
 // canonical K-major no-swizzle layout: core matrix = 8 rows x 16 bytes (128 B contiguous); the two core matrices along
@@ -344,9 +348,11 @@ knn_tc16_filter_kernel(const unsigned char* __restrict__ qpacked, const unsigned
     }
     __syncwarp();
   } else {
-    // ===== epilogue: TMEM lane group = warp % 4 (hardware rule), query block = (warp - 2) / 4 =====
-    const int lg = warp & 3, h = (warp - 2) >> 2;
-    const int et = tid - 64;                                   // epilogue thread 0..255
+    // ===== epilogue: TMEM lane group = warp % 4 (hardware rule); (warp - 2) / 4 picks the query block and, with two
+    // warps per (lane group, query block), the 64-column half of every tile the warp compares =====
+    const int lg = warp & 3, grp = (warp - 2) >> 2;
+    const int h = kSplit == 1 ? grp : grp >> 1, half = kSplit == 1 ? 0 : grp & 1;
+    const int et = tid - 64;                                   // epilogue thread
     float* l_cd = reinterpret_cast<float*>(smem + 2 * kQBufBytes + (size_t)kTStages * kTileBytes + 1024) + et;     // behind the barrier block
     int* l_ci = reinterpret_cast<int*>(l_cd - et + kKnnCand * kEpiThreads) + et;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(lg * 32) << 16);
@@ -374,35 +380,84 @@ knn_tc16_filter_kernel(const unsigned char* __restrict__ qpacked, const unsigned
         }
         __syncwarp();
       };
-      // two 64-column halves per tile, double-buffered ACROSS tiles: while one half is compared the other is in flight
-      uint32_t va[64], vb[64];
-      wait_epi(&acc_full[as], aph);
-      tc_fence_after();
-      tmem_ld64(lane_addr + (uint32_t)((as * 2 + h) * kRows), va);
-      for (int tb = 0; tb < t_tiles; ++tb) {
-        const int base = tb * kRows;
-        tmem_ld_wait();                                          // first half of tile tb is in registers
-        tmem_ld64(lane_addr + (uint32_t)((as * 2 + h) * kRows + 64), vb);
-        process(va, base);
-        process(va + 32, base + 32);
-        tmem_ld_wait();                                          // second half too: the accumulator stage can be reused
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[as]);
-        if (++as == kAccStages) { as = 0; aph ^= 1u; }
-        if (tb + 1 < t_tiles) {
+      if constexpr (kSplit == 1) {
+        // two 64-column halves per tile, double-buffered ACROSS tiles: while one half is compared the other is in flight
+        uint32_t va[64], vb[64];
+        wait_epi(&acc_full[as], aph);
+        tc_fence_after();
+        tmem_ld64(lane_addr + (uint32_t)((as * 2 + h) * kRows), va);
+        for (int tb = 0; tb < t_tiles; ++tb) {
+          const int base = tb * kRows;
+          tmem_ld_wait();                                          // first half of tile tb is in registers
+          tmem_ld64(lane_addr + (uint32_t)((as * 2 + h) * kRows + 64), vb);
+          process(va, base);
+          process(va + 32, base + 32);
+          tmem_ld_wait();                                          // second half too: the accumulator stage can be reused
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[as]);
+          if (++as == kAccStages) { as = 0; aph ^= 1u; }
+          if (tb + 1 < t_tiles) {
+            wait_epi(&acc_full[as], aph);
+            tc_fence_after();
+            tmem_ld64(lane_addr + (uint32_t)((as * 2 + h) * kRows), va);     // first half of the next tile
+          }
+          process(vb, base + 64);
+          process(vb + 32, base + 96);
+        }
+      } else {
+        // Two warps per (lane group, query block), each on its own 64 columns of every tile with its own candidate list:
+        // four epilogue warps per scheduler hide one another's TMEM-load and min-tree latencies (with two, issue slots
+        // were 28 % busy and the tensor pipe 20 %), the accumulator stage goes back to the MMA thread as soon as the 64
+        // scores are in registers, and the two lists are merged once per work unit.
+        uint32_t va[32], vb[32];
+        for (int tb = 0; tb < t_tiles; ++tb) {
+          const int base = tb * kRows + half * 64;
           wait_epi(&acc_full[as], aph);
           tc_fence_after();
-          tmem_ld64(lane_addr + (uint32_t)((as * 2 + h) * kRows), va);     // first half of the next tile
+          const uint32_t col = (uint32_t)((as * 2 + h) * kRows + half * 64);
+          tmem_ld32(lane_addr + col, va);
+          tmem_ld32(lane_addr + col + 32, vb);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[as]);
+          if (++as == kAccStages) { as = 0; aph ^= 1u; }
+          process(va, base);
+          process(vb, base + 32);
         }
-        process(vb, base + 64);
-        process(vb + 32, base + 96);
       }
-      const int64_t q = (int64_t)u * kUnitQ + h * kRows + lg * 32 + lane;
-      if (q < m) {
+      if constexpr (kSplit == 2) {
+        // merge: the warp of half 0 folds its partner's list (same lane group, same query block: 128 threads up) into its own
+        const int pair_bar = 1 + lg + 4 * h;
+        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+        if (half == 0) {
+          float cd[kC]; int ci[kC];
 #pragma unroll
-        for (int c = 0; c < kKnnCand; ++c) cand_idx[q * kKnnCand + c] = c < kC ? l_ci[c * kEpiThreads] : -1;
-        cand_worst[q] = l_cd[(kC - 1) * kEpiThreads];
+          for (int c = 0; c < kC; ++c) { cd[c] = l_cd[c * kEpiThreads]; ci[c] = l_ci[c * kEpiThreads]; }
+#pragma unroll
+          for (int b = 0; b < kC; ++b) {
+            float d = l_cd[b * kEpiThreads + 128]; int i = l_ci[b * kEpiThreads + 128];
+#pragma unroll
+            for (int c = 0; c < kC; ++c) {          // sorted insertion: carry the displaced entry down the list
+              if (d < cd[c]) { const float td = cd[c]; const int ti = ci[c]; cd[c] = d; ci[c] = i; d = td; i = ti; }
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < kC; ++c) { l_cd[c * kEpiThreads] = cd[c]; l_ci[c * kEpiThreads] = ci[c]; }
+        }
+      }
+      if (half == 0) {
+        const int64_t q = (int64_t)u * kUnitQ + h * kRows + lg * 32 + lane;
+        if (q < m) {
+#pragma unroll
+          for (int c = 0; c < kKnnCand; ++c) cand_idx[q * kKnnCand + c] = c < kC ? l_ci[c * kEpiThreads] : -1;
+          cand_worst[q] = l_cd[(kC - 1) * kEpiThreads];
+        }
+      }
+      if constexpr (kSplit == 2) {
+        // the partner must not re-initialise its list for the next unit before it has been read
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + lg + 4 * h) : "memory");
       }
     }
   }
