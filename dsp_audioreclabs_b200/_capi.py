@@ -91,6 +91,7 @@ SIGNATURES = {
     "dsp_knn_free": (C.c_int, [_P]),
     "dsp_knn_topk_host": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
     "dsp_knn_topk_device": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
+    "dsp_knn_topk_bounded_device": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P]),
     "dsp_knn_predict_host": (C.c_int, [_P, _P, _I64, _P]),
     "dsp_knn_predict_device": (C.c_int, [_P, _P, _I64, _P]),
     "dsp_knn_last_stats": (C.c_int, [_P, C.POINTER(_I64), C.POINTER(_I32)]),

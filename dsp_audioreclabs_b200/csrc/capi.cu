@@ -133,6 +133,7 @@ struct dsp_knn {
   DevBuf tc_train, tc_q, tc_flags;
   DevBuf train64, train32, labels, tnorm, cand_idx, cand_worst, qnorm, redo_list, redo_count, nbr_label, q, o_idx, o_dist, o_lab;
   DevBuf refine_list, refine_thr, surv_count, surv_rows;     // second pass of the D <= 15 path (knn_refine)
+  DevBuf thr0;                                               // bounded calls: per-query start thresholds of the filter
   DevBuf tpacked, tnorm_dense, qpacked, qnorm_chunk, dense_flags, part_d, part_i;
 };
 
@@ -834,7 +835,7 @@ static void knn_release(dsp_knn* k) {
   DevBuf* all[] = {&k->train64, &k->train32, &k->labels, &k->tnorm, &k->cand_idx, &k->cand_worst, &k->qnorm,
                    &k->redo_list, &k->redo_count, &k->nbr_label, &k->q, &k->o_idx, &k->o_dist, &k->o_lab,
                    &k->tpacked, &k->tnorm_dense, &k->qpacked, &k->qnorm_chunk, &k->dense_flags, &k->part_d, &k->part_i,
-                   &k->tc_train, &k->tc_q, &k->tc_flags, &k->refine_list, &k->refine_thr, &k->surv_count, &k->surv_rows};
+                   &k->tc_train, &k->tc_q, &k->tc_flags, &k->refine_list, &k->refine_thr, &k->surv_count, &k->surv_rows, &k->thr0};
   for (DevBuf* b : all) b->release();
 }
 
@@ -916,6 +917,11 @@ int dsp_knn_free(dsp_knn* k) {
 }
 
 int dsp_knn_topk_device(dsp_knn* h, const double* q, int64_t m, int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label) {
+  return dsp_knn_topk_bounded_device(h, q, m, nullptr, nbr_idx, nbr_sqdist, nbr_label);
+}
+
+int dsp_knn_topk_bounded_device(dsp_knn* h, const double* q, int64_t m, const double* bound, int64_t* nbr_idx, double* nbr_sqdist,
+                                int32_t* nbr_label) {
   if (!h || m < 0 || (!q && m)) return fail(DSP_ERR_INVALID, "bad argument");
   if (m == 0) return DSP_OK;
   if (m > INT32_MAX) return fail(DSP_ERR_UNSUPPORTED, "more than 2^31 queries per call");
@@ -928,18 +934,26 @@ int dsp_knn_topk_device(dsp_knn* h, const double* q, int64_t m, int64_t* nbr_idx
     CU(h->qnorm.ensure(sizeof(float) * (size_t)m));
     double err_rel = (double)(h->d + 4) * 1.1920929e-7, err_floor = 0.0;
     float qnorm_limit = 0.f;
+    const float* thr0 = nullptr;       // only the tensor-core filter takes start thresholds; the other scans ignore `bound`
     if (h->tc16) {
       // tensor-core filter; a query outside its range (|q|^2 above knn_tc16_max_norm(), NaN / inf) is scored as the zero
       // vector there and handed to the exhaustive float64 scan by the rerank kernel -- per query, on the device
       CU(h->tc_q.ensure(knn_tc16_packed_bytes(m, true)));
       int* qflags = h->tc_flags.as<int>() + 4;
       CU(knn_tc16_pack(q, m, h->d, true, h->tc_q.p, h->qnorm.as<float>(), qflags, c->stream));
-      CU(knn_tc16_filter(h->tc_q.p, h->tc_train.p, m, h->n, h->k, qflags, h->cand_idx.as<int>(), h->cand_worst.as<float>(),
-                         c->sm_count, c->stream));
-      c->launches += 2;
       err_rel = knn_dense_err_rel(16);
       err_floor = 1.0;
       qnorm_limit = knn_tc16_max_norm();
+      if (bound) {
+        // bounded call (row-sharded KNN): every query's filter starts at the score threshold of its radius
+        CU(h->thr0.ensure(sizeof(float) * (size_t)m));
+        CU(knn_bound_thresholds(bound, h->qnorm.as<float>(), m, err_rel, err_floor, h->thr0.as<float>(), c->stream));
+        thr0 = h->thr0.as<float>();
+        c->launches += 1;
+      }
+      CU(knn_tc16_filter(h->tc_q.p, h->tc_train.p, m, h->n, h->k, qflags, h->cand_idx.as<int>(), h->cand_worst.as<float>(),
+                         c->sm_count, c->stream, thr0));
+      c->launches += 2;
     } else {
       CU(knn_scan(h->dp, h->train32.as<float>(), h->n, q, m, h->d, h->cand_idx.as<int>(), h->cand_worst.as<float>(),
                   h->qnorm.as<float>(), nullptr, c->stream));
@@ -958,13 +972,13 @@ int dsp_knn_topk_device(dsp_knn* h, const double* q, int64_t m, int64_t* nbr_idx
                   h->labels.as<int32_t>(), h->cand_idx.as<int>(), h->cand_worst.as<float>(), h->qnorm.as<float>(),
                   h->tnorm_max, err_rel, err_floor, nbr_idx, nbr_sqdist, nbr_label, h->redo_list.as<int32_t>(),
                   h->redo_count.as<int32_t>(), c->stream, refine_cap ? h->refine_list.as<int32_t>() : nullptr,
-                  h->refine_thr.as<float>(), refine_cap, qnorm_limit));
+                  h->refine_thr.as<float>(), refine_cap, qnorm_limit, thr0 ? bound : nullptr, thr0));
     c->launches += 1;
     if (refine_cap) {
       CU(knn_refine(h->train64.as<double>(), h->train32.as<float>(), h->dp, h->n, q, h->d, h->k, h->index_base,
                     h->labels.as<int32_t>(), h->refine_list.as<int32_t>(), h->refine_thr.as<float>(), refine_cap,
                     h->surv_count.as<int32_t>(), h->surv_rows.as<int32_t>(), h->redo_count.as<int32_t>(),
-                    h->redo_list.as<int32_t>(), nbr_idx, nbr_sqdist, nbr_label, c->sm_count, c->stream));
+                    h->redo_list.as<int32_t>(), nbr_idx, nbr_sqdist, nbr_label, c->sm_count, c->stream, thr0 != nullptr));
       c->launches += 2;
     }
   } else if (h->dense) {

@@ -210,7 +210,8 @@ __global__ void knn_rerank_kernel(const double* __restrict__ train, const float*
                                   int64_t* __restrict__ nbr_idx, double* __restrict__ nbr_sqdist,
                                   int32_t* __restrict__ nbr_label, int32_t* __restrict__ redo_list,
                                   int32_t* __restrict__ redo_count, int32_t* __restrict__ refine_list,
-                                  float* __restrict__ refine_thr, int refine_cap, float qnorm_limit) {
+                                  float* __restrict__ refine_thr, int refine_cap, float qnorm_limit,
+                                  const double* __restrict__ bound, const float* __restrict__ thr0) {
   const int64_t qi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (qi >= m) return;
   const double* q = queries + qi * d;
@@ -226,39 +227,44 @@ __global__ void knn_rerank_kernel(const double* __restrict__ train, const float*
     cd[s] = dd; cidx[s] = i;
   }
   const int kk = (int)min((int64_t)k, n);
-  bool ok = (nc >= kk);
   // a query outside the tensor-core filter's range was scored as the zero vector (knn_tc16_pack_kernel): its candidates
   // mean nothing -- exhaustive float64 scan
   const bool in_range = !(qnorm_limit > 0.f) || qnorm[qi] <= qnorm_limit;
-  if (!in_range) { ok = false; nc = 0; }
-  if (ok && n > kKnnCand) {
-    // Every row that is NOT a candidate has score >= the worst kept score W, and the scan's score of row t is within
-    // err_rel * (|q| + |t|)^2 of |t|^2 - 2 q.t (the roundings act on terms bounded by (|q| + |t|)^2).  A row that
-    // could displace a candidate has exact distance <= D_k (the k-th exact candidate distance), hence |t| <= |q| +
-    // sqrt(D_k) by the triangle inequality, hence score error <= err_rel * (2 |q| + sqrt(D_k))^2 -- the norm of the
-    // rows that matter, not of the largest row of the train set (which made outliers in the train set reject 3 % of
-    // the queries of real feature sets).  So: D_k < W + |q|^2 - err certifies the candidates.
+  if (!in_range) nc = 0;
+  // T = the radius inside which no row may be missing: the k-th exact candidate distance, and / or the caller's upper
+  // bound U on the query's k-th distance (bounded calls: the shard is only asked for its rows within U, it may hold
+  // fewer than k of them).  W = the score every row that is not a candidate is known to reach: the worst kept score once
+  // the list has filled, and the threshold the filter started at.
+  const double U = bound ? bound[qi] : INFINITY;
+  const double Dk = nc >= kk ? cd[kk - 1] : INFINITY;
+  const double T = fmin(Dk, U);
+  bool ok = in_range && T < INFINITY;
+  if (ok && (n > kKnnCand || bound)) {
+    // The scan's score of row t is within err_rel * (|q| + |t|)^2 of |t|^2 - 2 q.t (the roundings act on terms bounded by
+    // (|q| + |t|)^2).  A row that could still matter has exact distance <= T, hence |t| <= |q| + sqrt(T) by the triangle
+    // inequality, hence score error <= err_rel * (2 |q| + sqrt(T))^2 -- the norm of the rows that matter, not of the
+    // largest row of the train set (which made outliers in the train set reject 3 % of the queries of real feature
+    // sets).  So: T < W + |q|^2 - err certifies that nothing inside the radius is missing.
     const float qn = qnorm[qi];
-    const double bound = 2.0 * (double)sqrtf(qn) * 1.0000002 + sqrt(cd[kk - 1]);
+    const double brad = 2.0 * (double)sqrtf(qn) * 1.0000002 + sqrt(T);
     // err_floor: the split-fp16 filter also has an ABSOLUTE error (fp16 subnormal spacing of the lo planes), covered
     // by evaluating the relative bound at no less than err_floor
-    const double err = err_rel * fmax(bound * bound, err_floor);
-    const double lower = (double)cand_worst[qi] + (double)qn - err;
-    ok = cd[kk - 1] < lower;
+    const double err = err_rel * fmax(brad * brad, err_floor);
+    const double W = fmin((double)cand_worst[qi], thr0 ? (double)thr0[qi] : INFINITY);
+    ok = T < W + (double)qn - err;
   }
   if (!ok) {
-    // Not certified.  With k candidates in hand their k-th exact distance D bounds the true k-th distance from above:
-    // every row that can still matter has exact distance <= D, i.e. fp32 score <= D - |q|^2 + err32 -- the threshold of
-    // the second pass (knn_refine_collect_kernel); without a refine list, or past its capacity: exhaustive float64 scan
-    if (refine_list && nc >= kk && train32) {
+    // Not certified.  Every row that can still matter has exact distance <= T, i.e. fp32 score <= T - |q|^2 + err32 -- the
+    // threshold of the second pass (knn_refine_collect_kernel); without a refine list, without a radius, or past the
+    // list's capacity: exhaustive float64 scan
+    if (refine_list && in_range && T < INFINITY && train32) {
       const int slot = atomicAdd(redo_count + 1, 1);
       if (slot < refine_cap) {
-        // rows that matter have |t| <= |q| + sqrt(D_k) (above): the fp32 scan's error on them
         const float qn = qnorm[qi];
-        const double bound = 2.0 * (double)sqrtf(qn) * 1.0000002 + sqrt(cd[kk - 1]);
-        const double err32 = (double)(d + 4) * 1.1920929e-7 * bound * bound;
+        const double brad = 2.0 * (double)sqrtf(qn) * 1.0000002 + sqrt(T);
+        const double err32 = (double)(d + 4) * 1.1920929e-7 * brad * brad;
         refine_list[slot] = (int)qi;
-        refine_thr[slot] = __double2float_ru(cd[kk - 1] - (double)qn + err32);
+        refine_thr[slot] = __double2float_ru(T - (double)qn + err32);
         return;
       }
     }
@@ -266,7 +272,13 @@ __global__ void knn_rerank_kernel(const double* __restrict__ train, const float*
     redo_list[slot] = (int)qi;
     return;
   }
-  for (int c = 0; c < kk; ++c) {
+  const int have = min(kk, nc);
+  for (int c = have; c < kk; ++c) {         // a bounded call whose shard holds fewer than k rows inside the radius
+    if (nbr_idx) nbr_idx[qi * k + c] = -1;
+    if (nbr_sqdist) nbr_sqdist[qi * k + c] = INFINITY;
+    if (nbr_label) nbr_label[qi * k + c] = -1;
+  }
+  for (int c = 0; c < have; ++c) {
     if (nbr_idx) nbr_idx[qi * k + c] = index_base + cidx[c];
     if (nbr_sqdist) nbr_sqdist[qi * k + c] = cd[c];
     if (nbr_label) nbr_label[qi * k + c] = labels[cidx[c]];
@@ -629,6 +641,22 @@ __global__ void knn_iota_kernel(int32_t* list, int32_t* count, int64_t m) {
 // more than kRefineCap survivors goes to the exhaustive scan.  Work items = (block of 128 rejected queries) x (part of
 // the train rows), persistent grid, everything sized on the device: no host round trip.
 // ---------------------------------------------------------------------------------------
+__global__ void knn_bound_thresholds_kernel(const double* __restrict__ bound, const float* __restrict__ qnorm, int64_t m,
+                                            double err_rel, double err_floor, float* __restrict__ thr0) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const double U = bound[i];
+  float t = INFINITY;
+  if (U < INFINITY && U >= 0.0) {
+    const double qn = (double)qnorm[i];
+    const double brad = 2.0 * sqrt(qn) * 1.0000002 + sqrt(U);
+    const double err = err_rel * fmax(brad * brad, err_floor);
+    // twice the error: once for the rows' scores, once so that the rerank certificate (strict) holds at T = U
+    t = __double2float_ru((U - qn + 2.0 * err) * (U - qn + 2.0 * err >= 0.0 ? 1.000001 : 0.999999));
+  }
+  thr0[i] = t;
+}
+
 constexpr int kRefineCap = 64;
 constexpr int kRefineThreads = 128;
 
@@ -698,14 +726,14 @@ __global__ void knn_refine_finish_kernel(const double* __restrict__ train, const
                                          const int32_t* __restrict__ refine_list, int32_t* __restrict__ counts, int refine_cap,
                                          const int32_t* __restrict__ surv_count, const int32_t* __restrict__ surv_rows,
                                          int64_t* __restrict__ nbr_idx, double* __restrict__ nbr_sqdist,
-                                         int32_t* __restrict__ nbr_label, int32_t* __restrict__ redo_list) {
+                                         int32_t* __restrict__ nbr_label, int32_t* __restrict__ redo_list, bool allow_short) {
   const int lane = threadIdx.x & 31;
   const int total = min(counts[1], refine_cap);
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; slot < total; slot += warps) {
     const int64_t qi = refine_list[slot];
     const int cnt = surv_count[slot];
-    if (cnt > kRefineCap || cnt < k) {       // too many survivors (or, defensively, too few): exhaustive float64 scan
+    if (cnt > kRefineCap || (cnt < k && !allow_short)) {       // too many survivors (or, in an unbounded call, too few): exhaustive float64 scan
       if (lane == 0) { const int s = atomicAdd(counts, 1); redo_list[s] = (int)qi; atomicAdd(counts + 2, 1); }
       continue;
     }
@@ -739,9 +767,10 @@ __global__ void knn_refine_finish_kernel(const double* __restrict__ train, const
         for (int r = 0; r < kRefineCap / 32; ++r) if (br == r) { dd[r] = INFINITY; ii[r] = INT64_MAX; }
       }
       if (lane == 0) {
-        if (nbr_idx) nbr_idx[qi * k + c] = index_base + mi;
+        const bool valid = mi != INT64_MAX;           // bounded calls: fewer than k rows inside the radius
+        if (nbr_idx) nbr_idx[qi * k + c] = valid ? index_base + mi : -1;
         if (nbr_sqdist) nbr_sqdist[qi * k + c] = md;
-        if (nbr_label) nbr_label[qi * k + c] = labels[mi];
+        if (nbr_label) nbr_label[qi * k + c] = valid ? labels[mi] : -1;
       }
     }
   }
@@ -789,7 +818,7 @@ cudaError_t knn_rerank(const double* train, const float* train32, int dp, int64_
                        const int* cand_idx, const float* cand_worst, const float* qnorm,
                        float tnorm_max_host, double err_rel, double err_floor, int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label,
                        int32_t* redo_list, int32_t* redo_count, cudaStream_t st, int32_t* refine_list, float* refine_thr,
-                       int refine_cap, float qnorm_limit) {
+                       int refine_cap, float qnorm_limit, const double* bound, const float* thr0) {
   if (m == 0) return cudaSuccess;
   cudaMemsetAsync(redo_count, 0, 4 * sizeof(int32_t), st);
   if (d > 64) {
@@ -801,22 +830,29 @@ cudaError_t knn_rerank(const double* train, const float* train32, int dp, int64_
   }
   knn_rerank_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(
       train, train32, dp, n, q, m, d, k, index_base, labels, cand_idx, cand_worst, qnorm, tnorm_max_host, err_rel, err_floor,
-      nbr_idx, nbr_sqdist, nbr_label, redo_list, redo_count, refine_list, refine_thr, refine_cap, qnorm_limit);
+      nbr_idx, nbr_sqdist, nbr_label, redo_list, redo_count, refine_list, refine_thr, refine_cap, qnorm_limit, bound, thr0);
   return cudaGetLastError();
 }
 
 int knn_refine_survivor_cap() { return kRefineCap; }
 
+cudaError_t knn_bound_thresholds(const double* bound, const float* qnorm, int64_t m, double err_rel, double err_floor, float* thr0,
+                                 cudaStream_t st) {
+  if (m == 0) return cudaSuccess;
+  knn_bound_thresholds_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(bound, qnorm, m, err_rel, err_floor, thr0);
+  return cudaGetLastError();
+}
+
 cudaError_t knn_refine(const double* train, const float* train32, int dp, int64_t n, const double* q, int d, int k,
                        int64_t index_base, const int32_t* labels, const int32_t* refine_list, const float* refine_thr,
                        int refine_cap, int32_t* surv_count, int32_t* surv_rows, int32_t* counts, int32_t* redo_list,
-                       int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label, int sm_count, cudaStream_t st) {
+                       int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label, int sm_count, cudaStream_t st, bool allow_short) {
   if (dp != 16 || refine_cap <= 0) return cudaSuccess;
   cudaMemsetAsync(surv_count, 0, sizeof(int32_t) * (size_t)refine_cap, st);
   knn_refine_collect_kernel<16><<<sm_count * 4, kRefineThreads, 0, st>>>(train32, n, q, d, refine_list, refine_thr, counts, refine_cap,
                                                                           surv_count, surv_rows);
   knn_refine_finish_kernel<<<sm_count * 2, 256, 0, st>>>(train, q, d, k, index_base, labels, refine_list, counts, refine_cap,
-                                                          surv_count, surv_rows, nbr_idx, nbr_sqdist, nbr_label, redo_list);
+                                                          surv_count, surv_rows, nbr_idx, nbr_sqdist, nbr_label, redo_list, allow_short);
   return cudaGetLastError();
 }
 

@@ -20,14 +20,16 @@ cudaError_t knn_rerank(const double* train, const float* train32, int dp, int64_
                        const int* cand_idx, const float* cand_worst, const float* qnorm,
                        float tnorm_max_host, double err_rel, double err_floor, int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label,
                        int32_t* redo_list, int32_t* redo_count, cudaStream_t st, int32_t* refine_list = nullptr,
-                       float* refine_thr = nullptr, int refine_cap = 0, float qnorm_limit = 0.f);
+                       float* refine_thr = nullptr, int refine_cap = 0, float qnorm_limit = 0.f,
+                       const double* bound = nullptr, const float* thr0 = nullptr);
 // D <= 15: second pass for the queries the certificate rejected (fp32 threshold scan + float64 ranking of the survivors);
 // counts = redo_count: [0] exhaustive rescans, [1] refined queries, [2] refined queries passed on to the exhaustive scan
 int knn_refine_survivor_cap();
 cudaError_t knn_refine(const double* train, const float* train32, int dp, int64_t n, const double* q, int d, int k,
                        int64_t index_base, const int32_t* labels, const int32_t* refine_list, const float* refine_thr,
                        int refine_cap, int32_t* surv_count, int32_t* surv_rows, int32_t* counts, int32_t* redo_list,
-                       int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label, int sm_count, cudaStream_t st);
+                       int64_t* nbr_idx, double* nbr_sqdist, int32_t* nbr_label, int sm_count, cudaStream_t st,
+                       bool allow_short = false);
 cudaError_t knn_redo_all(int32_t* redo_list, int32_t* redo_count, int64_t m, cudaStream_t st);
 cudaError_t knn_rescan(const double* train, int64_t n, const double* q, int d, int k, int64_t index_base,
                        const int32_t* labels, const int32_t* redo_list, const int32_t* redo_count,
@@ -48,8 +50,13 @@ size_t knn_tc16_packed_bytes(int64_t rows, bool query);
 // flags[0] = max |x|^2 (float bits), flags[1] = 1 when a row is outside the range; norms (optional): |x|^2 per row
 cudaError_t knn_tc16_pack(const double* x, int64_t rows, int d, bool query, void* packed, float* norms, int* flags, cudaStream_t st);
 // k: neighbours the caller will certify (the filter keeps k + 2 candidates for k <= 3, else 8); needs n >= 64
+// thr0 (optional, [m]): start every query's filter at this score threshold (knn_bound_thresholds)
 cudaError_t knn_tc16_filter(const void* qpacked, const void* tpacked, int64_t m, int64_t n, int k, const int* qflags, int* cand_idx,
-                            float* cand_worst, int sm_count, cudaStream_t st);
+                            float* cand_worst, int sm_count, cudaStream_t st, const float* thr0 = nullptr);
+// bound[i] = an upper bound on query i's k-th squared distance (exact arithmetic) -> thr0[i] = the score threshold below
+// which every row that can still matter is guaranteed to fall (bound - |q|^2 + twice the scan's error at that radius)
+cudaError_t knn_bound_thresholds(const double* bound, const float* qnorm, int64_t m, double err_rel, double err_floor, float* thr0,
+                                 cudaStream_t st);
 
 // knn_dense.cu: tensor-core candidate scan for feature dimensions beyond the tiled scan (sequence features, D = 2 * max_len)
 int knn_dense_kblocks(int d);

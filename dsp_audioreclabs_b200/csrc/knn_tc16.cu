@@ -262,7 +262,7 @@ template <int kDebug, int kC>
 __global__ void __launch_bounds__(kTcThreads, 1)
 knn_tc16_filter_kernel(const unsigned char* __restrict__ qpacked, const unsigned char* __restrict__ tpacked, int64_t m, int n,
                        int units, int t_tiles, const int* __restrict__ qflags, int* __restrict__ cand_idx,
-                       float* __restrict__ cand_worst) {
+                       float* __restrict__ cand_worst, const float* __restrict__ thr0) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // (a query outside the filter's range was packed as the zero vector: it gets candidates like any other and the rerank
   //  kernel sends it to the exhaustive float64 scan -- qflags is informational)
@@ -360,7 +360,12 @@ knn_tc16_filter_kernel(const unsigned char* __restrict__ qpacked, const unsigned
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
 #pragma unroll
       for (int c = 0; c < kKnnCand; ++c) { l_cd[c * kEpiThreads] = INFINITY; l_ci[c * kEpiThreads] = -1; }
-      float thr = INFINITY;
+      // thr0 (optional): the caller knows an upper bound on the query's k-th distance (row-sharded KNN: the k-th distance
+      // within the shard that owns the query) -- the filter starts AT that threshold instead of paying ~C ln(n / C)
+      // insertions per query to find its own, and never rises above it while its list is still filling
+      const int64_t q_own = (int64_t)u * kUnitQ + h * kRows + lg * 32 + lane;
+      const float thr_cap = (thr0 && q_own < m) ? thr0[q_own] : INFINITY;
+      float thr = thr_cap;
       // Fast path: the minimum of each 8 scores and of all 32 by 3-input mins, all in registers.  A group of 8 whose
       // minimum beats the thread's C-th best goes to tc16_slow8.  History of this path (1 M x 100 k on one B200, the
       // TMEM -> register pipeline alone takes 7.9 ms): 128 unrolled register insertions (100+ KB of SASS, instruction-
@@ -372,9 +377,9 @@ knn_tc16_filter_kernel(const unsigned char* __restrict__ qpacked, const unsigned
         if (fminf(fminf(s0, s1), fminf(s2, s3)) < thr) {
 #define DSP_TC16_GROUP(g, sg)                                                                                                     \
           if (sg < thr)                                                                                                          \
-            thr = tc16_slow8<kC>(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]),            \
+            thr = fminf(thr_cap, tc16_slow8<kC>(__uint_as_float(v[8 * g]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]), \
                                  __uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]),        \
-                                 __uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]), idx0 + 8 * g, thr, l_cd, l_ci);
+                                 __uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]), idx0 + 8 * g, thr, l_cd, l_ci));
           DSP_TC16_GROUP(0, s0) DSP_TC16_GROUP(1, s1) DSP_TC16_GROUP(2, s2) DSP_TC16_GROUP(3, s3)
 #undef DSP_TC16_GROUP
         }
@@ -485,7 +490,7 @@ cudaError_t knn_tc16_pack(const double* x, int64_t rows, int d, bool query, void
 }
 
 cudaError_t knn_tc16_filter(const void* qpacked, const void* tpacked, int64_t m, int64_t n, int k, const int* qflags, int* cand_idx,
-                            float* cand_worst, int sm_count, cudaStream_t st) {
+                            float* cand_worst, int sm_count, cudaStream_t st, const float* thr0) {
   if (m == 0) return cudaSuccess;
   const int units = (int)(knn_tc16_padded_rows(m, true) / kUnitQ), t_tiles = (int)(knn_tc16_padded_rows(n, false) / kRows);
   static const int debug = [] { const char* e = std::getenv("DSP_TC16_DEBUG"); return e ? std::atoi(e) & 3 : 0; }();
@@ -497,7 +502,7 @@ cudaError_t knn_tc16_filter(const void* qpacked, const void* tpacked, int64_t m,
   if (e != cudaSuccess) return e;
   const int grid = units < sm_count ? units : sm_count;
   fn<<<grid, kTcThreads, kTcSmem, st>>>(static_cast<const unsigned char*>(qpacked), static_cast<const unsigned char*>(tpacked), m, (int)n,
-                                        units, t_tiles, qflags, cand_idx, cand_worst);
+                                        units, t_tiles, qflags, cand_idx, cand_worst, thr0);
   return cudaGetLastError();
 }
 

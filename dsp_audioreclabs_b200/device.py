@@ -124,14 +124,21 @@ class DeviceKNN:
         self.handle = h
         return self
 
-    def topk(self, queries):
+    def topk(self, queries, bound=None):
+        """(sqdist, idx, label) [m, k].  bound (optional float64 [m]): an upper bound on each query's k-th squared
+        distance in the WHOLE train set when this handle holds a row shard of it (dsp_knn_topk_bounded_device): the
+        shard returns its rows inside that radius -- possibly fewer than k, the rest (-1, inf, -1)."""
         assert queries.is_cuda and queries.dtype == torch.float64 and queries.is_contiguous()
         self._stream()
         m = queries.shape[0]
         idx = torch.empty(m, self.k, dtype=torch.int64, device=self.device)
         d2 = torch.empty(m, self.k, dtype=torch.float64, device=self.device)
         lab = torch.empty(m, self.k, dtype=torch.int32, device=self.device)
-        check(self.ctx.lib.dsp_knn_topk_device(self.handle, _dp(queries), m, _dp(idx), _dp(d2), _dp(lab)))
+        if bound is None:
+            check(self.ctx.lib.dsp_knn_topk_device(self.handle, _dp(queries), m, _dp(idx), _dp(d2), _dp(lab)))
+        else:
+            assert bound.is_cuda and bound.dtype == torch.float64 and bound.is_contiguous() and bound.numel() == m
+            check(self.ctx.lib.dsp_knn_topk_bounded_device(self.handle, _dp(queries), m, _dp(bound), _dp(idx), _dp(d2), _dp(lab)))
         return d2, idx, lab
 
     def predict(self, queries):

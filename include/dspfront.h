@@ -213,6 +213,14 @@ int dsp_knn_topk_host(dsp_knn* knn, const double* queries, int64_t m, int64_t* n
                       double* nbr_sqdist, int32_t* nbr_label);
 int dsp_knn_topk_device(dsp_knn* knn, const double* queries, int64_t m, int64_t* nbr_idx,
                         double* nbr_sqdist, int32_t* nbr_label);
+/* The same for a ROW SHARD of the train set when the caller knows, per query, an upper bound on the squared distance of
+ * its k-th neighbour in the WHOLE train set (row-sharded KNN: the k-th distance within the shard that owns the query,
+ * src/models.py:56-58 semantics unchanged): the shard returns its rows inside that radius -- possibly fewer than k,
+ * the rest of a query's slots are (-1, +inf, -1) -- and never has to discover a threshold of its own.  Exact like
+ * dsp_knn_topk_device: every row of the shard within the bound (ties included) is returned or displaced by k better
+ * ones.  bound_sqdist: float64 [m], +inf = no bound; NULL = dsp_knn_topk_device. */
+int dsp_knn_topk_bounded_device(dsp_knn* knn, const double* queries, int64_t m, const double* bound_sqdist, int64_t* nbr_idx,
+                                double* nbr_sqdist, int32_t* nbr_label);
 /* predict = topk + majority vote, vote ties to the smallest label. */
 int dsp_knn_predict_host(dsp_knn* knn, const double* queries, int64_t m, int32_t* labels_out);
 /* Diagnostics of the last topk / predict call on this handle (waits for it): how many queries the

@@ -25,6 +25,18 @@ def _oracle_topk(train, labels, queries, k, index_base):
     return torch.from_numpy(d2), torch.from_numpy(idx + index_base), torch.from_numpy(lab.astype(np.int32))
 
 
+def _oracle_topk_bounded(train, labels, queries, k, index_base, bound=None):
+    """A local_topk that takes the threshold hints and USES them: rows outside a query's radius are dropped, so the
+    exchange and the merge see short lists (what the CUDA library returns for a bounded call)."""
+    d2, idx, lab = _oracle_topk(train, labels, queries, k, index_base)
+    if bound is not None:
+        out = d2 > bound[:, None]
+        d2 = torch.where(out, torch.full_like(d2, float("inf")), d2)
+        idx = torch.where(out, torch.full_like(idx, -1), idx)
+        lab = torch.where(out, torch.full_like(lab, -1), lab)
+    return d2, idx, lab
+
+
 def _oracle_merge(cd, ci, cl):
     from oracle import knn_oracle as ko
     mi, _ = ko.merge_candidates(cd.numpy(), ci.numpy(), cd.shape[2])
@@ -54,6 +66,11 @@ def _worker(rank, world, port, out_dir):
     assert np.array_equal(a, a2)
     assert np.array_equal(knn.predict(q_local).numpy(), a)  # automatic choice (replicated here: the train set is tiny)
     b = knn.predict_replicated(q_local).numpy()
+    hinted = ddist.ShardedKNN(3, local_topk=_oracle_topk_bounded, merge_vote=_oracle_merge)
+    hinted.fit(torch.from_numpy(xn[tb[rank]:tb[rank + 1]]), torch.from_numpy(y[tb[rank]:tb[rank + 1]]))
+    assert hinted._takes_bound and not knn._takes_bound
+    assert np.array_equal(hinted.predict_sharded(q_local).numpy(), a)                         # threshold hints travel with the queries
+    assert np.array_equal(hinted.predict_sharded(q_local, [len(q_local)] * world).numpy(), a)
     mean, std = ddist.zscore_stats_allreduce(torch.from_numpy(k["d15/train"][tb[rank]:tb[rank + 1]]))
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), a=a, b=b, lo=qb[rank], hi=qb[rank + 1],
              mean=mean.numpy(), std=std.numpy())

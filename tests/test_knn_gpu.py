@@ -100,6 +100,47 @@ def test_row_sharded_knn_merge_equals_single_shard(ctx, golden_knn):
         assert np.array_equal(labels.cpu().numpy(), k["d15/pred"])
 
 
+def test_row_sharded_knn_with_threshold_hints(ctx, golden_knn):
+    """dsp_knn_topk_bounded_device: every query arrives with the k-th distance found in the shard that owns it (an upper
+    bound on its k-th distance in the whole train set); the other shards return only their rows inside that radius --
+    possibly fewer than k -- and the merge is still sklearn's answer bit for bit.  Also: bounds that are exactly the
+    global k-th distance (ties at the radius must come back), +inf bounds (= the unbounded call), and the config-3 set."""
+    import torch
+    from dsp_audioreclabs_b200 import device
+    k = golden_knn
+    dev = torch.device("cuda", 0)
+    xn = torch.from_numpy(k["d15/train_norm"]).to(dev)
+    y = torch.from_numpy(k["d15/train_labels"].astype(np.int32)).to(dev)
+    q = torch.from_numpy(k["d15/query_norm"]).to(dev)
+    m = q.shape[0]
+    full_kth = device.DeviceKNN(3, ctx=ctx, device=dev).fit(xn.contiguous(), y.contiguous()).topk(q)[0][:, 2].contiguous()
+    for shards in (2, 8):
+        bounds = np.linspace(0, xn.shape[0], shards + 1).astype(int)
+        knns = [device.DeviceKNN(3, ctx=ctx, device=dev, index_base=int(bounds[r])).fit(
+            xn[bounds[r]:bounds[r + 1]].contiguous(), y[bounds[r]:bounds[r + 1]].contiguous()) for r in range(shards)]
+        owner = torch.arange(m, device=dev) % shards
+        own_kth = torch.stack([kn.topk(q)[0][:, 2] for kn in knns])                     # [shards, m]
+        for mode in ("owner", "tight", "inf"):
+            if mode == "owner":
+                bound = own_kth.gather(0, owner[None, :])[0].contiguous()
+            elif mode == "tight":
+                bound = full_kth                                                         # the global k-th distance itself
+            else:
+                bound = torch.full((m,), float("inf"), dtype=torch.float64, device=dev)
+            cd, ci, cl = [], [], []
+            short = 0
+            for kn in knns:
+                d2, idx, lab = kn.topk(q, bound)
+                short += int((idx < 0).sum())
+                assert bool(((idx < 0) == torch.isinf(d2)).all()) and bool(((idx < 0) == (lab < 0)).all())
+                cd.append(d2); ci.append(idx); cl.append(lab)
+            labels, idx, _ = knns[0].merge_vote(torch.stack(cd), torch.stack(ci), torch.stack(cl))
+            torch.cuda.synchronize()
+            assert np.array_equal(idx.cpu().numpy(), k["d15/nbr_idx"]), (shards, mode)
+            assert np.array_equal(labels.cpu().numpy(), k["d15/pred"]), (shards, mode)
+            assert (short > 0) == (mode != "inf"), (shards, mode, short)                  # hinted shards really return short lists
+
+
 # ---- tensor-core candidate filter for d <= 15 (csrc/knn_tc16.cu) ---------------------------------------------
 SCAN_FP32, SCAN_TC16 = 1, 3
 
