@@ -1348,15 +1348,22 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
         return __popc((E ^ O) & m1) + __popc((O ^ (E >> 1)) & m2);
       };
       auto unpack1 = [](unsigned long long pk) { return ((int)((uint32_t)pk << 8)) >> 8; };
-      // ragged-edge geometries have few, long frames (98 of 1,102 samples at the reference's default): TWO threads per
-      // frame there, each taking one edge, half of the whole groups and half of the bit string; one exchange per frame
+      // ragged-edge geometries have few, long frames (98 of 1,102 samples at the reference's default): TWO lanes per
+      // frame there, each taking half of the whole groups and of the bit string and one of the frame's two ragged ends,
+      // on ONE code path; a butterfly exchange per frame.  (Written for 2 / 4 / 8 lanes; 4 measured slower -- 1.47 against
+      // 1.29 ms per 20k utterances at 1102 / 441: the per-frame float64 epilogue every lane runs then repeats twice.)
       const bool pair = !kChain && edges;
-      const int fstep = pair ? kStreamThreads / 2 : kStreamThreads;
+      constexpr int kMaxLaneShift = 1;
+      int lshift = 0;                                     // log2(lanes per frame)
+      if (pair) { lshift = 1; while (lshift < kMaxLaneShift && (nfull << (lshift + 1)) <= 2 * kStreamThreads) ++lshift; }
+      const int lpf = 1 << lshift;
+      const int fstep = kStreamThreads >> lshift;
 #pragma unroll 1
       for (int f0 = 0; f0 < fmax; f0 += fstep) {
-        const int f = f0 + (pair ? (stid >> 1) : stid);
-        const int half = pair ? (stid & 1) : 0;
-        const unsigned act = __ballot_sync(0xffffffffu, f < nfull);     // the lanes that reach the pair exchange below
+        const int f = f0 + (stid >> lshift);
+        const int sub = stid & (lpf - 1);
+        const int half = sub;                               // (lane 0 of a frame's group stores its results)
+        const unsigned act = __ballot_sync(0xffffffffu, f < nfull);     // the lanes that reach the exchange below
         if (f >= fmax) continue;
         const int p = f * fs;
         int zc = 0;
@@ -1400,9 +1407,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
             long long k1 = 0, k2 = 0;
             const int ps = p + sh, qs = ps + fl;
             const int ga = ps / kGroup, gb = qs / kGroup;
-            const int gmid = pair ? (ga + gb + 1) >> 1 : gb;
+            const int gspan = gb - ga;
 #pragma unroll 1
-            for (int g = half ? gmid : ga; g < (half ? gb : gmid); ++g) {
+            for (int g = ga + ((gspan * sub) >> lshift); g < ga + ((gspan * (sub + 1)) >> lshift); ++g) {
               const unsigned long long pk = gsum[g];
               k2 += (long long)(pk >> 24);
               k1 += (long long)unpack1(pk);
@@ -1434,14 +1441,20 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
               k1 += sign * (long long)(256 * sumh + (int)sl);
               k2 += sign * ((long long)hh * 65536 + (long long)hl * 512 + (long long)ll);
             };
-            // (this branch always runs paired; both halves execute the same instructions on their own edge / range)
+            // (this branch always runs with lpf >= 2 lanes per frame; all of them execute the same instructions)
             {
-              const int hr = (half ? qs : ps) & (kGroup - 1);
-              if (hr) head(half ? gb : ga, hr, half ? 1 : -1);
-              // sign changes at the pairs (i, i + 1), i in [ps, qs - 1): split at the middle sample
-              const int pmid = (ps + qs) >> 1;
-              zc = count_changes(s_bits, half ? pmid : ps, half ? qs : pmid + 1);
-              k1 += __shfl_xor_sync(act, k1, 1); k2 += __shfl_xor_sync(act, k2, 1); zc += __shfl_xor_sync(act, zc, 1);
+              const bool first = sub == 0, lastl = sub == lpf - 1;
+              if (first || lastl) {
+                const int hr = (lastl ? qs : ps) & (kGroup - 1);
+                if (hr) head(lastl ? gb : ga, hr, lastl ? 1 : -1);
+              }
+              // sign changes at the pairs (i, i + 1), i in [ps, qs - 1): lane j takes i in [b_j, b_(j+1))
+              const int b0 = ps + (((qs - ps) * sub) >> lshift), b1 = ps + (((qs - ps) * (sub + 1)) >> lshift);
+              zc = count_changes(s_bits, b0, lastl ? qs : b1 + 1);
+#pragma unroll 1
+              for (int o = 1; o < lpf; o <<= 1) {
+                k1 += __shfl_xor_sync(act, k1, o); k2 += __shfl_xor_sync(act, k2, o); zc += __shfl_xor_sync(act, zc, o);
+              }
             }
             s1 = k1 - (long long)fl * thr;
             s2 = k2 - 2ll * thr * k1 + (long long)fl * thr2;
