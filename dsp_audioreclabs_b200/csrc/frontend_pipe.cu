@@ -526,15 +526,6 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
     // there -- they are the LAST m samples of the frame two blocks back, added by a small correction pass).  One code
     // path and one LDG.128 per block for every alignment; the registers are loaded per utterance (tail_chain below).
 
-#ifdef DSP_EXP_HOIST
-    float cw[2][8], cw2[2][8];
-    if constexpr (kChain) {
-#pragma unroll
-      for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int q8 = 0; q8 < 8; ++q8) { const float w = s_win[c * 128 + 8 * (lane & 15) + q8]; cw[c][q8] = w; cw2[c][q8] = w * w; }
-    }
-#endif
     long long tp[5] = {0, 0, 0, 0, 0}, tprev = clock64();
     auto tick = [&](int i) { if (a.prof) { const long long t = clock64(); tp[i] += t - tprev; tprev = t; } };
     for (int it = 0;; ++it) {
@@ -766,21 +757,12 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
           const int last = max(nfr, 0);                      // last hop block this chain may touch
           const bool hi8 = (sub & 8) != 0, writer = (sub & 7) == 0;
           // block i at ptr[16 * i]; an idle chain re-reads the first block of the segment and stores nothing
-#ifdef DSP_EXP_MAL0
-          const int mal = 0;
-#else
           const int mal = (int)((reinterpret_cast<uintptr_t>(x + start) & 15) >> 1);       // = the utterance's shift: start is a multiple of 128
-#endif
-#ifndef DSP_EXP_HOIST
           float cw[2][8], cw2[2][8];
-#endif
 #pragma unroll
           for (int c = 0; c < 2; ++c)
 #pragma unroll
             for (int q8 = 0; q8 < 8; ++q8) {
-#ifdef DSP_EXP_HOIST
-              break;
-#endif
               const int pos = c * 128 + 8 * sub + q8 - mal;
               const float w = s_win[max(pos, 0)];
               cw[c][q8] = pos >= 0 ? w : 0.f; cw2[c][q8] = pos >= 0 ? w * w : 0.f;
@@ -1072,11 +1054,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
     // (sh = 0..7, per utterance).  Groups, chunks and bit strings are indexed by STREAM position; a frame that starts at
     // sample p is the run of whole groups from p / 64 minus the first sh samples of its first group plus the first sh
     // samples of the group behind its last one -- the "head" sums / head bits every group records next to its totals.
-#ifdef DSP_EXP_NOSHIFT
-    const int n = dsc.y & 0xfffff, sh = 0;
-#else
     const int n = dsc.y & 0xfffff, sh = dsc.y >> 20;
-#endif
     const int np = n + sh;
     const int nchunks = np > 0 ? (np + kChunkSamples - 1) / kChunkSamples : 1;
     const int ng = (np + kGroup - 1) / kGroup;
