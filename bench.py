@@ -277,10 +277,9 @@ def run_reference(args):
         "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "sample_per_step": f"{cores * per_worker} utterances (bounded sample of the 100k-utterance batch; per-utterance cost is constant)"},
+        "config": bench_config(args, int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": c["kind"],
-                         "sample": f"{cores * per_worker} utterances per step x {args.steps} steps, multiprocessing.Pool({cores}), {c['what']}; "
+                         "sample": f"{cores * per_worker} utterances per step (a bounded sample of the 100k-utterance batch: per-utterance cost is constant) x {args.steps} steps, multiprocessing.Pool({cores}), {c['what']}; "
                                    f"KNN against a {N_TRAIN_CPU}-row train set fitted before the timed region"},
         "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -291,6 +290,17 @@ def run_reference(args):
 METRIC = "audio-seconds processed/sec (features+endpoints+KNN)"
 WORKLOAD = ("configs[1] batch through the configs[2] pipeline: 100k synthetic 1 s utterances per GPU, frame 256 / shift 128, three windows "
             "cycled over steps -> fused front end -> z-score -> KNN(3) vs a 100k-utterance train set framed with the same window")
+
+
+def bench_config(args, world):
+    """The workload both arms are quoted on (the reference arm times a bounded sample of it per step: its
+    cpu_baseline.sample says which)."""
+    return {"workload": WORKLOAD,
+            "utterances_per_gpu": args.utts, "samples_per_utterance": UTT_LEN, "frame_length": FL, "frame_shift": FS,
+            "windows": list(WINDOWS), "train_utterances": args.train_utts, "knn_k": 3,
+            "parallelism": f"utterance shards x{world}" + ("" if world == 1 else f", KNN train rows {args.knn_path} x{world} (NCCL)"),
+            "layout": "packed CSR, no padding between utterances",
+            "l2_policy": f"input {args.utts * UTT_LEN * 2 / 1e9:.2f} GB per pass >> 126 MB L2 (no flush needed)"}
 
 
 def knn_section(dev, ctx):
@@ -477,8 +487,8 @@ def run_ours(args):
                 "hbm_frac": pipe_bytes / (avg_step_ms / 1e3) / 1e9 / peak,
                 "knn": {"queries_per_gpu_per_step": n_utts, "train_rows": args.train_utts, "dim": 15, "k": 3,
                         "train_layout": "whole train set on the GPU" if world == 1 else
-                        (f"rows sharded x{world}; per step: all-gather of the query features, ONE NCCL all-gather of the packed top-k candidates "
-                         f"({world * n_utts} queries x 3 x 16 B per rank), merge + vote" if args.knn_path == "sharded" else
+                        (f"rows sharded x{world}; per step: own queries against own rows (threshold hints), all-gather of the query features + hints, "
+                         f"ONE NCCL all-gather of the packed top-k candidates ({world * n_utts} queries x 3 x 16 B per rank), merge + vote" if args.knn_path == "sharded" else
                          f"rows all-gathered once at fit (replicated), no per-step exchange")}}
     if world > 1 and args.knn_path == "sharded":
         # the same steps with the train rows all-gathered once at fit (the D = 15 fast path: no per-step exchange)
@@ -533,6 +543,28 @@ def run_ours(args):
         del rf
     except Exception as exc:      # secondary numbers must never break the bench line
         per_config["error"] = repr(exc)
+
+    # ---- BASELINE configs[3] on the same batch: the reference's default geometry and the ends of its ablation grids,
+    # one launch per configuration (front end only, Hamming) ---------------------------------------------------------
+    try:
+        for gfl, gfs in ((1102, 441), (2205, 441), (1102, 132), (512, 256), (128, 64)):
+            gf = devapi.DeviceFrontend(row_offsets, gfl, gfs, "hamming", ctx=ctx, device=dev)
+            with torch.cuda.stream(stream):
+                for _ in range(2):
+                    gf.run(samples, stream=stream)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(3):
+                    gf.run(samples, stream=stream)
+                e1.record(stream)
+            stream.synchronize()
+            g_ms = e0.elapsed_time(e1) / 3
+            per_config[f"frame_{gfl}_shift_{gfs}"] = {"ms": g_ms, "audio_s_per_s": audio_s_per_step / (g_ms / 1e3),
+                                                      "hbm_frac": gf.algorithmic_bytes() / (g_ms / 1e3) / 1e9 / peak,
+                                                      "replayed_in_float64": int((gf.status >= 0x100).sum().item())}
+            del gf
+    except Exception as exc:      # secondary numbers must never break the bench line
+        per_config["geometry_error"] = repr(exc)
 
     # ---- parity spot check against the oracle on a few of the benchmarked utterances -------------------------------------
     parity = None
@@ -610,12 +642,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "audio-s/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i16->f32/f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD,
-                       "utterances_per_gpu": n_utts, "samples_per_utterance": UTT_LEN, "frame_length": FL, "frame_shift": FS,
-                       "windows": list(WINDOWS), "train_utterances": args.train_utts, "knn_k": 3,
-                       "parallelism": f"utterance shards x{world}" + ("" if world == 1 else f", KNN train rows {args.knn_path} x{world} (NCCL)"),
-                       "layout": "packed CSR, no padding between utterances",
-                       "l2_policy": f"input {samples.numel() * 2 / 1e9:.2f} GB per pass >> 126 MB L2 (no flush needed)"},
+            "config": bench_config(args, world),
             "roofline": roofline, "pipeline": pipeline, "frontend_only": frontend_only, "per_window": per_window,
             "per_config": per_config, "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches), "parity": parity, "numa": numa,
