@@ -845,7 +845,10 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
           // more in instruction misses than it hid in latency); loads past the chain's last block re-read that block.
           // ld.global.cs: by the time a batch is processed the segment has usually left L2 (hit rate ~10 %) and this is
           // its last use -- streaming loads keep the dead lines from displacing the ring's traffic (-4 % DRAM reads)
-          constexpr int kInFlight = 6;
+#ifndef DSP_CHAIN_INFLIGHT
+#define DSP_CHAIN_INFLIGHT 6
+#endif
+          constexpr int kInFlight = DSP_CHAIN_INFLIGHT;
           int4 q[kInFlight];
           auto load_block = [&](int bi) -> int4 { return __ldcs(ptr + 16 * bi); };
 #pragma unroll

@@ -48,8 +48,13 @@ constexpr int kQBufBytes = 2 * kTileBytes;       // two query blocks
 #endif
 constexpr int kSplit = DSP_TC16_SPLIT;
 constexpr int kTStages = kSplit == 1 ? 18 : 16;                     // 144 KB of train tiles in flight; with the query buffers and the candidate lists the CTA owns its SM (all of TMEM is allocated)
-constexpr int kAccStages = 2;
-constexpr int kEpiWarps = 8 * kSplit;
+// kSplit 4 (experiment, kept compilable): the 16 epilogue warps of kSplit 2 on HALF tiles -- MMAs of N = 64, four
+// accumulator stages of 2 x 64 columns, a warp compares 32 columns per stage and loads the next stage's 32 while it does
+// (register double buffer).  Parity-green and slower: 1 M x 100 k in 25.0 ms against 20.1 ms -- twice the MMA issues,
+// commits and barrier round trips per pair cost more than the hidden TMEM-load latency returns.
+constexpr int kAccStages = kSplit == 4 ? 4 : 2;
+constexpr int kMmaN = kSplit == 4 ? 64 : kRows;           // train rows per MMA
+constexpr int kEpiWarps = kSplit == 1 ? 8 : 16;
 constexpr int kTcThreads = 32 * (2 + kEpiWarps);
 constexpr int kTmemCols = 512;
 constexpr int kEpiThreads = 32 * kEpiWarps;
@@ -59,7 +64,7 @@ constexpr size_t kTcSmem = 2 * kQBufBytes + (size_t)kTStages * kTileBytes + kLis
 // K of one 8-row group are adjacent (LBO = 128 B); row groups follow every 256 B (SBO)
 constexpr uint32_t kLBO = 128, kSBO = 256;
 // instruction descriptor (kind::f16): D = F32 (bit 4), A = B = F16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kRows >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(kMmaN >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
 static_assert(8 * (4 + 2 * kTStages + 2 * kAccStages) + 8 <= 1024, "barrier block of the shared-memory plan");
 constexpr float kPadNorm = 30000.f;              // |t|^2 of padding rows: above every real score (knn_tc16_max_norm)
 
@@ -325,6 +330,30 @@ knn_tc16_filter_kernel(const unsigned char* __restrict__ qpacked, const unsigned
         tc_fence_after();
         const uint32_t q0 = smem_u32(s_q + (size_t)qb * kQBufBytes);
         for (int tb = 0; tb < t_tiles; ++tb) {
+          if constexpr (kSplit == 4) {
+            // two half-tile steps of 64 train rows: row groups of 8 lie kSBO bytes apart in the K-major tile
+            wait(&t_full[s], ph);
+            const uint32_t t_base = smem_u32(s_t + (size_t)s * kTileBytes);
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              wait(&acc_empty[as], aph ^ 1u);           // the epilogue has loaded this accumulator stage
+              tc_fence_after();
+              const uint32_t t_hi = t_base + (uint32_t)sub * (kMmaN / 8) * kSBO, t_lo = t_hi + kPlaneBytes;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const uint32_t q_hi = q0 + (uint32_t)h * kTileBytes, q_lo = q_hi + kPlaneBytes;
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * 2 * kMmaN + h * kMmaN);
+                umma_f16(d_tmem, umma_desc(q_hi), umma_desc(t_hi), 0u);
+                umma_f16(d_tmem, umma_desc(q_hi), umma_desc(t_lo), 1u);
+                umma_f16(d_tmem, umma_desc(q_lo), umma_desc(t_hi), 1u);
+              }
+              if (sub == 1) umma_commit(&t_empty[s]);               // ring slot free once these MMAs have read it
+              umma_commit(&acc_full[as]);
+              if (++as == kAccStages) { as = 0; aph ^= 1u; }
+            }
+            if (++s == kTStages) { s = 0; ph ^= 1u; }
+            continue;
+          }
           wait(&acc_empty[as], aph ^ 1u);             // the epilogue has drained this accumulator stage
           wait(&t_full[s], ph);
           tc_fence_after();
@@ -410,6 +439,36 @@ knn_tc16_filter_kernel(const unsigned char* __restrict__ qpacked, const unsigned
           process(vb, base + 64);
           process(vb + 32, base + 96);
         }
+      } else if constexpr (kSplit == 4) {
+        // half-tile stages: 32 columns per warp and stage, the next stage's 32 in flight while these are compared
+        uint32_t va[32], vb[32];
+        auto stage_col = [&](int st) { return (uint32_t)(st * 2 * kMmaN + h * kMmaN + half * 32); };
+        wait_epi(&acc_full[as], aph);
+        tc_fence_after();
+        tmem_ld32(lane_addr + stage_col(as), va);
+        for (int tb = 0; tb < t_tiles; ++tb) {
+          const int base = tb * kRows + half * 32;
+          tmem_ld_wait();                                          // (tb, rows 0..63) is in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[as]);
+          if (++as == kAccStages) { as = 0; aph ^= 1u; }
+          wait_epi(&acc_full[as], aph);
+          tc_fence_after();
+          tmem_ld32(lane_addr + stage_col(as), vb);                 // (tb, rows 64..127)
+          process(va, base);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[as]);
+          if (++as == kAccStages) { as = 0; aph ^= 1u; }
+          if (tb + 1 < t_tiles) {
+            wait_epi(&acc_full[as], aph);
+            tc_fence_after();
+            tmem_ld32(lane_addr + stage_col(as), va);               // (tb + 1, rows 0..63)
+          }
+          process(vb, base + 64);
+        }
       } else {
         // Two warps per (lane group, query block), each on its own 64 columns of every tile with its own candidate list:
         // four epilogue warps per scheduler hide one another's TMEM-load and min-tree latencies (with two, issue slots
@@ -432,7 +491,7 @@ knn_tc16_filter_kernel(const unsigned char* __restrict__ qpacked, const unsigned
           process(vb, base + 32);
         }
       }
-      if constexpr (kSplit == 2) {
+      if constexpr (kSplit >= 2) {
         // merge: the warp of half 0 folds its partner's list (same lane group, same query block: 128 threads up) into its own
         const int pair_bar = 1 + lg + 4 * h;
         asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
@@ -460,7 +519,7 @@ knn_tc16_filter_kernel(const unsigned char* __restrict__ qpacked, const unsigned
           cand_worst[q] = l_cd[(kC - 1) * kEpiThreads];
         }
       }
-      if constexpr (kSplit == 2) {
+      if constexpr (kSplit >= 2) {
         // the partner must not re-initialise its list for the next unit before it has been read
         asm volatile("bar.sync %0, 64;" ::"r"(1 + lg + 4 * h) : "memory");
       }
