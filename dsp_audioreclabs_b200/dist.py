@@ -256,7 +256,13 @@ class ShardedDTW:
     def _cuda_topk(self, templates, labels, queries, k, index_base):
         from .mfcc_dtw import DTWClassifier
         if self._clf is None:
-            self._clf = DTWClassifier(k, index_base=index_base).fit(templates, labels)
+            # this rank's GPU: the library context of the device the exchange buffers live on (without it every rank of a
+            # box computed on GPU 0)
+            ctx = None
+            if self.device is not None and torch.device(self.device).type == "cuda":
+                from .batch import default_context
+                ctx = default_context(torch.device(self.device).index or 0)
+            self._clf = DTWClassifier(k, ctx=ctx, index_base=index_base).fit(templates, labels)
         nc, ni, nl = self._clf.kneighbors(queries)
         return nc, ni, self._clf.classes_[np.clip(nl, 0, None)].astype(np.int32) * (nl >= 0) - (nl < 0)
 

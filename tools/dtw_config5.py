@@ -36,7 +36,7 @@ templates = [seqs[i] for i in tsel]
 labels = tsel % 10
 tb = ddist.balanced_bounds(nt, world)
 sd = ddist.ShardedDTW(3, device=(dev if world > 1 else None)).fit(templates[tb[rank]:tb[rank + 1]], labels[tb[rank]:tb[rank + 1]])
-sd.kneighbors(queries[:64])                                  # warm-up: staging buffers
+sd.kneighbors(queries)                                       # full-size warm-up: the library's device buffers (a 400 MB cost matrix at N = 1) are allocated here
 if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
