@@ -57,8 +57,10 @@ def mfcc_batch(samples, offsets, start, end, lengths=None, ctx=None, **params):
     if p["window_type"] not in WINDOW_IDS:
         raise ValueError(f"unsupported window type: {p['window_type']}")
     lib = ctx.lib
-    nfr = np.array([lib.dsp_frame_count(int(max(e - s, 0)), p["frame_length"], p["frame_shift"]) for s, e in zip(start, end)],
-                   dtype=np.int64)
+    # frame_signal's frame count in closed form (dsp_frame_count; src/audio_processing.py:320-331), vectorised
+    seg = np.maximum(end.astype(np.int64) - start.astype(np.int64), 0)
+    fl_, fs_ = int(p["frame_length"]), int(p["frame_shift"])
+    nfr = np.where(seg > 0, np.minimum(-(-seg // fs_), -(-np.maximum(seg - fl_, 0) // fs_) + 1), 0).astype(np.int64)
     mo = np.zeros(b + 1, dtype=np.int64)
     np.cumsum(nfr, out=mo[1:])
     out = np.zeros((int(mo[-1]), p["n_ceps"]), dtype=np.float32)
