@@ -41,20 +41,28 @@ constexpr int kGroupsPerChunk = kChunkSamples / kGroup;   // 32: one group per s
 // utterances against 3.26 (12 warps), 3.69 (16) and 3.57 (4) -- every stream warp repeats ~140 instructions of
 // per-utterance set-up, and 22 chunks split 3/3/3/3/3/3/2/2 over 8 warps.  More than 8 use the register split.
 constexpr int kStreamWarps = DSP_PIPE_STREAM_WARPS;       // a multiple of 4: whole warpgroups (setmaxnreg)
-constexpr int kMaxTailWarps = 7;
+#ifndef DSP_PIPE_TAIL_WARPS
+#define DSP_PIPE_TAIL_WARPS 7
+#endif
+// 7 tail warps: with 11 (-DDSP_PIPE_TAIL_WARPS=11 -DDSP_PIPE_STREAM_REGS=72: 640 threads, stream warps at 72 and tail warps at
+// 112 registers, 22 records, a 24-slot ring) the kernel is parity-green and slower, 3.81 against 3.43 ms per 100k utterances
+constexpr int kMaxTailWarps = DSP_PIPE_TAIL_WARPS;        // tail warps + the control warp: whole warpgroups too
 constexpr int kPipeWarps = kStreamWarps + kMaxTailWarps + 1;
 constexpr int kPipeThreads = 32 * kPipeWarps;             // 512
 // Register split (setmaxnreg, per warpgroup; only for kStreamWarps > 8): the stream warps run short integer loops and give their
 // registers to the tail warps, which keep whole sequences in registers.  The launch allocates
 // kLaunchRegs = 65536 / kPipeThreads registers per thread (rounded down to 8) and the CTA owns only those:
 // setmaxnreg.inc can take no more than the stream warps have given back, or it waits forever.
-constexpr bool kSplitRegs = kStreamWarps > 8;
+constexpr bool kSplitRegs = kPipeWarps > 16;              // more than 512 threads: 128 registers each no longer fit
 constexpr int kLaunchRegs = (65536 / kPipeThreads) & ~7;
-constexpr int kStreamRegs = kStreamWarps == 16 ? 56 : 64;
+#ifndef DSP_PIPE_STREAM_REGS
+#define DSP_PIPE_STREAM_REGS (DSP_PIPE_STREAM_WARPS == 16 ? 56 : 64)
+#endif
+constexpr int kStreamRegs = DSP_PIPE_STREAM_REGS;
 constexpr int kTailRegs = ((kLaunchRegs * kPipeThreads - kStreamWarps * 32 * kStreamRegs) / ((kMaxTailWarps + 1) * 32)) & ~7;
 static_assert(kStreamWarps % 4 == 0 && (kMaxTailWarps + 1) % 4 == 0, "roles must cover whole warpgroups");
 static_assert(!kSplitRegs || kStreamWarps * 32 * kStreamRegs + (kMaxTailWarps + 1) * 32 * kTailRegs <= kLaunchRegs * kPipeThreads, "register pool of the CTA");
-static_assert(!kSplitRegs || kTailRegs >= 128, "tail warps keep whole sequences in registers");
+static_assert(!kSplitRegs || kTailRegs >= 104, "tail warps keep whole sequences in registers");
 constexpr int kStreamThreads = 32 * kStreamWarps;
 constexpr int kDescRing = 64;              // > max ring slots: the producer can never lap a reader
 constexpr int kMaxRingSlots = 56;
