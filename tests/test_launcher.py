@@ -72,3 +72,27 @@ def test_launcher_usage_errors():
     assert r.returncode == 2 and "run.py" in r.stdout
     r = subprocess.run([sys.executable, "-m", "dsp_audioreclabs_b200.run", "/nonexistent/x.py"], cwd=ROOT, capture_output=True, text=True)
     assert r.returncode == 2 and "no such script" in r.stderr
+
+
+def test_bench_arms_are_quoted_on_the_same_config():
+    """bench.py: the CUDA arm and the --impl reference arm print the same `config` dict for a given N (the reference arm
+    says which bounded sample of it a step times in cpu_baseline.sample)."""
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    args = types.SimpleNamespace(utts=100000, train_utts=100000, knn_path="sharded")
+    c1, c8 = bench.bench_config(args, 1), bench.bench_config(args, 8)
+    assert c1["workload"] == bench.WORKLOAD and c1["samples_per_utterance"] == 44100 and c1["frame_length"] == 256
+    assert "NCCL" in c8["parallelism"] and "NCCL" not in c1["parallelism"]
+    assert bench.METRIC.endswith("(features+endpoints+KNN)")
+
+
+def test_numa_binding_is_best_effort():
+    """dist.bind_to_gpu_numa never raises: without a GPU / sysfs entry it reports what it could not do."""
+    from dsp_audioreclabs_b200 import dist as ddist
+    before = os.sched_getaffinity(0)
+    info = ddist.bind_to_gpu_numa(0)
+    assert set(info) >= {"gpu", "numa_node", "cpus", "bound"} and info["bound"] in (True, False)
+    os.sched_setaffinity(0, before)
