@@ -186,39 +186,43 @@ __device__ __forceinline__ int frame_count32(int n, int fl, int fs) {
 
 __device__ __forceinline__ int sext16(uint32_t w) { return (int)(short)(w & 0xffffu); }
 
-// ---- sign-bit string helpers (linear order, bit i = "sample i is above the mean") ------------
-__device__ __forceinline__ int bit_at(const uint32_t* bits, int i) { return (bits[i >> 5] >> (i & 31)) & 1; }
+// ---- sign-bit string helpers ---------------------------------------------------------------------------------------
+// The string is kept in the form pass B produces it in: per 64-sample group two 32-bit planes, E (bit a = sample 2a is
+// above the mean) at bits[2g] and O (sample 2a + 1) at bits[2g + 1].  Sign changes at the pairs (i, i + 1) of a group:
+// even i = 2a are the bits of E ^ O, odd i = 2a + 1 the bits of O ^ (E shifted down by one, the next group's first
+// sample moving into bit 31).  Nothing has to interleave the planes: pass B keeps its 2-instructions-per-word form for
+// the ragged-edge geometries too, and a count over a range costs what it cost on the linear string.
+__device__ __forceinline__ int bit_at(const uint32_t* bits, int i) { return (bits[2 * (i >> 6) + (i & 1)] >> ((i & 63) >> 1)) & 1; }
+__device__ __forceinline__ uint32_t low_mask(int n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
 
+// sign changes at the pairs (i, i + 1), i in [p, q - 2] (stream positions)
 __device__ __forceinline__ int count_changes(const uint32_t* bits, int p, int q) {
   if (q - p < 2) return 0;
-  int c = 0;
-  if (((p | q) & 31) == 0) {
-    const int w0 = p >> 5, w1 = (q >> 5) - 1;
-    uint32_t cur = bits[w0];
-    for (int w = w0; w < w1; ++w) {
-      const uint32_t nxt = bits[w + 1];
-      c += __popc(cur ^ __funnelshift_r(cur, nxt, 1));
-      cur = nxt;
-    }
-    c += __popc((cur ^ (cur >> 1)) & 0x7fffffffu);
-    return c;
-  }
-  // pairs (i, i + 1) for i in [p, q - 2]: bit i of cur ^ (the string shifted down by one); the two end words masked,
-  // the words in between whole, each word loaded once
   const int last = q - 2;
-  const int w0 = p >> 5, w1 = last >> 5;
-  const uint32_t mfirst = 0xffffffffu << (p & 31), mlast = 0xffffffffu >> (31 - (last & 31));
-  uint32_t cur = bits[w0], nxt = bits[w0 + 1];
-  uint32_t x = cur ^ __funnelshift_r(cur, nxt, 1);
-  if (w0 == w1) return __popc(x & mfirst & mlast);
-  c = __popc(x & mfirst);
+  const int g0 = p >> 6, g1 = last >> 6;
+  const int lo = p & 63, hi = (last & 63) + 1;                 // pairs lo.. of the first group, ..hi-1 of the last
+  const uint32_t mE0 = ~low_mask((lo + 1) >> 1), mO0 = ~low_mask(lo >> 1);
+  const uint32_t mE1 = low_mask((hi + 1) >> 1), mO1 = low_mask(hi >> 1);
+  uint32_t E = bits[2 * g0], O = bits[2 * g0 + 1], En = bits[2 * g0 + 2];
+  uint32_t x1 = E ^ O, x2 = O ^ __funnelshift_r(E, En, 1);
+  if (g0 == g1) return __popc(x1 & mE0 & mE1) + __popc(x2 & mO0 & mO1);
+  int c = __popc(x1 & mE0) + __popc(x2 & mO0);
+  // (two groups per trip, their loads independent: this loop is on the critical path of the ragged geometries' pass F,
+  //  where a thread walks the ~9 groups of its half of a frame by itself)
+  int g = g0 + 1;
 #pragma unroll 1
-  for (int w = w0 + 1; w < w1; ++w) {
-    cur = nxt; nxt = bits[w + 1];
-    c += __popc(cur ^ __funnelshift_r(cur, nxt, 1));
+  for (; g + 1 < g1; g += 2) {
+    const uint32_t Ea = En, Oa = bits[2 * g + 1], Eb = bits[2 * g + 2], Ob = bits[2 * g + 3], Ec = bits[2 * g + 4];
+    c += __popc(Ea ^ Oa) + __popc(Oa ^ __funnelshift_r(Ea, Eb, 1)) + __popc(Eb ^ Ob) + __popc(Ob ^ __funnelshift_r(Eb, Ec, 1));
+    En = Ec;
   }
-  cur = nxt; nxt = bits[w1 + 1];
-  c += __popc((cur ^ __funnelshift_r(cur, nxt, 1)) & mlast);
+#pragma unroll 1
+  for (; g < g1; ++g) {
+    E = En; O = bits[2 * g + 1]; En = bits[2 * g + 2];
+    c += __popc(E ^ O) + __popc(O ^ __funnelshift_r(E, En, 1));
+  }
+  E = En; O = bits[2 * g1 + 1]; En = bits[2 * g1 + 2];
+  c += __popc((E ^ O) & mE1) + __popc((O ^ __funnelshift_r(E, En, 1)) & mO1);
   return c;
 }
 
@@ -928,6 +932,9 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
             const int valid = min(fl, end - p);
             const int mm = (int)((reinterpret_cast<uintptr_t>(x + p) & 15) >> 1);
             const int4* xv = reinterpret_cast<const int4*>(x + p - mm);
+            const float gc1f = -(8388608.f + 32768.f) - (float)thr;
+            const f32x2 gc1 = pk2(gc1f, gc1f), gphi = pk2(-phi, -phi);
+            f32x2 e2 = pk2(0.f, 0.f), m2 = e2;
             const int nv = (mm + valid + 7) >> 3;
             auto acc8 = [&](const int4& q, int v) {
               const uint32_t w[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
@@ -940,13 +947,29 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { const int j = j0 + i; const bool in = (unsigned)j < (unsigned)valid; const float wv = s_win[in ? j : 0]; ww[i] = in ? wv : 0.f; }
               }
+              if constexpr (kChain) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float dlo = (float)(sext16(w[k]) - thr) - phi;
-                const float dhi = (float)(((int)w[k] >> 16) - thr) - phi;
-                const float alo = ww[2 * k] * dlo, ahi = ww[2 * k + 1] * dhi;
-                e = fmaf(alo, alo, e); m += fabsf(alo);
-                e = fmaf(ahi, ahi, e); m += fabsf(ahi);
+                for (int k = 0; k < 4; ++k) {
+                  const float dlo = (float)(sext16(w[k]) - thr) - phi;
+                  const float dhi = (float)(((int)w[k] >> 16) - thr) - phi;
+                  const float alo = ww[2 * k] * dlo, ahi = ww[2 * k + 1] * dhi;
+                  e = fmaf(alo, alo, e); m += fabsf(alo);
+                  e = fmaf(ahi, ahi, e); m += fabsf(ahi);
+                }
+              } else {
+                // the general geometries spend a third of their instructions here: the two samples of a word travel as one
+                // packed fp32x2 pair, converted like the chain's (0x4B000000 | (k ^ 0x8000) = 2^23 + 32768 + k, minus the
+                // integer part exactly, minus phi in one rounding): 7 instead of 10.5 instructions per sample
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t ub = w[k] ^ 0x80008000u;
+                  const float xlo = __uint_as_float(__byte_perm(ub, 0x4b000000u, 0x7610));
+                  const float xhi = __uint_as_float(__byte_perm(ub, 0x4b000000u, 0x7632));
+                  const f32x2 d = add2(add2(pk2(xlo, xhi), gc1), gphi);
+                  const f32x2 av = mul2(pk2(ww[2 * k], ww[2 * k + 1]), d);
+                  e2 = fma2(av, av, e2);
+                  m2 = add2(av & 0x7fffffff7fffffffull, m2);
+                }
               }
             };
             // four 16-byte loads in flight per lane (the samples come from L2); the specialised 256 / 128 instantiation
@@ -961,6 +984,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
             }
 #pragma unroll 1
             for (; vq < nv; vq += kLanesPerFrame) { const int4 q = __ldg(xv + vq); acc8(q, vq); }
+            if constexpr (!kChain) { e += hsum2(e2); m += hsum2(m2); }
           }
 #pragma unroll
           for (int o = kLanesPerFrame / 2; o > 0; o >>= 1) {
@@ -1185,13 +1209,20 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
     // offset) the subtraction runs on the packed word: w - (thr << 16) has the sign of the high sample,
     // w * 65536 - (thr << 16) that of the low one -- one instruction each, no unpacking.
     const bool narrow = (mx - thr <= 32766) && (thr - mn <= 32768) && thr >= -32766 && thr <= 32767;
-    const uint32_t thr16 = (uint32_t)thr << 16;
     // fastest form (whole-group frames, narrow range): max(min(k - thr + 1, 1), 0) on both halves of a word in
     // ONE instruction (VIADDMNMX.S16x2.RELU) is the pair of "above the mean" bits; acc + acc + r appends
     // them to an even-sample and an odd-sample bit plane.  Only the per-group record (crossings inside the
     // group, its first / last two bits) is needed downstream, the bit string itself is never stored.
-    const bool fastb = narrow && !edges;
-    if (fastb) {
+    const bool fastb = narrow && !edges;        // whole-group frames, narrow range: the bit string itself is never stored
+    // group record of whole-group frames: crossings inside the group | samples 0,2,4,6,8 | samples 1,3,5,7 | sample 62 | sample 63
+    auto group_meta = [](uint32_t E, uint32_t O) {
+      const uint32_t x1 = E ^ O, x2 = (O ^ (E >> 1)) & 0x7fffffffu;
+      return (uint32_t)(__popc(x1) + __popc(x2)) | ((E & 0x1fu) << kMetaE) | ((O & 0xfu) << kMetaO) | ((E >> 31) << kMetaP) | ((O >> 31) << kMetaL);
+    };
+    if (narrow) {
+      // max(min(k - thr + 1, 1), 0) on both halves of a word in ONE instruction (VIADDMNMX.S16x2.RELU) is the pair of
+      // "above the mean" bits; a shift-add drops them into an even-sample and an odd-sample bit plane.  Whole-group
+      // frames keep only the per-group record; ragged-edge frames keep the planes themselves (bit-string helpers above).
       const uint32_t t2 = ((uint32_t)(1 - thr) & 0xffffu) * 0x00010001u;
 #pragma unroll 1
       for (int c = swid; c < nchunks; c += kStreamWarps) {
@@ -1219,9 +1250,17 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
           // planes in processing order -> undo the rotation: bit a of E / O is sample 2a / 2a+1 of the group
           const uint32_t ep = __byte_perm(acc0, acc1, 0x5410), op = __byte_perm(acc0, acc1, 0x7632);
           const uint32_t E = __funnelshift_l(ep, ep, 4 * rot), O = __funnelshift_l(op, op, 4 * rot);
-          const uint32_t x1 = E ^ O, x2 = (O ^ (E >> 1)) & 0x7fffffffu;
-          // group record: crossings inside the group | samples 0,2,4,6,8 | samples 1,3,5,7 | sample 62 | sample 63
-          s_meta[g] = (uint32_t)(__popc(x1) + __popc(x2)) | ((E & 0x1fu) << kMetaE) | ((O & 0xfu) << kMetaO) | ((E >> 31) << kMetaP) | ((O >> 31) << kMetaL);
+          if (!edges) s_meta[g] = group_meta(E, O);
+          else { s_bits[2 * g] = E; s_bits[2 * g + 1] = O; }
+        } else if (edges && g * kGroup < np) {
+          // partial last group, one sample at a time
+          uint32_t E = 0, O = 0;
+#pragma unroll 1
+          for (int i = 0; i < kGroup && g * kGroup + i < np; ++i) {
+            const uint32_t bit = (at_pos(g * kGroup + i) - thr >= 0);
+            if (i & 1) O |= bit << (i >> 1); else E |= bit << (i >> 1);
+          }
+          s_bits[2 * g] = E; s_bits[2 * g + 1] = O;
         } else if (sh && g * kGroup < np) {
           // partial last group of a shifted stream: the last whole frame may end inside its head -- first 9 bits only
           uint32_t m = 0;
@@ -1229,72 +1268,29 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
             if (at_pos(g * kGroup + i) - thr >= 0) m |= 1u << ((i & 1) ? kMetaO + (i >> 1) : kMetaE + (i >> 1));
           s_meta[g] = m;
         }
-        // this chunk's last read: hand the slot back now, not after the warp's other chunks (the producer refills
-        // the ring in order, and the next utterance's last chunks are the ones pass A ends up waiting for)
+        // whole-group frames: this was the chunk's last read -- hand the slot back now, not after the warp's other chunks
+        // (the producer refills the ring in order, and the next utterance's last chunks are the ones pass A ends up
+        // waiting for); ragged-edge frames read their edges from the ring in pass F and release there
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_empty[s]);
+        if (!edges && lane == 0) mbar_arrive(&bar_empty[s]);
       }
+      if (edges && stid < 4) s_bits[2 * ng + stid] = 0;
     } else {
+    // wide range (a full-scale signal on a large DC offset: k - thr does not fit 16 bits): one subtraction per sample
 #pragma unroll 1
     for (int c = swid; c < nchunks; c += kStreamWarps) {
       int s = cslot + c; if (s >= R) s -= R;
       const int g = kGroupsPerChunk * c + lane;
       const int base = g * kGroup;
-      uint32_t b0 = 0, b1 = 0;
-      if (base + kGroup <= np) {
-        const unsigned char* gp = s_ring + (size_t)s * kChunkBytes + lane * (2 * kGroup);
-        const int rot = lane & 7;
-        uint32_t nlo = 0, nhi = 0;         // "below the mean" bits, MSB-first, in processing order
-        if (narrow) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int4 qa = *reinterpret_cast<const int4*>(gp + 16 * ((j + rot) & 7));
-            const int4 qb = *reinterpret_cast<const int4*>(gp + 16 * ((j + 4 + rot) & 7));
-            const uint32_t wa[4] = {(uint32_t)qa.x, (uint32_t)qa.y, (uint32_t)qa.z, (uint32_t)qa.w};
-            const uint32_t wb[4] = {(uint32_t)qb.x, (uint32_t)qb.y, (uint32_t)qb.z, (uint32_t)qb.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              nhi = __funnelshift_l(wa[k] * 65536u - thr16, nhi, 1); nhi = __funnelshift_l(wa[k] - thr16, nhi, 1);
-              nlo = __funnelshift_l(wb[k] * 65536u - thr16, nlo, 1); nlo = __funnelshift_l(wb[k] - thr16, nlo, 1);
-            }
-          }
-        } else {
-#pragma unroll 1
-          for (int j = 0; j < 4; ++j) {
-            const int4 qa = *reinterpret_cast<const int4*>(gp + 16 * ((j + rot) & 7));
-            const int4 qb = *reinterpret_cast<const int4*>(gp + 16 * ((j + 4 + rot) & 7));
-            const uint32_t wa[4] = {(uint32_t)qa.x, (uint32_t)qa.y, (uint32_t)qa.z, (uint32_t)qa.w};
-            const uint32_t wb[4] = {(uint32_t)qb.x, (uint32_t)qb.y, (uint32_t)qb.z, (uint32_t)qb.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int alo = sext16(wa[k]) - thr, ahi = ((int)wa[k] >> 16) - thr;
-              const int blo = sext16(wb[k]) - thr, bhi = ((int)wb[k] >> 16) - thr;
-              nhi = __funnelshift_l((uint32_t)alo, nhi, 1); nhi = __funnelshift_l((uint32_t)ahi, nhi, 1);
-              nlo = __funnelshift_l((uint32_t)blo, nlo, 1); nlo = __funnelshift_l((uint32_t)bhi, nlo, 1);
-            }
-          }
-        }
-        // stream (nhi:nlo) holds vector `rot` first (at the top); reverse to LSB-first, undo the rotation
-        const unsigned long long y = ((unsigned long long)__brev(nlo) << 32) | (unsigned long long)__brev(nhi);
-        const int sh = 8 * rot;
-        const unsigned long long z = sh ? ((y << sh) | (y >> (64 - sh))) : y;
-        b0 = ~(uint32_t)z; b1 = ~(uint32_t)(z >> 32);
-      } else if (base < np) {
+      uint32_t E = 0, O = 0;
+      if (base < np) {
 #pragma unroll 1
         for (int i = 0; i < kGroup && base + i < np; ++i) {
           const uint32_t bit = (at_pos(base + i) - thr >= 0);
-          if (i < 32) b0 |= bit << i; else b1 |= bit << (i - 32);
+          if (i & 1) O |= bit << (i >> 1); else E |= bit << (i >> 1);
         }
-      }
-      if (base < np) {
-        s_bits[2 * g] = b0; s_bits[2 * g + 1] = b1;
-        if (!edges) {      // whole-group frames read the group records (same layout as the fast form writes)
-          const uint32_t x0 = b0 ^ __funnelshift_r(b0, b1, 1), x1 = (b1 ^ (b1 >> 1)) & 0x7fffffffu;
-          uint32_t m = (uint32_t)(__popc(x0) + __popc(x1)) | (((b1 >> 30) & 1u) << kMetaP) | ((b1 >> 31) << kMetaL);
-#pragma unroll
-          for (int i = 0; i < 9; ++i) m |= ((b0 >> i) & 1u) << ((i & 1) ? kMetaO + (i >> 1) : kMetaE + (i >> 1));
-          s_meta[g] = m;
-        }
+        s_bits[2 * g] = E; s_bits[2 * g + 1] = O;
+        if (!edges) s_meta[g] = group_meta(E, O);      // whole-group frames read the group records
       }
     }
     if (stid < 4) s_bits[2 * ng + stid] = 0;
@@ -1397,7 +1393,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
             const int ps = p + sh, qs = ps + fl;
             const int ga = ps / kGroup, gb = qs / kGroup;
             const int gspan = gb - ga;
-#pragma unroll 1
+#pragma unroll 4
             for (int g = ga + ((gspan * sub) >> lshift); g < ga + ((gspan * (sub + 1)) >> lshift); ++g) {
               const unsigned long long pk = gsum[g];
               k2 += (long long)(pk >> 24);
