@@ -58,7 +58,6 @@ if "ragged" not in LAYOUTS:
     sys.exit(0)
 rng = np.random.default_rng(99)
 lo_s, hi_s = (float(v) for v in os.environ.get("QUICK_RAGGED", "0.8,1.2").split(","))
-lens = (rng.uniform(lo_s, hi_s, int(n * 1.3)) * 44100).astype(np.int64)
-r_off = np.concatenate([[0], np.cumsum(lens)])
-r_off = r_off[: int(np.searchsorted(r_off, n * L, side="right"))]
+lens = (rng.uniform(lo_s, hi_s, n) * 44100).astype(np.int64)
+samples, r_off = bench.synth_batch_device(n, dev, seed=8, lengths=lens)       # every utterance generated at its own length
 timed(f"ragged U({lo_s},{hi_s}) s packed CSR (any alignment)", r_off)
