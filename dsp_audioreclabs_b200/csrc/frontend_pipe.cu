@@ -1164,13 +1164,55 @@ __global__ void __launch_bounds__(kPipeThreads, 1) frontend_pipe_kernel(const Pc
         S += s1;
         gsum[g] = ((unsigned long long)s2 << 24) | (unsigned long long)((uint32_t)s1 & 0xffffffu);
       } else if (base < np) {
-        // the partial last group, one sample at a time (valid stream positions only)
-        int s1 = 0, h1s = 0; long long s2 = 0, h2s = 0;
+        // The partial last group (r = 1..63 valid samples): whole vectors like a full group, the ragged vector masked
+        // for the sums and filled with copies of the group's first sample for min / max.  (One sample at a time this
+        // lane walked up to 63 dependent shared-memory loads while seven warps waited at the barrier: the barrier's share
+        // of pass A on ragged batches was 47 %.)
+        const unsigned char* gp = s_ring + (size_t)s * kChunkBytes + lane * (2 * kGroup);
+        const int r = np - base;
+        const uint32_t kf2 = ((uint32_t)(unsigned short)reinterpret_cast<const int16_t*>(gp)[0]) * 0x00010001u;
+        // word w of a vector keeps its samples below cnt (cnt = valid samples of that vector, 0..8)
+        auto wmask = [](int w, int cnt) { return (2 * w + 1 < cnt) ? 0xffffffffu : ((2 * w < cnt) ? 0x0000ffffu : 0u); };
+        int hh = 0, hl = 0, sumh = 0;
+        uint32_t ll = 0, sl = 0;
+        int h_hh = 0, h_hl = 0, h_sumh = 0;
+        uint32_t h_ll = 0, h_sl = 0;
 #pragma unroll 1
-        for (int i = base; i < np; ++i) {
-          const int k = at_pos(i); s1 += k; s2 += (long long)k * k; mn = min(mn, k); mx = max(mx, k);
-          if (i < base + sh) { h1s += k; h2s += (long long)k * k; }
+        for (int v = 0; 8 * v < r; ++v) {
+          int4 q = *reinterpret_cast<const int4*>(gp + 16 * v);
+          const int cnt = min(8, r - 8 * v);
+          uint32_t xw[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const uint32_t mk = wmask(w, cnt);
+            const uint32_t mmw = (xw[w] & mk) | (kf2 & ~mk);           // min / max: invalid halves repeat a valid sample
+            mn2 = __vimin3_s16x2(mn2, mmw, mmw); mx2 = __vimax3_s16x2(mx2, mmw, mmw);
+            xw[w] &= mk;                                               // sums: invalid halves are zero
+          }
+          const uint32_t h0 = __byte_perm(xw[0], xw[1], 0x7531), l0 = __byte_perm(xw[0], xw[1], 0x6420);
+          const uint32_t h1 = __byte_perm(xw[2], xw[3], 0x7531), l1 = __byte_perm(xw[2], xw[3], 0x6420);
+          hh = dp4a_ss((int)h0, (int)h0, hh); hh = dp4a_ss((int)h1, (int)h1, hh);
+          hl = dp4a_su((int)h0, l0, hl);      hl = dp4a_su((int)h1, l1, hl);
+          ll = dp4a_uu(l0, l0, ll);           ll = dp4a_uu(l1, l1, ll);
+          sumh = dp4a_ss((int)h0, 0x01010101, sumh); sumh = dp4a_ss((int)h1, 0x01010101, sumh);
+          sl = dp4a_uu(l0, 0x01010101u, sl);  sl = dp4a_uu(l1, 0x01010101u, sl);
+          if (v == 0 && sh) {
+            // head of the group: its first min(sh, r) samples (all inside this vector)
+            const int hc = min(sh, r);
+            const uint32_t y0 = xw[0] & wmask(0, hc), y1 = xw[1] & wmask(1, hc), y2 = xw[2] & wmask(2, hc), y3 = xw[3] & wmask(3, hc);
+            const uint32_t g0 = __byte_perm(y0, y1, 0x7531), m0 = __byte_perm(y0, y1, 0x6420);
+            const uint32_t g1 = __byte_perm(y2, y3, 0x7531), m1 = __byte_perm(y2, y3, 0x6420);
+            h_hh = dp4a_ss((int)g1, (int)g1, dp4a_ss((int)g0, (int)g0, 0));
+            h_hl = dp4a_su((int)g1, m1, dp4a_su((int)g0, m0, 0));
+            h_ll = dp4a_uu(m1, m1, dp4a_uu(m0, m0, 0u));
+            h_sumh = dp4a_ss((int)g1, 0x01010101, dp4a_ss((int)g0, 0x01010101, 0));
+            h_sl = dp4a_uu(m1, 0x01010101u, dp4a_uu(m0, 0x01010101u, 0u));
+          }
         }
+        const int s1 = 256 * sumh + (int)sl;
+        const long long s2 = (long long)hh * 65536 + (long long)hl * 512 + (long long)ll;
+        const int h1s = 256 * h_sumh + (int)h_sl;
+        const long long h2s = (long long)h_hh * 65536 + (long long)h_hl * 512 + (long long)h_ll;
         S += s1;
         gsum[g] = ((unsigned long long)s2 << 24) | (unsigned long long)((uint32_t)s1 & 0xffffffu);
         head[g] = ((unsigned long long)h2s << 24) | (unsigned long long)((uint32_t)h1s & 0xffffffu);
